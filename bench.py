@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""Headline benchmark: DREAM chain-steps/s on the 100-D correlated Gaussian.
+
+  python bench.py --gpus N --steps K --warmup W            (this framework, N GPUs)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (CPU port of the reference)
+
+A "step" is one DREAM generation of the whole population (every chain proposes, evaluates
+its likelihood and is accepted / rejected once).  Workload = BASELINE.json configs[1]:
+DREAM (del_pairs=3, n_cr=3, n_cr_gen=50, burnin_gen=2000) on Gauss_100D(rho=0.5) with 10^5
+chains per GPU (weak scaling), Philox seed 42, chains started over-dispersed
+(N(0, diag Sigma)) and advanced 60 untimed generations first so the timed region is the
+burn-in steady state with crossover adaptation, running moments and full history ON.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_PER_GPU = 100000
+DIM = 100
+SETUP_GENS = 60
+METRIC = "DREAM chain-steps/s, 100-D Gaussian"
+UNIT = "chain-steps/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_spec(n_chains):
+    return dict(target="gauss100", theta_0=list(np.zeros(DIM)), n_chains=n_chains, algo="dream",
+                seed=42, varepsilon=1e-6, ctor_kwargs=dict(n_cr_gen=50, burnin_gen=2000))
+
+
+def run_reference(args):
+    """The reference's algorithm on the host cores (oracle/mp_port.py: the oracle port of
+    DreamMpi with the mpi4py collectives replaced by shared memory)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.mp_port import time_port
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    n_chains = 40 * procs
+    # a step = one generation of the sample population; warm-up generations are untimed
+    dt, steps = time_port(cpu_port_spec(n_chains), procs, gens=args.steps, gens_warm=max(args.warmup, 1))
+    v = steps / dt
+    sample = "DREAM 100-D Gaussian, %d chains (40 per process), %d timed generations" % (n_chains, args.steps)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "gpu_launches": 0,
+            "config": {"workload": "configs[1]: DREAM, Gauss_100D(rho=0.5), CPU sample of %d chains" % n_chains,
+                       "del_pairs": 3, "n_cr": 3, "n_cr_gen": 50, "burnin_gen": 2000},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def cpu_baseline_leg():
+    from oracle.mp_port import time_port
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    n_chains = 40 * procs
+    gens = 25
+    dt, steps = time_port(cpu_port_spec(n_chains), procs, gens=gens, gens_warm=2)
+    return {"value": steps / dt, "unit": UNIT, "cores": procs, "kind": "port",
+            "sample": "oracle port of DreamMpi (shared-memory ranks), 100-D Gaussian, %d chains, "
+                      "%d generations, %.1f s" % (n_chains, gens, dt)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from bipymc_b200 import DreamMpi, targets, _lib
+    N = N_PER_GPU * world
+    tgt = targets.Gauss_100D(rho=0.5, dim=DIM)
+    np.random.seed(42)
+    K, W = args.steps, args.warmup
+    s = DreamMpi(tgt.ln_like, np.zeros(DIM), n_chains=N, varepsilon=np.arange(DIM) + 1.0, seed=42,
+                 n_cr_gen=50, burnin_gen=2000, device=local_rank,
+                 history=args.history, history_chunk_bytes=(K + W + SETUP_GENS + 4) * (N // world) * DIM * 8)
+    lib, h = s._libh, s._handle
+    n_local = len(s.rank_chain_ids)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    k_done = 0
+
+    def gens(n):
+        nonlocal k_done
+        s.run_mcmc(N * (n + 1), _k_gen0=k_done)
+        k_done += n
+
+    gens(SETUP_GENS)
+    gens(W)
+    sync_all()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    _lib.check(lib.bpm_profile(h, 1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    gens(K)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    ck = clocks.stop()
+    ms_kind = (C.c_double * 8)()
+    n_kind = (C.c_int64 * 8)()
+    _lib.check(lib.bpm_profile_read(h, ms_kind, n_kind))
+    _lib.check(lib.bpm_profile(h, 0))
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = N * K / (ms * 1e-3)
+    acc_frac = s.acceptance_fraction
+
+    # ---- roofline of the dominant kernel (per GPU) -------------------------------------
+    kinds = ["split", "propose", "likelihood", "accept", "fused_phase", "cr_reduce"]
+    ms_k = [ms_kind[i] for i in range(6)]
+    n_k = [int(n_kind[i]) for i in range(6)]
+    dom = int(np.argmax(ms_k))
+    d = DIM
+    hist_b = 8 * d if args.history == "full" else 0
+    # algorithmic bytes per chain-step: own row + 6 partner rows + write + lnL r/w,
+    # + running moments r/w (mean, M2) during burn-in adaptation, + history append
+    step_bytes = 64 * d + 16 + 32 * d + hist_b
+    per_kind_bytes = {"fused_phase": step_bytes,
+                      "propose": 8 * d * (1 + 6 + 1 + 1),          # own + partners + M2 read + proposal write
+                      "likelihood": 8 * d + 8,                      # proposal read + lnL write
+                      "accept": 8 * d * (1 + 1 + 4) + hist_b + 16}  # proposal read, state write, moments r/w
+    hbm, peak_src = peaks()
+    roof = None
+    if n_k[dom] > 0 and kinds[dom] in per_kind_bytes:
+        chains_per_launch = n_local / 2.0
+        avg_ms = ms_k[dom] / n_k[dom]
+        ach = per_kind_bytes[kinds[dom]] * chains_per_launch / (avg_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": kinds[dom], "achieved": ach, "peak": hbm, "unit": "GB/s",
+                "frac": ach / hbm, "traffic": None, "avg_launch_ms": avg_ms,
+                "bytes_per_chain_step": per_kind_bytes[kinds[dom]], "peak_source": peak_src,
+                "share_of_step": ms_k[dom] / max(sum(ms_k), 1e-12)}
+        if kinds[dom] == "likelihood":
+            fl = 2.0 * d * d * chains_per_launch / (avg_ms * 1e-3) / 1e12
+            roof.update({"fp64_tflops": fl})
+    launches = sum(n_k) + n_k[5]          # cr_reduce records cover 2 kernels (reduce + apply)
+
+    # ---- end to end through the C-ABI with HOST buffers (rank-local population) --------
+    e2e = None
+    if world == 1:
+        Xh = torch.empty((N, s._ld), dtype=torch.float64).pin_memory()
+        Lh = torch.empty((N,), dtype=torch.float64).pin_memory()
+        Xh.copy_(s._X.cpu()); Lh.copy_(s._lnl.cpu())
+        ke = max(3, min(K, 20))
+        g0 = s._hist.length
+        for i in range(2):
+            _lib.check(lib.bpm_generations_host(h, Xh.data_ptr(), Lh.data_ptr(), k_done + i, g0 + i, 1))
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for i in range(ke):
+            _lib.check(lib.bpm_generations_host(h, Xh.data_ptr(), Lh.data_ptr(), k_done + 2 + i, g0 + 2 + i, 1))
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        nb = N * s._ld * 8 + N * 8
+        e2e = {"value": N * ke / dt, "unit": UNIT, "h2d_bytes_per_step": nb, "d2h_bytes_per_step": nb,
+               "steps": ke, "ms_per_step": 1e3 * dt / ke,
+               "note": "bpm_generations_host: pinned host population -> H2D -> one generation -> D2H, every step"}
+
+    cpu = cpu_baseline_leg() if (rank == 0 and world == 1 and not args.no_cpu) else None
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "configs[1]: DREAM on Gauss_100D(rho=0.5), %d chains per GPU" % N_PER_GPU,
+                           "n_chains": N, "dim": DIM, "del_pairs": 3, "n_cr": 3, "n_cr_gen": 50,
+                           "burnin_gen": 2000, "history": args.history, "cr_adaptation": "on",
+                           "init": "theta_0 + N(0, diag(Sigma)), %d untimed setup generations" % SETUP_GENS,
+                           "rng": "philox4x32-10 seed 42", "parallelism": "chains sharded x%d" % world,
+                           "l2": "working set per generation (state 80 MB + moments 160 MB + history "
+                                 "row 80 MB per GPU) exceeds the 126 MB L2; no explicit flush"},
+                "acceptance_fraction": acc_frac, "gpu_launches": launches,
+                "kernel_ms": dict(zip(kinds, ms_k)), "kernel_launches": dict(zip(kinds, n_k)),
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": ck}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--history", default="full", choices=["full", "none"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,688 @@
+// Host side of the C-ABI (include/bipymc_b200.h): owns the per-handle workspace,
+// turns a generation of DeMcMpi._mcmc_run (bipymc/demc.py:79-135) into kernel launches
+// on the caller's stream, and never touches the CPU for arithmetic.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/bipymc_b200.h"
+#include "kernels_generic.cuh"
+#include "kernels_fused.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& m) {
+  g_err = m;
+  return 1;
+}
+
+#define CU_TRY(expr)                                                                       \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      return fail(std::string(#expr) + ": " + cudaGetErrorString(e__));                    \
+  } while (0)
+
+#define BPM_TRY(expr)      \
+  do {                     \
+    int r__ = (expr);      \
+    if (r__) return r__;   \
+  } while (0)
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+inline int pick_lpc(int d) {
+  if (d <= 4) return 1;
+  if (d <= 16) return 4;
+  if (d <= 32) return 8;
+  return 32;
+}
+
+}  // namespace
+
+struct bpm_engine {
+  bpm_config cfg;
+  int nA;  // ceil(N / 2): np.array_split gives the first half the extra element
+  // workspace (device)
+  int32_t* perm = nullptr;
+  int32_t* flip = nullptr;
+  double* prop = nullptr;
+  double* lnl_prop = nullptr;
+  double* cr_delta = nullptr;
+  int32_t* cr_pick = nullptr;
+  double* p_cr = nullptr;
+  double* cr_dm = nullptr;
+  double* cr_cnt = nullptr;
+  double* cr_part = nullptr;
+  unsigned long long* counters = nullptr;  // [0] accepted, [1] rejected
+  int32_t* nan_flag = nullptr;
+  // target
+  int target = BPM_TARGET_EXTERNAL;
+  bpm::BananaParams banana;
+  bpm::BimodalParams bimodal;
+  double* tparams = nullptr;  // device copy of gauss / linefit parameters
+  int64_t n_tparams = 0;
+  int gauss_r = 0, gauss_logpdf_flag = 0;
+  double gauss_c0 = 0.0;
+  int linefit_M = 0;
+  bpm_lnl_fn user_fn = nullptr;
+  void* user_ptr = nullptr;
+  // split-path generation context
+  bpm::PhaseArgs cur;
+  bool cur_replay = false;
+  bool in_generation = false;
+  int64_t cur_k_gen = 0;
+  // host-entry buffers
+  double* hX = nullptr;
+  double* hL = nullptr;
+  int fused_ok = 1;  // allow the fused fast paths
+  // optional per-kernel timing (bpm_profile): CUDA events around every launch, by kind
+  struct Rec { int kind; cudaEvent_t a, b; };
+  bool prof_on = false;
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> ev_pool;
+  cudaEvent_t get_event() {
+    if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void prof_begin(int kind, cudaStream_t s) {
+    if (!prof_on) return;
+    Rec r; r.kind = kind; r.a = get_event(); r.b = get_event();
+    cudaEventRecord(r.a, s);
+    recs.push_back(r);
+  }
+  void prof_end(cudaStream_t s) {
+    if (!prof_on) return;
+    cudaEventRecord(recs.back().b, s);
+  }
+
+  ~bpm_engine() {
+    cudaFree(perm); cudaFree(flip); cudaFree(prop); cudaFree(lnl_prop); cudaFree(cr_delta);
+    cudaFree(cr_pick); cudaFree(p_cr); cudaFree(cr_dm); cudaFree(cr_cnt); cudaFree(cr_part);
+    cudaFree(counters); cudaFree(nan_flag); cudaFree(tparams); cudaFree(hX); cudaFree(hL);
+    for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : ev_pool) cudaEventDestroy(e);
+  }
+
+  int init() {
+    const int N = cfg.n_chains;
+    nA = (N + 1) / 2;
+    CU_TRY(cudaSetDevice(cfg.device));
+    CU_TRY(cudaMalloc(&perm, sizeof(int32_t) * N));
+    CU_TRY(cudaMalloc(&flip, sizeof(int32_t)));
+    CU_TRY(cudaMalloc(&prop, sizeof(double) * (size_t)nA * cfg.ld));
+    CU_TRY(cudaMalloc(&lnl_prop, sizeof(double) * nA));
+    CU_TRY(cudaMalloc(&cr_delta, sizeof(double) * N));
+    CU_TRY(cudaMalloc(&cr_pick, sizeof(int32_t) * N));
+    CU_TRY(cudaMalloc(&p_cr, sizeof(double) * BPM_MAX_CR));
+    CU_TRY(cudaMalloc(&cr_dm, sizeof(double) * BPM_MAX_CR));
+    CU_TRY(cudaMalloc(&cr_cnt, sizeof(double) * BPM_MAX_CR));
+    CU_TRY(cudaMalloc(&cr_part, sizeof(double) * 2 * BPM_MAX_CR));
+    CU_TRY(cudaMalloc(&counters, sizeof(unsigned long long) * 2));
+    CU_TRY(cudaMalloc(&nan_flag, sizeof(int32_t)));
+    CU_TRY(cudaMemset(flip, 0, sizeof(int32_t)));
+    CU_TRY(cudaMemset(cr_pick, 0xFF, sizeof(int32_t) * N));
+    CU_TRY(cudaMemset(cr_delta, 0, sizeof(double) * N));
+    CU_TRY(cudaMemset(counters, 0, sizeof(unsigned long long) * 2));
+    CU_TRY(cudaMemset(nan_flag, 0, sizeof(int32_t)));
+    CU_TRY(cudaMemset(cr_dm, 0, sizeof(double) * BPM_MAX_CR));
+    CU_TRY(cudaMemset(cr_cnt, 0, sizeof(double) * BPM_MAX_CR));
+    std::vector<double> p(BPM_MAX_CR, 0.0);
+    for (int m = 0; m < cfg.n_cr; ++m) p[m] = 1.0 / cfg.n_cr;  // dream.py:114
+    CU_TRY(cudaMemcpy(p_cr, p.data(), sizeof(double) * BPM_MAX_CR, cudaMemcpyHostToDevice));
+    return 0;
+  }
+
+  // Parameter block of one half-phase of generation k_gen.
+  bpm::PhaseArgs make_args(const bpm_state* st, int64_t k_gen, int phase, const bpm_replay* rp,
+                           const bpm_trace_out* tr) const {
+    bpm::PhaseArgs a;
+    memset(&a, 0, sizeof(a));
+    a.X = st->X; a.lnl = st->lnl; a.mean = st->mean; a.m2 = st->m2;
+    a.hist_row = st->history ? st->history + (size_t)st->hist_len * (cfg.chain_hi - cfg.chain_lo) * cfg.ld
+                             : nullptr;
+    a.perm = perm; a.flip = flip; a.phase = phase;
+    a.N = cfg.n_chains; a.nA = nA; a.d = cfg.dim; a.ld = cfg.ld;
+    a.chain_lo = cfg.chain_lo; a.chain_hi = cfg.chain_hi;
+    a.algo = cfg.algo;
+    a.del_pairs = cfg.algo == BPM_ALGO_DREAM ? cfg.del_pairs : 1;
+    a.n_cr = cfg.n_cr;
+    if (cfg.algo == BPM_ALGO_DREAM) {
+      a.gamma_jump = (k_gen % 5) == 0;   // dream.py:77
+      a.gamma_p0 = 0.20;
+    } else {
+      a.gamma_jump = (k_gen % 10) == 0;  // demc.py:174
+      a.gamma_p0 = 0.1;
+    }
+    a.gamma_fixed = cfg.gamma > 0.0 ? cfg.gamma : 2.38 / sqrt(2.0 * cfg.dim);   // demc.py:162
+    a.gamma_num = cfg.gamma_scale * 2.38;                                        // dream.py:61
+    a.eps = cfg.epsilon > 0.0 ? sqrt(cfg.epsilon * cfg.epsilon) : 0.0;           // util.py:11-14
+    a.u_eps = cfg.u_epsilon > 0.0 ? cfg.u_epsilon : 0.0;
+    a.adapt = cfg.algo == BPM_ALGO_DREAM && cfg.burnin_gen > k_gen && st->hist_len > cfg.n_cr_gen &&
+              st->m2 != nullptr;                                                 // dream.py:92,124
+    a.hist_len = st->hist_len;
+    a.p_cr = p_cr; a.cr_delta = cr_delta; a.cr_pick = cr_pick;
+    a.prop = prop; a.lnl_prop = lnl_prop;
+    a.n_acc = counters; a.n_rej = counters + 1; a.nan_flag = nan_flag;
+    a.rng = bpm::make_rng(cfg.seed, (uint64_t)st->hist_len);
+    if (rp) a.rp = *rp;
+    if (tr) a.tr = *tr;
+    return a;
+  }
+
+  int begin(const bpm_state* st, const bpm_replay* rp, cudaStream_t s) {
+    const int N = cfg.n_chains;
+    prof_begin(0, s);
+    if (rp) {
+      CU_TRY(cudaMemcpyAsync(perm, rp->shuffle_idx, sizeof(int32_t) * N, cudaMemcpyDeviceToDevice, s));
+      bpm::set_flag_kernel<<<1, 1, 0, s>>>(flip, rp->flip ? 1 : 0);
+    } else {
+      bpm::RngCtx rng = bpm::make_rng(cfg.seed, (uint64_t)st->hist_len);
+      bpm::split_native_kernel<<<cdiv(N, 256), 256, 0, s>>>(perm, flip, N, cfg.shuffle, cfg.flip, rng);
+    }
+    prof_end(s);
+    CU_TRY(cudaGetLastError());
+    return 0;
+  }
+
+  template <bool REPLAY>
+  int launch_propose(const bpm::PhaseArgs& a, cudaStream_t s) {
+    const int lpc = pick_lpc(cfg.dim);
+    const int grid = cdiv((int64_t)nA * lpc, bpm::kThreads);
+    switch (lpc) {
+      case 1: bpm::propose_kernel<REPLAY, 1><<<grid, bpm::kThreads, 0, s>>>(a); break;
+      case 4: bpm::propose_kernel<REPLAY, 4><<<grid, bpm::kThreads, 0, s>>>(a); break;
+      case 8: bpm::propose_kernel<REPLAY, 8><<<grid, bpm::kThreads, 0, s>>>(a); break;
+      default: bpm::propose_kernel<REPLAY, 32><<<grid, bpm::kThreads, 0, s>>>(a); break;
+    }
+    CU_TRY(cudaGetLastError());
+    return 0;
+  }
+  template <bool REPLAY>
+  int launch_accept(const bpm::PhaseArgs& a, cudaStream_t s) {
+    const int lpc = pick_lpc(cfg.dim);
+    const int grid = cdiv((int64_t)nA * lpc, bpm::kThreads);
+    switch (lpc) {
+      case 1: bpm::accept_kernel<REPLAY, 1><<<grid, bpm::kThreads, 0, s>>>(a); break;
+      case 4: bpm::accept_kernel<REPLAY, 4><<<grid, bpm::kThreads, 0, s>>>(a); break;
+      case 8: bpm::accept_kernel<REPLAY, 8><<<grid, bpm::kThreads, 0, s>>>(a); break;
+      default: bpm::accept_kernel<REPLAY, 32><<<grid, bpm::kThreads, 0, s>>>(a); break;
+    }
+    CU_TRY(cudaGetLastError());
+    return 0;
+  }
+
+  int eval_lnl(const double* P, int n, int ld, double* out, cudaStream_t s) {
+    if (n <= 0) return 0;
+    switch (target) {
+      case BPM_TARGET_BANANA:
+        if (cfg.dim != 2) return fail("banana target needs dim == 2");
+        bpm::lnl_banana_kernel<<<cdiv(n, 256), 256, 0, s>>>(P, n, ld, banana, out);
+        break;
+      case BPM_TARGET_BIMODAL:
+        if (cfg.dim != 2) return fail("bimodal target needs dim == 2");
+        bpm::lnl_bimodal_kernel<<<cdiv(n, 256), 256, 0, s>>>(P, n, ld, bimodal, out);
+        break;
+      case BPM_TARGET_GAUSS: {
+        const double* mu = tparams;
+        const double* W = tparams + cfg.dim;
+        if (fused_ok && bpm::gauss_rows_supported(cfg.dim, gauss_r))
+          BPM_TRY(bpm::launch_gauss_rows(P, n, ld, cfg.dim, gauss_r, mu, W, gauss_c0,
+                                         gauss_logpdf_flag, out, s));
+        else
+          bpm::lnl_gauss_tiled_kernel<<<cdiv(n, 64), 256, 0, s>>>(P, n, ld, cfg.dim, gauss_r, mu, W,
+                                                                  gauss_c0, gauss_logpdf_flag, out);
+        break;
+      }
+      case BPM_TARGET_LINEFIT:
+        if (cfg.dim != 3) return fail("linefit target needs dim == 3");
+        bpm::lnl_linefit_kernel<<<cdiv(n, 128), 128, sizeof(double) * 3 * linefit_M, s>>>(
+            P, n, ld, tparams, linefit_M, out);
+        break;
+      default:
+        if (!user_fn) return fail("no likelihood: set a built-in target or a batched callback, or "
+                                  "drive the split bpm_propose / bpm_accept API");
+        if (user_fn(P, n, cfg.dim, ld, out, user_ptr, (bpm_stream)s))
+          return fail("batched ln_like callback returned non-zero");
+    }
+    {
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return fail(std::string("likelihood launch: ") + cudaGetErrorString(e));
+    }
+    return 0;
+  }
+
+  int end(cudaStream_t s) {
+    if (cfg.algo != BPM_ALGO_DREAM) return 0;
+    prof_begin(5, s);
+    bpm::cr_reduce_kernel<<<1, 1024, 0, s>>>(cr_delta, cr_pick, cfg.chain_lo, cfg.chain_hi, cfg.n_cr,
+                                             cr_part);
+    CU_TRY(cudaGetLastError());
+    const bool sharded = cfg.chain_lo != 0 || cfg.chain_hi != cfg.n_chains;
+    if (!sharded) {  // multi-rank hosts all-reduce cr_part first, then call bpm_apply_cr
+      bpm::cr_apply_kernel<<<1, 32, 0, s>>>(cr_part, cfg.n_cr, cr_dm, cr_cnt, p_cr);
+      CU_TRY(cudaGetLastError());
+    }
+    prof_end(s);
+    return 0;
+  }
+
+  template <bool REPLAY>
+  int phase(const bpm_state* st, int64_t k_gen, int ph, const bpm_replay* rp, const bpm_trace_out* tr,
+            cudaStream_t s) {
+    bpm::PhaseArgs a = make_args(st, k_gen, ph, rp, tr);
+    if (fused_ok && !a.tr.prop) {
+      int done = 0;
+      prof_begin(4, s);
+      BPM_TRY(bpm::try_fused_phase<REPLAY>(*this_target(), a, s, &done));
+      if (done) { prof_end(s); return 0; }
+      if (prof_on) { ev_pool.push_back(recs.back().a); ev_pool.push_back(recs.back().b); recs.pop_back(); }
+    }
+    prof_begin(1, s);
+    BPM_TRY(launch_propose<REPLAY>(a, s));
+    prof_end(s);
+    prof_begin(2, s);
+    BPM_TRY(eval_lnl(prop, nA, cfg.ld, lnl_prop, s));
+    prof_end(s);
+    prof_begin(3, s);
+    BPM_TRY(launch_accept<REPLAY>(a, s));
+    prof_end(s);
+    return 0;
+  }
+
+  // View of the target parameters the fused kernels need.
+  bpm::TargetView tv;
+  const bpm::TargetView* this_target() {
+    tv.target = target;
+    tv.banana = banana;
+    tv.bimodal = bimodal;
+    tv.mu = tparams;
+    tv.W = tparams ? tparams + cfg.dim : nullptr;
+    tv.r = gauss_r;
+    tv.c0 = gauss_c0;
+    tv.log_of_pdf = gauss_logpdf_flag;
+    tv.linefit = tparams;
+    tv.linefit_M = linefit_M;
+    return &tv;
+  }
+
+  template <bool REPLAY>
+  int generation(bpm_state* st, int64_t k_gen, const bpm_replay* rp, const bpm_trace_out* tr,
+                 cudaStream_t s) {
+    BPM_TRY(begin(st, rp, s));
+    BPM_TRY(phase<REPLAY>(st, k_gen, 0, rp, tr, s));
+    BPM_TRY(phase<REPLAY>(st, k_gen, 1, rp, tr, s));
+    BPM_TRY(end(s));
+    st->hist_len += 1;
+    return 0;
+  }
+};
+
+// ===================================================================================
+extern "C" {
+
+const char* bpm_last_error(void) { return g_err.c_str(); }
+int bpm_version(void) { return 100; }
+
+int bpm_create(const bpm_config* cfg, bpm_handle* out) {
+  if (!cfg || !out) return fail("bpm_create: null argument");
+  if (cfg->n_chains < 4) return fail("n_chains >= 4 required (samplers.py:249)");
+  if (cfg->dim < 1 || cfg->ld < cfg->dim) return fail("bad dim / ld");
+  if (cfg->dim > 4 * bpm::kMaxBlocksPerLane * 32) return fail("dim > 1024 not supported yet");
+  if (cfg->algo != BPM_ALGO_DEMC && cfg->algo != BPM_ALGO_DREAM) return fail("bad algo");
+  if (cfg->algo == BPM_ALGO_DREAM && (cfg->del_pairs < 1 || cfg->del_pairs > BPM_MAX_PAIRS))
+    return fail("del_pairs must be in [1, 8]");
+  if (cfg->n_cr < 1 || cfg->n_cr > BPM_MAX_CR) return fail("n_cr must be in [1, 16]");
+  if (cfg->chain_lo < 0 || cfg->chain_hi > cfg->n_chains || cfg->chain_lo >= cfg->chain_hi)
+    return fail("bad chain shard");
+  if (cfg->n_chains / 2 < 2) return fail("pool too small");
+  bpm_engine* e = new (std::nothrow) bpm_engine();
+  if (!e) return fail("out of host memory");
+  e->cfg = *cfg;
+  if (e->init()) {
+    delete e;
+    return 1;
+  }
+  *out = e;
+  return 0;
+}
+
+int bpm_destroy(bpm_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  delete h;
+  return 0;
+}
+
+int bpm_set_run_params(bpm_handle h, double flip, int32_t shuffle, double epsilon, double u_epsilon,
+                       double gamma) {
+  if (!h) return fail("null handle");
+  h->cfg.flip = flip < 0.0 ? 0.0 : (flip > 1.0 ? 1.0 : flip);
+  h->cfg.shuffle = shuffle;
+  h->cfg.epsilon = epsilon;
+  h->cfg.u_epsilon = u_epsilon;
+  h->cfg.gamma = gamma;
+  return 0;
+}
+
+int bpm_set_fused(bpm_handle h, int32_t on) {
+  if (!h) return fail("null handle");
+  h->fused_ok = on;
+  return 0;
+}
+
+static void fill_mvn2(bpm::Mvn2& g, const double* p) {
+  g.mu0 = p[0]; g.mu1 = p[1]; g.U00 = p[2]; g.U01 = p[3]; g.U10 = p[4]; g.U11 = p[5]; g.c0 = p[6];
+}
+
+int bpm_set_target(bpm_handle h, int32_t target, const double* params, int64_t n) {
+  if (!h) return fail("null handle");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  const int d = h->cfg.dim;
+  switch (target) {
+    case BPM_TARGET_EXTERNAL: break;
+    case BPM_TARGET_BANANA:
+      if (n != 10) return fail("banana: 10 parameters expected");
+      h->banana.log_of_pdf = params[0]; h->banana.a = params[1]; h->banana.b = params[2];
+      fill_mvn2(h->banana.g, params + 3);
+      break;
+    case BPM_TARGET_BIMODAL:
+      if (n != 17) return fail("bimodal: 17 parameters expected");
+      h->bimodal.log_of_pdf = params[0]; h->bimodal.w1 = params[1]; h->bimodal.w2 = params[2];
+      fill_mvn2(h->bimodal.g1, params + 3);
+      fill_mvn2(h->bimodal.g2, params + 10);
+      break;
+    case BPM_TARGET_GAUSS: {
+      // [log_of_pdf, c0, r, mu[d], W[d][r]]
+      if (n < 3) return fail("gauss: header missing");
+      const int r = (int)params[2];
+      if (r < 1 || n != 3 + d + (int64_t)d * r) return fail("gauss: parameter count mismatch");
+      h->gauss_logpdf_flag = params[0] != 0.0; h->gauss_c0 = params[1]; h->gauss_r = r;
+      cudaFree(h->tparams); h->tparams = nullptr;
+      CU_TRY(cudaMalloc(&h->tparams, sizeof(double) * (n - 3)));
+      CU_TRY(cudaMemcpy(h->tparams, params + 3, sizeof(double) * (n - 3), cudaMemcpyHostToDevice));
+      break;
+    }
+    case BPM_TARGET_LINEFIT: {
+      // [M, x[M], y[M], yerr[M]]
+      if (n < 1) return fail("linefit: header missing");
+      const int M = (int)params[0];
+      if (M < 1 || n != 1 + 3 * (int64_t)M || M > 2000) return fail("linefit: parameter count mismatch");
+      h->linefit_M = M;
+      cudaFree(h->tparams); h->tparams = nullptr;
+      CU_TRY(cudaMalloc(&h->tparams, sizeof(double) * 3 * M));
+      CU_TRY(cudaMemcpy(h->tparams, params + 1, sizeof(double) * 3 * M, cudaMemcpyHostToDevice));
+      break;
+    }
+    default: return fail("unknown target id");
+  }
+  h->target = target;
+  return 0;
+}
+
+int bpm_set_batched_lnl(bpm_handle h, bpm_lnl_fn fn, void* user) {
+  if (!h) return fail("null handle");
+  h->user_fn = fn;
+  h->user_ptr = user;
+  h->target = BPM_TARGET_EXTERNAL;
+  return 0;
+}
+
+int bpm_eval_lnl(bpm_handle h, const double* X, int32_t n, double* lnl, bpm_stream stream) {
+  if (!h) return fail("null handle");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  return h->eval_lnl(X, n, h->cfg.ld, lnl, (cudaStream_t)stream);
+}
+
+int bpm_set_cr_state(bpm_handle h, const double* p_cr, const double* dm, const double* cnt) {
+  if (!h) return fail("null handle");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  const size_t b = sizeof(double) * h->cfg.n_cr;
+  if (p_cr) CU_TRY(cudaMemcpy(h->p_cr, p_cr, b, cudaMemcpyHostToDevice));
+  if (dm) CU_TRY(cudaMemcpy(h->cr_dm, dm, b, cudaMemcpyHostToDevice));
+  if (cnt) CU_TRY(cudaMemcpy(h->cr_cnt, cnt, b, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int bpm_get_cr_state(bpm_handle h, double* p_cr, double* dm, double* cnt) {
+  if (!h) return fail("null handle");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  const size_t b = sizeof(double) * h->cfg.n_cr;
+  if (p_cr) CU_TRY(cudaMemcpy(p_cr, h->p_cr, b, cudaMemcpyDeviceToHost));
+  if (dm) CU_TRY(cudaMemcpy(dm, h->cr_dm, b, cudaMemcpyDeviceToHost));
+  if (cnt) CU_TRY(cudaMemcpy(cnt, h->cr_cnt, b, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// Multi-rank CR adaptation: device pointer to this rank's per-generation partial sums
+// (2 * n_cr doubles: jump statistics, then counts) for the host's all-reduce, and the
+// p_cr update from the reduced values.
+int bpm_cr_partials(bpm_handle h, double** dev_ptr) {
+  if (!h || !dev_ptr) return fail("null argument");
+  *dev_ptr = h->cr_part;
+  return 0;
+}
+int bpm_apply_cr(bpm_handle h, bpm_stream stream) {
+  if (!h) return fail("null handle");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  bpm::cr_apply_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->cr_part, h->cfg.n_cr, h->cr_dm,
+                                                          h->cr_cnt, h->p_cr);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+int bpm_get_counters(bpm_handle h, uint64_t* acc, uint64_t* rej, int32_t* nan_alpha) {
+  if (!h) return fail("null handle");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  unsigned long long c[2];
+  int32_t f;
+  CU_TRY(cudaMemcpy(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(&f, h->nan_flag, sizeof(f), cudaMemcpyDeviceToHost));
+  if (acc) *acc = c[0];
+  if (rej) *rej = c[1];
+  if (nan_alpha) *nan_alpha = f;
+  return 0;
+}
+
+int bpm_reset_counters(bpm_handle h) {
+  if (!h) return fail("null handle");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  CU_TRY(cudaMemset(h->counters, 0, sizeof(unsigned long long) * 2));
+  CU_TRY(cudaMemset(h->nan_flag, 0, sizeof(int32_t)));
+  return 0;
+}
+
+int bpm_step_generations(bpm_handle h, bpm_state* st, int64_t k_gen0, int32_t n_gen,
+                         bpm_stream stream) {
+  if (!h || !st) return fail("null argument");
+  if (!st->X || !st->lnl) return fail("state needs X and lnl");
+  if (h->target == BPM_TARGET_EXTERNAL && !h->user_fn)
+    return fail("bpm_step_generations needs a built-in target or a batched callback");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  for (int g = 0; g < n_gen; ++g)
+    BPM_TRY(h->generation<false>(st, k_gen0 + g, nullptr, nullptr, (cudaStream_t)stream));
+  return 0;
+}
+
+int bpm_step_generation_replay(bpm_handle h, bpm_state* st, const bpm_replay* rp, int64_t k_gen,
+                               const bpm_trace_out* trace, bpm_stream stream) {
+  if (!h || !st || !rp) return fail("null argument");
+  if (!st->X || !st->lnl) return fail("state needs X and lnl");
+  if (h->target == BPM_TARGET_EXTERNAL && !h->user_fn)
+    return fail("replay step needs a built-in target or a batched callback");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  return h->generation<true>(st, k_gen, rp, trace, (cudaStream_t)stream);
+}
+
+int bpm_dump_draws(bpm_handle h, const bpm_state* st, int64_t k_gen, bpm_replay* out, int32_t* flip,
+                   bpm_stream stream) {
+  if (!h || !st || !out) return fail("null argument");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  BPM_TRY(h->begin(st, nullptr, s));
+  bpm::PhaseArgs a = h->make_args(st, k_gen, 0, nullptr, nullptr);
+  bpm::dump_draws_kernel<<<cdiv(h->cfg.n_chains, 128), 128, 0, s>>>(a, *out);
+  CU_TRY(cudaGetLastError());
+  if (flip) {
+    CU_TRY(cudaStreamSynchronize(s));
+    CU_TRY(cudaMemcpy(flip, h->flip, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    out->flip = *flip;
+  }
+  return 0;
+}
+
+int bpm_begin_generation(bpm_handle h, bpm_state* st, int64_t k_gen, const bpm_replay* rp,
+                         bpm_stream stream) {
+  if (!h || !st) return fail("null argument");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  BPM_TRY(h->begin(st, rp, (cudaStream_t)stream));
+  h->cur = h->make_args(st, k_gen, 0, rp, nullptr);
+  h->cur_replay = rp != nullptr;
+  h->cur_k_gen = k_gen;
+  h->in_generation = true;
+  return 0;
+}
+
+int bpm_propose(bpm_handle h, bpm_state* st, int32_t phase, double** prop, int32_t* n_phase,
+                bpm_stream stream) {
+  if (!h || !st) return fail("null argument");
+  if (!h->in_generation) return fail("bpm_propose outside bpm_begin_generation / bpm_end_generation");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  h->cur.phase = phase;
+  h->cur.X = st->X; h->cur.lnl = st->lnl;
+  if (h->cur_replay) BPM_TRY(h->launch_propose<true>(h->cur, (cudaStream_t)stream));
+  else BPM_TRY(h->launch_propose<false>(h->cur, (cudaStream_t)stream));
+  if (prop) *prop = h->prop;
+  if (n_phase) {
+    // the phase size depends on the flip when N is odd: read the flag back
+    int32_t f = 0;
+    CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    CU_TRY(cudaMemcpy(&f, h->flip, sizeof(f), cudaMemcpyDeviceToHost));
+    const bool first = ((phase ^ (f != 0)) == 0);
+    *n_phase = first ? h->nA : h->cfg.n_chains - h->nA;
+  }
+  return 0;
+}
+
+int bpm_accept(bpm_handle h, bpm_state* st, int32_t phase, const double* lnl_prop,
+               const bpm_trace_out* trace, bpm_stream stream) {
+  if (!h || !st || !lnl_prop) return fail("null argument");
+  if (!h->in_generation) return fail("bpm_accept outside a generation");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  bpm::PhaseArgs a = h->cur;
+  a.phase = phase;
+  a.lnl_prop = const_cast<double*>(lnl_prop);
+  if (trace) a.tr = *trace;
+  if (h->cur_replay) BPM_TRY(h->launch_accept<true>(a, (cudaStream_t)stream));
+  else BPM_TRY(h->launch_accept<false>(a, (cudaStream_t)stream));
+  return 0;
+}
+
+int bpm_phase(bpm_handle h, bpm_state* st, int32_t phase, bpm_stream stream) {
+  if (!h || !st) return fail("null argument");
+  if (!h->in_generation) return fail("bpm_phase outside a generation");
+  if (h->target == BPM_TARGET_EXTERNAL && !h->user_fn)
+    return fail("bpm_phase needs a built-in target or a batched callback");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  const bpm_replay* rp = h->cur_replay ? &h->cur.rp : nullptr;
+  const int64_t k_gen = h->cur_k_gen;
+  if (h->cur_replay) return h->phase<true>(st, k_gen, phase, rp, nullptr, (cudaStream_t)stream);
+  return h->phase<false>(st, k_gen, phase, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int bpm_end_generation(bpm_handle h, bpm_state* st, bpm_stream stream) {
+  if (!h || !st) return fail("null argument");
+  if (!h->in_generation) return fail("bpm_end_generation without bpm_begin_generation");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  BPM_TRY(h->end((cudaStream_t)stream));
+  st->hist_len += 1;
+  h->in_generation = false;
+  return 0;
+}
+
+int bpm_generations_host(bpm_handle h, double* X_host, double* lnl_host, int64_t k_gen0,
+                         int64_t g_abs0, int32_t n_gen) {
+  if (!h || !X_host || !lnl_host) return fail("null argument");
+  if (h->cfg.chain_lo != 0 || h->cfg.chain_hi != h->cfg.n_chains)
+    return fail("host entry is single-rank");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  const size_t nx = sizeof(double) * (size_t)h->cfg.n_chains * h->cfg.ld;
+  const size_t nl = sizeof(double) * (size_t)h->cfg.n_chains;
+  if (!h->hX) {
+    CU_TRY(cudaMalloc(&h->hX, nx));
+    CU_TRY(cudaMalloc(&h->hL, nl));
+  }
+  cudaStream_t s = 0;
+  CU_TRY(cudaMemcpyAsync(h->hX, X_host, nx, cudaMemcpyHostToDevice, s));
+  CU_TRY(cudaMemcpyAsync(h->hL, lnl_host, nl, cudaMemcpyHostToDevice, s));
+  bpm_state st;
+  memset(&st, 0, sizeof(st));
+  st.X = h->hX; st.lnl = h->hL; st.hist_len = g_abs0;
+  for (int g = 0; g < n_gen; ++g) BPM_TRY(h->generation<false>(&st, k_gen0 + g, nullptr, nullptr, s));
+  CU_TRY(cudaMemcpyAsync(X_host, h->hX, nx, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaMemcpyAsync(lnl_host, h->hL, nl, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int bpm_moments_from_history(bpm_handle h, bpm_state* st, bpm_stream stream) {
+  if (!h || !st || !st->history || !st->mean || !st->m2) return fail("null argument");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  const int64_t tot = (int64_t)(h->cfg.chain_hi - h->cfg.chain_lo) * h->cfg.ld;
+  bpm::moments_from_history_kernel<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>(
+      st->history, st->hist_len, h->cfg.n_chains, h->cfg.dim, h->cfg.ld, h->cfg.chain_lo,
+      h->cfg.chain_hi, st->mean, st->m2);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+int bpm_profile(bpm_handle h, int32_t on) {
+  if (!h) return fail("null handle");
+  h->prof_on = on != 0;
+  return 0;
+}
+
+int bpm_profile_read(bpm_handle h, double* ms_by_kind, int64_t* launches_by_kind) {
+  if (!h || !ms_by_kind || !launches_by_kind) return fail("null argument");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  CU_TRY(cudaDeviceSynchronize());
+  for (int k = 0; k < 8; ++k) { ms_by_kind[k] = 0.0; launches_by_kind[k] = 0; }
+  for (auto& r : h->recs) {
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_by_kind[r.kind] += ms;
+    launches_by_kind[r.kind] += 1;
+    h->ev_pool.push_back(r.a);
+    h->ev_pool.push_back(r.b);
+  }
+  h->recs.clear();
+  return 0;
+}
+
+int bpm_test_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+  bpm::Philox4 q = bpm::philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+  out[0] = q.x; out[1] = q.y; out[2] = q.z; out[3] = q.w;
+  return 0;
+}
+
+int bpm_test_permutation(uint64_t seed, uint64_t g_abs, int32_t n, int32_t* out_perm) {
+  if (n < 1 || !out_perm) return fail("bad argument");
+  bpm::RngCtx r = bpm::make_rng(seed, g_abs);
+  bpm::FeistelKey f = bpm::make_feistel(r, (uint32_t)n);
+  for (int32_t j = 0; j < n; ++j) out_perm[j] = (int32_t)bpm::feistel_perm(f, (uint32_t)j);
+  return 0;
+}
+
+int bpm_outlier_reset(bpm_handle, bpm_state*, const double*, int32_t*, bpm_stream) {
+  return fail("bpm_outlier_reset: not implemented yet");
+}
+int bpm_rhat(bpm_handle, const bpm_state*, int64_t, double*, bpm_stream) {
+  return fail("bpm_rhat: not implemented yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,394 @@
+// Generic (any d, any likelihood) split path of one half-phase:
+//   propose_kernel  -> prop[n_self][ld]           (demc.py:161-182 / dream.py:40-93)
+//   <likelihood>    -> lnl_prop[n_self]            (samplers.py:330)
+//   accept_kernel   -> X, lnl, moments, history    (samplers.py:328-336, demc.py:188-196)
+// A group of LPC lanes (1, 4, 8 or 32) owns one chain; each lane owns dimension blocks
+// of four consecutive doubles, b = sub + t * LPC.  The fused single-kernel variants in
+// kernels_fused.cuh reuse the same draw / arithmetic helpers (step.cuh), so both paths
+// produce bit-identical chains.
+#pragma once
+#include "step.cuh"
+#include "targets.cuh"
+
+namespace bpm {
+
+constexpr int kMaxBlocksPerLane = 8;  // d <= 4 * 8 * LPC  (1024 at LPC = 32)
+constexpr int kThreads = 256;
+
+// ---- demc.py:81-100: flip coin + shuffled split (native RNG) ----------------------
+__global__ void split_native_kernel(int32_t* __restrict__ perm, int32_t* __restrict__ flip, int N,
+                                    int shuffle, double flip_p, RngCtx rng) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0) {
+    Philox4 q = draw4(rng, 0xFFFFFFFFu, RNG_GEN, 0);
+    double thr = __ddiv_rn(flip_p, __dadd_rn(flip_p, __dsub_rn(1.0, flip_p)));
+    *flip = u53(q.x, q.y) < thr ? 1 : 0;
+  }
+  if (j >= N) return;
+  if (shuffle) {
+    FeistelKey f = make_feistel(rng, (uint32_t)N);
+    perm[j] = (int32_t)feistel_perm(f, (uint32_t)j);
+  } else {
+    perm[j] = j;
+  }
+}
+
+__global__ void set_flag_kernel(int32_t* flag, int32_t v) { *flag = v; }
+
+// ---- proposal ---------------------------------------------------------------------
+template <bool REPLAY, int LPC>
+__global__ void __launch_bounds__(kThreads) propose_kernel(const PhaseArgs a) {
+  const int gid = (blockIdx.x * kThreads + threadIdx.x) / LPC;
+  const int sub = threadIdx.x % LPC;
+  const PhaseLists L = phase_lists(a);
+  bool valid = gid < L.n_self;
+  const int c = valid ? L.self[gid] : 0;
+  valid = valid && c >= a.chain_lo && c < a.chain_hi;
+  const bool dream = a.algo == BPM_ALGO_DREAM;
+  const int nblk = (a.d + 3) >> 2;
+
+  ChainDraws D;
+  D.cr_idx = 0; D.fallback = -1; D.gamma_u = 0.0;
+  if (valid) chain_scalar_draws<REPLAY>(a, c, L.n_pool, D);
+
+  // pass 1 (DREAM): crossover mask of this lane's dimensions, d' (dream.py:51-58)
+  uint32_t mbits = 0xFFFFFFFFu;
+  double gamma;
+  if (dream) {
+    mbits = 0u;
+    const double cr = __ddiv_rn((double)(D.cr_idx + 1), (double)a.n_cr);
+    if (valid) {
+#pragma unroll
+      for (int t = 0; t < kMaxBlocksPerLane; ++t) {
+        const int b = sub + t * LPC;
+        if (b < nblk) {
+          double z[4];
+          z4<REPLAY>(a, c, b, z);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (4 * b + q < a.d && z[q] <= cr) mbits |= 1u << (4 * t + q);
+        }
+      }
+    }
+    int d_prime = group_sum_i<LPC>(__popc(mbits));
+    if (d_prime == 0) {  // dream.py:55-57: one random dimension
+      const int fb = D.fallback >> 2;
+      if (valid && (fb % LPC) == sub) mbits |= 1u << (4 * (fb / LPC) + (D.fallback & 3));
+      d_prime = 1;
+    }
+    gamma = dream_gamma(a, d_prime, D.gamma_u);
+  } else {
+    gamma = demc_gamma(a, D.gamma_u);
+  }
+
+  // pass 2: gather partner rows, build the proposal
+  const int npair = dream ? a.del_pairs : 1;
+  const double* pa[BPM_MAX_PAIRS];
+  const double* pb[BPM_MAX_PAIRS];
+#pragma unroll
+  for (int p = 0; p < BPM_MAX_PAIRS; ++p) {
+    pa[p] = a.X; pb[p] = a.X;
+    if (valid && p < npair) {
+      pa[p] = a.X + (size_t)L.pool[D.r1[p]] * a.ld;
+      pb[p] = a.X + (size_t)L.pool[D.r2[p]] * a.ld;
+    }
+  }
+  const double* xc = a.X + (size_t)c * a.ld;
+  double* out = a.prop + (size_t)gid * a.ld;
+  const double inv_T = 1.0 / (double)a.hist_len;
+  double delta = 0.0;
+  if (valid) {
+#pragma unroll
+    for (int t = 0; t < kMaxBlocksPerLane; ++t) {
+      const int b = sub + t * LPC;
+      if (b < nblk) {
+        double e[4] = {0, 0, 0, 0}, n[4];
+        if (dream) e4<REPLAY>(a, c, b, e);
+        n4<REPLAY>(a, c, b, n);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = 4 * b + q;
+          if (i < a.d) {
+            const double cur = xc[i];
+            double S = __dsub_rn(pa[0][i], pb[0][i]);
+#pragma unroll
+            for (int p = 1; p < BPM_MAX_PAIRS; ++p)
+              if (p < npair) S = __dadd_rn(S, __dsub_rn(pa[p][i], pb[p][i]));
+            double pr;
+            if (dream) {
+              const double mf = (mbits >> (4 * t + q)) & 1u ? 1.0 : 0.0;
+              pr = dream_prop(cur, S, e[q], n[q], gamma, mf);
+              if (a.adapt) delta += cr_term(cur, pr, a.m2[(size_t)(c - a.chain_lo) * a.ld + i], inv_T);
+            } else {
+              pr = demc_prop(cur, S, n[q], gamma);
+            }
+            out[i] = pr;
+            if (a.tr.prop) a.tr.prop[(size_t)c * a.d + i] = pr;
+          }
+        }
+      }
+    }
+  }
+  if (dream) {
+    delta = group_sum_d<LPC>(delta);
+    if (valid && sub == 0) {
+      a.cr_pick[c] = a.adapt ? D.cr_idx : -1;
+      a.cr_delta[c] = delta;
+    }
+  }
+}
+
+// ---- accept / reject + state, moments, history ---------------------------------
+template <bool REPLAY, int LPC>
+__global__ void __launch_bounds__(kThreads) accept_kernel(const PhaseArgs a) {
+  const int gid = (blockIdx.x * kThreads + threadIdx.x) / LPC;
+  const int sub = threadIdx.x % LPC;
+  const PhaseLists L = phase_lists(a);
+  bool valid = gid < L.n_self;
+  const int c = valid ? L.self[gid] : 0;
+  valid = valid && c >= a.chain_lo && c < a.chain_hi;
+  const int nblk = (a.d + 3) >> 2;
+  int acc = 0;
+  double lp = 0.0;
+  if (valid) {
+    lp = a.lnl_prop[gid];
+    const double u = accept_uniform<REPLAY>(a, c);
+    acc = metropolis(a.lnl[c], lp, u);
+    if (acc < 0) {
+      *a.nan_flag = 1;
+      acc = 0;
+    }
+    double* xc = a.X + (size_t)c * a.ld;
+    const double* pr = a.prop + (size_t)gid * a.ld;
+    const double n1 = (double)(a.hist_len + 1);
+#pragma unroll
+    for (int t = 0; t < kMaxBlocksPerLane; ++t) {
+      const int b = sub + t * LPC;
+      if (b < nblk) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = 4 * b + q;
+          if (i < a.d) {
+            double s = xc[i];
+            if (acc) {
+              s = pr[i];
+              xc[i] = s;
+            }
+            if (a.mean) {  // Welford update with the appended row (chain.py:51-54)
+              const size_t o = (size_t)(c - a.chain_lo) * a.ld + i;
+              const double mu = a.mean[o];
+              const double dl = s - mu;
+              const double mu2 = mu + dl / n1;
+              a.mean[o] = mu2;
+              a.m2[o] += dl * (s - mu2);
+            }
+            if (a.hist_row) a.hist_row[(size_t)(c - a.chain_lo) * a.ld + i] = s;
+          }
+        }
+      }
+    }
+    if (sub == 0) {
+      if (acc) a.lnl[c] = lp;
+      if (a.tr.accept) a.tr.accept[c] = acc;
+      if (a.tr.lnl_prop) a.tr.lnl_prop[c] = lp;
+    }
+  }
+  const unsigned am = __ballot_sync(0xFFFFFFFFu, valid && sub == 0 && acc);
+  const unsigned rm = __ballot_sync(0xFFFFFFFFu, valid && sub == 0 && !acc);
+  if ((threadIdx.x & 31) == 0) {
+    if (am) atomicAdd(a.n_acc, (unsigned long long)__popc(am));
+    if (rm) atomicAdd(a.n_rej, (unsigned long long)__popc(rm));
+  }
+}
+
+// ---- built-in likelihood kernels over a dense [n][ld] block of rows ---------------
+__global__ void lnl_banana_kernel(const double* __restrict__ P, int n, int ld, BananaParams prm,
+                                  double* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) out[j] = banana_lnl(prm, P[(size_t)j * ld], P[(size_t)j * ld + 1]);
+}
+__global__ void lnl_bimodal_kernel(const double* __restrict__ P, int n, int ld, BimodalParams prm,
+                                   double* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) out[j] = bimodal_lnl(prm, P[(size_t)j * ld], P[(size_t)j * ld + 1]);
+}
+__global__ void lnl_linefit_kernel(const double* __restrict__ P, int n, int ld,
+                                   const double* __restrict__ data, int M, double* __restrict__ out) {
+  extern __shared__ double sdata[];
+  for (int i = threadIdx.x; i < 3 * M; i += blockDim.x) sdata[i] = data[i];
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n)
+    out[j] = linefit_lnl(sdata, sdata + M, sdata + 2 * M, M, P[(size_t)j * ld], P[(size_t)j * ld + 1],
+                         P[(size_t)j * ld + 2]);
+}
+
+// Generic tiled quadratic form for any d: out[j] = finish(|(P[j] - mu) . W|^2).
+// 64 x 64 output tile per CTA, 4 x 4 register tile per thread, k-tile 16; the tile's
+// squared entries are folded into per-row sums so Y = (P - mu) W never reaches memory.
+__global__ void __launch_bounds__(256) lnl_gauss_tiled_kernel(const double* __restrict__ P, int n,
+                                                              int ld, int d, int r,
+                                                              const double* __restrict__ mu,
+                                                              const double* __restrict__ W,
+                                                              double c0, int log_of_pdf,
+                                                              double* __restrict__ out) {
+  constexpr int TM = 64, TN = 64, TK = 16;
+  __shared__ double As[TK][TM + 1];
+  __shared__ double Bs[TK][TN];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.x * TM;
+  double rowsum[4] = {0, 0, 0, 0};
+  for (int n0 = 0; n0 < r; n0 += TN) {
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int k0 = 0; k0 < d; k0 += TK) {
+      for (int idx = threadIdx.x; idx < TM * TK; idx += 256) {
+        const int kk = idx % TK, mm = idx / TK;
+        const int row = m0 + mm, k = k0 + kk;
+        As[kk][mm] = (row < n && k < d) ? P[(size_t)row * ld + k] - mu[k] : 0.0;
+      }
+      for (int idx = threadIdx.x; idx < TK * TN; idx += 256) {
+        const int nn = idx % TN, kk = idx / TN;
+        const int k = k0 + kk, col = n0 + nn;
+        Bs[kk][nn] = (k < d && col < r) ? W[(size_t)k * r + col] : 0.0;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < TK; ++kk) {
+        double av[4], bv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rowsum[i] = fma(acc[i][j], acc[i][j], rowsum[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double v = rowsum[i];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    const int row = m0 + ty * 4 + i;
+    if (tx == 0 && row < n) out[row] = gauss_finish(c0, v, log_of_pdf);
+  }
+}
+
+// ---- CR adaptation: deterministic reduction + p_cr update (dream.py:119-140) -----
+__global__ void __launch_bounds__(1024) cr_reduce_kernel(const double* __restrict__ cr_delta,
+                                                         const int32_t* __restrict__ cr_pick, int lo,
+                                                         int hi, int n_cr, double* __restrict__ part) {
+  // part[0:n_cr) = sum of jump statistics per CR value, part[n_cr:2n_cr) = counts
+  __shared__ double sm[32];
+  for (int m = 0; m < n_cr; ++m) {
+    double s = 0.0, k = 0.0;
+    for (int c = lo + threadIdx.x; c < hi; c += blockDim.x)
+      if (cr_pick[c] == m) { s += cr_delta[c]; k += 1.0; }
+    for (int pass = 0; pass < 2; ++pass) {
+      double v = pass == 0 ? s : k;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+      if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        double w = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xFFFFFFFFu, w, o);
+        if (threadIdx.x == 0) part[pass * n_cr + m] = w;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void cr_apply_kernel(const double* __restrict__ part, int n_cr, double* __restrict__ dm,
+                                double* __restrict__ cnt, double* __restrict__ p_cr) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double got = 0.0;
+  for (int m = 0; m < n_cr; ++m) {
+    dm[m] += part[m];
+    cnt[m] += part[n_cr + m];
+    got += part[n_cr + m];
+  }
+  if (got == 0.0) return;  // no chain ran _update_cr_ratios this generation
+  int nz = 0;
+  for (int m = 0; m < n_cr; ++m) nz += cnt[m] > 0.0;
+  if (nz == n_cr)
+    for (int m = 0; m < n_cr; ++m) p_cr[m] = dm[m] / cnt[m];
+  double tot = 0.0;
+  for (int m = 0; m < n_cr; ++m) tot += p_cr[m];
+  for (int m = 0; m < n_cr; ++m) p_cr[m] /= tot;
+}
+
+// ---- moments rebuilt from a stored history (load_state / warm start) -------------
+__global__ void moments_from_history_kernel(const double* __restrict__ hist, int64_t T, int N, int d,
+                                            int ld, int lo, int hi, double* __restrict__ mean,
+                                            double* __restrict__ m2) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t tot = (int64_t)(hi - lo) * ld;
+  if (idx >= tot) return;
+  const int c = lo + (int)(idx / ld), i = (int)(idx % ld);
+  if (i >= d) return;
+  double mu = 0.0, s2 = 0.0;
+  for (int64_t t = 0; t < T; ++t) {
+    const double s = hist[((size_t)t * (hi - lo) + (c - lo)) * ld + i];
+    const double dl = s - mu;
+    mu = mu + dl / (double)(t + 1);
+    s2 += dl * (s - mu);
+  }
+  mean[(size_t)(c - lo) * ld + i] = mu;
+  m2[(size_t)(c - lo) * ld + i] = s2;
+}
+
+// ---- materialise the native stream into replay buffers (testing / provenance) ----
+__global__ void dump_draws_kernel(const PhaseArgs a, bpm_replay out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.N) return;
+  const int c = a.perm[j];
+  const bool first_half = j < a.nA;
+  const int n_pool = first_half ? a.N - a.nA : a.nA;  // pool sizes do not depend on the flip
+  const_cast<int32_t*>(out.shuffle_idx)[j] = c;
+  ChainDraws D;
+  chain_scalar_draws<false>(a, c, n_pool, D);
+  const int npair = a.algo == BPM_ALGO_DREAM ? a.del_pairs : 1;
+  for (int p = 0; p < npair; ++p) {
+    const_cast<int32_t*>(out.pairs)[((size_t)c * npair + p) * 2 + 0] = D.r1[p];
+    const_cast<int32_t*>(out.pairs)[((size_t)c * npair + p) * 2 + 1] = D.r2[p];
+  }
+  const_cast<double*>(out.gamma_u)[c] = D.gamma_u;
+  const_cast<double*>(out.accept_u)[c] = accept_uniform<false>(a, c);
+  if (a.algo == BPM_ALGO_DREAM) {
+    const_cast<int32_t*>(out.cr_idx)[c] = D.cr_idx;
+    const_cast<int32_t*>(out.fallback_dim)[c] = D.fallback;
+  }
+  const int nblk = (a.d + 3) >> 2;
+  for (int b = 0; b < nblk; ++b) {
+    double z[4], e[4], n[4];
+    z4<false>(a, c, b, z);
+    e4<false>(a, c, b, e);
+    n4<false>(a, c, b, n);
+    for (int q = 0; q < 4; ++q) {
+      const int i = 4 * b + q;
+      if (i < a.d) {
+        if (a.algo == BPM_ALGO_DREAM) {
+          const_cast<double*>(out.z)[(size_t)c * a.d + i] = z[q];
+          const_cast<double*>(out.e)[(size_t)c * a.d + i] = e[q];
+        }
+        const_cast<double*>(out.nrm)[(size_t)c * a.d + i] = n[q];
+      }
+    }
+  }
+}
+
+}  // namespace bpm

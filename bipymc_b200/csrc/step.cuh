@@ -1,0 +1,259 @@
+// Shared device-side pieces of one DE-MC / DREAM chain-step: kernel parameter block,
+// draw providers (native Philox or RNG-replay), and the proposal / accept arithmetic
+// written with explicit round-to-nearest intrinsics so the compiler can never contract
+// a multiply-add -- in replay mode the proposal must reproduce numpy's elementwise
+// float64 results bit for bit (demc.py:180-182, dream.py:85-89).
+#pragma once
+#include <stdint.h>
+#include "rng.cuh"
+#include "../../include/bipymc_b200.h"
+
+namespace bpm {
+
+// Everything a phase kernel needs, passed by value (fits the 4 KB param space easily).
+struct PhaseArgs {
+  // population (caller-owned)
+  double* X;
+  double* lnl;
+  double* mean;
+  double* m2;
+  double* hist_row;  // destination row block [N][ld] for this generation, or nullptr
+  // phase lists: perm[0:nA) is half "a", perm[nA:N) half "b" before the flip swap
+  const int32_t* perm;
+  const int32_t* flip;  // device flag (demc.py:81,98-100)
+  int32_t phase;        // 0: update a from frozen b; 1: update b from updated a
+  int32_t N, nA, d, ld;
+  int32_t chain_lo, chain_hi;
+  // schedule
+  int32_t algo, del_pairs, n_cr;
+  int32_t gamma_jump;  // k % 5 == 0 (DREAM, dream.py:77) / k % 10 == 0 (DE-MC, demc.py:174)
+  double gamma_p0;     // 0.2 / 0.1: probability of KEEPING gamma_base on a jump generation
+  double gamma_fixed;  // DE-MC gamma_base (demc.py:162)
+  double gamma_num;    // DREAM: gamma_scale * 2.38 (dream.py:61)
+  double eps;          // Gaussian jitter sd (already sqrt(epsilon**2))
+  double u_eps;        // box jitter half-width
+  int32_t adapt;       // burnin_gen > k && hist_len > n_cr_gen (dream.py:92,124)
+  int64_t hist_len;    // rows in every chain's history BEFORE this generation's append
+  // CR state
+  const double* p_cr;  // [n_cr]
+  double* cr_delta;    // [N] per-chain jump statistic of this generation (or untouched)
+  int32_t* cr_pick;    // [N] chosen CR index, -1 when no statistic was recorded
+  // workspace
+  double* prop;      // [nA][ld] proposals in phase order
+  double* lnl_prop;  // [nA]
+  // counters
+  unsigned long long* n_acc;
+  unsigned long long* n_rej;
+  int32_t* nan_flag;
+  // native RNG
+  RngCtx rng;
+  // replay buffers (REPLAY kernels only)
+  bpm_replay rp;
+  // optional trace
+  bpm_trace_out tr;
+};
+
+// Phase-list helpers.  self = chains updated in this phase, pool = the other half.
+struct PhaseLists {
+  const int32_t* self;
+  const int32_t* pool;
+  int32_t n_self, n_pool;
+};
+__device__ __forceinline__ PhaseLists phase_lists(const PhaseArgs& a) {
+  const int32_t first = (a.phase ^ (*a.flip != 0)) == 0;  // true: self is perm[0:nA)
+  PhaseLists L;
+  if (first) {
+    L.self = a.perm; L.n_self = a.nA; L.pool = a.perm + a.nA; L.n_pool = a.N - a.nA;
+  } else {
+    L.self = a.perm + a.nA; L.n_self = a.N - a.nA; L.pool = a.perm; L.n_pool = a.nA;
+  }
+  return L;
+}
+
+// Reduce over the LPC lanes that share one chain (LPC is a power of two <= 32).
+template <int LPC>
+__device__ __forceinline__ int group_sum_i(int v) {
+#pragma unroll
+  for (int o = LPC / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+template <int LPC>
+__device__ __forceinline__ double group_sum_d(double v) {
+#pragma unroll
+  for (int o = LPC / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+
+// numpy choice over a cdf: idx = searchsorted(cdf / cdf[-1], u, side='right')
+// (legacy RandomState.choice; dream.py:51).
+__device__ __forceinline__ int pick_cr(const double* p_cr, int n_cr, double u) {
+  double tot = 0.0;
+  for (int m = 0; m < n_cr; ++m) tot = __dadd_rn(tot, p_cr[m]);
+  double acc = 0.0;
+  int idx = 0;
+  for (int m = 0; m < n_cr; ++m) {
+    acc = __dadd_rn(acc, p_cr[m]);
+    if (__ddiv_rn(acc, tot) <= u) idx = m + 1;
+  }
+  return idx < n_cr ? idx : n_cr - 1;
+}
+
+// samplers.py:328-336: alpha = clip(min(1, exp(lp - lc)), 0, 1);
+// accept iff u < alpha / (alpha + (1 - alpha))   (numpy choice with p=[alpha, 1-alpha]).
+// Returns 1 accept, 0 reject, -1 NaN alpha (numpy raises ValueError there).
+__device__ __forceinline__ int metropolis(double lnl_cur, double lnl_prop, double u) {
+  double alpha = exp(__dsub_rn(lnl_prop, lnl_cur));
+  if (alpha != alpha) return -1;
+  alpha = alpha > 1.0 ? 1.0 : alpha;
+  alpha = alpha < 0.0 ? 0.0 : alpha;
+  double thr = __ddiv_rn(alpha, __dadd_rn(alpha, __dsub_rn(1.0, alpha)));
+  return u < thr ? 1 : 0;
+}
+
+// Per-chain scalar draws.
+struct ChainDraws {
+  int cr_idx;
+  int fallback;
+  double gamma_u;
+  int r1[BPM_MAX_PAIRS], r2[BPM_MAX_PAIRS];  // POOL-LOCAL partner indices
+};
+
+template <bool REPLAY>
+__device__ __forceinline__ void chain_scalar_draws(const PhaseArgs& a, int c, int n_pool,
+                                                   ChainDraws& D) {
+  const int npair = a.algo == BPM_ALGO_DREAM ? a.del_pairs : 1;
+  if (REPLAY) {
+    D.cr_idx = a.algo == BPM_ALGO_DREAM ? a.rp.cr_idx[c] : 0;
+    D.fallback = a.algo == BPM_ALGO_DREAM ? a.rp.fallback_dim[c] : -1;
+    D.gamma_u = a.rp.gamma_u[c];
+#pragma unroll
+    for (int p = 0; p < BPM_MAX_PAIRS; ++p)
+      if (p < npair) {
+        D.r1[p] = a.rp.pairs[((size_t)c * npair + p) * 2 + 0];
+        D.r2[p] = a.rp.pairs[((size_t)c * npair + p) * 2 + 1];
+      }
+  } else {
+    Philox4 s0 = draw4(a.rng, (uint32_t)c, RNG_SCALAR, 0);
+    Philox4 s1 = draw4(a.rng, (uint32_t)c, RNG_SCALAR, 1);
+    D.cr_idx = a.algo == BPM_ALGO_DREAM ? pick_cr(a.p_cr, a.n_cr, u53(s0.x, s0.y)) : 0;
+    D.gamma_u = u53(s1.x, s1.y);
+    D.fallback = (int)below64(s1.z, s1.w, (uint32_t)a.d);
+#pragma unroll
+    for (int p = 0; p < BPM_MAX_PAIRS; ++p)
+      if (p < npair) {
+        Philox4 q = draw4(a.rng, (uint32_t)c, RNG_SCALAR, 2 + p);
+        // distinct pair, uniform over ordered pairs: same law as permutation(P)[:2]
+        uint32_t i = below64(q.x, q.y, (uint32_t)n_pool);
+        uint32_t j = below64(q.z, q.w, (uint32_t)(n_pool - 1));
+        j += (j >= i);
+        D.r1[p] = (int)i;
+        D.r2[p] = (int)j;
+      }
+  }
+}
+
+template <bool REPLAY>
+__device__ __forceinline__ double accept_uniform(const PhaseArgs& a, int c) {
+  if (REPLAY) return a.rp.accept_u[c];
+  Philox4 s0 = draw4(a.rng, (uint32_t)c, RNG_SCALAR, 0);
+  return u53(s0.z, s0.w);
+}
+
+// Four per-dimension draws for dims 4b .. 4b+3 of chain c.
+template <bool REPLAY>
+__device__ __forceinline__ void z4(const PhaseArgs& a, int c, int b, double z[4]) {
+  if (REPLAY) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      int i = 4 * b + t;
+      z[t] = i < a.d ? a.rp.z[(size_t)c * a.d + i] : 2.0;
+    }
+  } else {
+    Philox4 q = draw4(a.rng, (uint32_t)c, RNG_Z, (uint32_t)b);
+    z[0] = u32d(q.x); z[1] = u32d(q.y); z[2] = u32d(q.z); z[3] = u32d(q.w);
+  }
+}
+template <bool REPLAY>
+__device__ __forceinline__ void e4(const PhaseArgs& a, int c, int b, double e[4]) {
+  if (REPLAY) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      int i = 4 * b + t;
+      e[t] = (i < a.d && a.rp.e) ? a.rp.e[(size_t)c * a.d + i] : 0.0;
+    }
+  } else {
+    if (a.u_eps > 0.0) {
+      Philox4 q = draw4(a.rng, (uint32_t)c, RNG_E, (uint32_t)b);
+      const double lo = -a.u_eps, w = __dsub_rn(a.u_eps, lo);  // numpy: low + (high-low)*u
+      e[0] = __dadd_rn(lo, __dmul_rn(w, u32d(q.x)));
+      e[1] = __dadd_rn(lo, __dmul_rn(w, u32d(q.y)));
+      e[2] = __dadd_rn(lo, __dmul_rn(w, u32d(q.z)));
+      e[3] = __dadd_rn(lo, __dmul_rn(w, u32d(q.w)));
+    } else {
+      e[0] = e[1] = e[2] = e[3] = 0.0;  // var_box returns 0. and draws nothing (util.py:24-28)
+    }
+  }
+}
+template <bool REPLAY>
+__device__ __forceinline__ void n4(const PhaseArgs& a, int c, int b, double n[4]) {
+  if (REPLAY) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      int i = 4 * b + t;
+      n[t] = (i < a.d && a.rp.nrm) ? a.rp.nrm[(size_t)c * a.d + i] : 0.0;
+    }
+  } else {
+    if (a.eps > 0.0) {
+      Philox4 q = draw4(a.rng, (uint32_t)c, RNG_N, (uint32_t)b);
+      float f0, f1, f2, f3;
+      normal2(q.x, q.y, f0, f1);
+      normal2(q.z, q.w, f2, f3);
+      n[0] = __dmul_rn(a.eps, (double)f0);
+      n[1] = __dmul_rn(a.eps, (double)f1);
+      n[2] = __dmul_rn(a.eps, (double)f2);
+      n[3] = __dmul_rn(a.eps, (double)f3);
+    } else {
+      n[0] = n[1] = n[2] = n[3] = 0.0;  // var_ball returns 0. and draws nothing (util.py:11-16)
+    }
+  }
+}
+
+// dream.py:85-89:  ((1 + e) * gamma * S + n) * mask + cur, evaluated left to right.
+__device__ __forceinline__ double dream_prop(double cur, double S, double e, double n, double gamma,
+                                             double maskf) {
+  double t = __dadd_rn(1.0, e);
+  t = __dmul_rn(t, gamma);
+  t = __dmul_rn(t, S);
+  t = __dadd_rn(t, n);
+  t = __dmul_rn(t, maskf);
+  return __dadd_rn(t, cur);
+}
+// demc.py:180-182:  gamma * (a - b); += cur; += n
+__device__ __forceinline__ double demc_prop(double cur, double diff, double n, double gamma) {
+  double t = __dmul_rn(gamma, diff);
+  t = __dadd_rn(t, cur);
+  return __dadd_rn(t, n);
+}
+
+// dream.py:61 / 77-80 and demc.py:162 / 174-177
+__device__ __forceinline__ double dream_gamma(const PhaseArgs& a, int d_prime, double gamma_u) {
+  double base = __ddiv_rn(a.gamma_num, __dsqrt_rn(__dmul_rn(__dmul_rn(2.0, (double)a.del_pairs),
+                                                            (double)d_prime)));
+  if (a.gamma_jump) return gamma_u < a.gamma_p0 ? base : 1.0;
+  return base;
+}
+__device__ __forceinline__ double demc_gamma(const PhaseArgs& a, double gamma_u) {
+  if (a.gamma_jump) return gamma_u < a.gamma_p0 ? a.gamma_fixed : 1.0;
+  return a.gamma_fixed;
+}
+
+// dream.py:128-130 contribution of one dimension: (cur - prop)^2 / std^2 with
+// std^2 = M2 / T (population variance of the chain's history), 0 -> (1e-12)^2.
+__device__ __forceinline__ double cr_term(double cur, double prop, double m2, double inv_T) {
+  double var = __dmul_rn(m2, inv_T);
+  if (!(var > 0.0)) var = 1e-12 * 1e-12;
+  double df = __dsub_rn(cur, prop);
+  return __ddiv_rn(__dmul_rn(df, df), var);
+}
+
+}  // namespace bpm

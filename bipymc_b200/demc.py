@@ -1,0 +1,754 @@
+"""DeMcMpi -- drop-in for bipymc/demc.py:10-338 on a device-resident population.
+
+Same constructor, ``run_mcmc``, ``param_est``, ``save_state`` / ``load_state``,
+``super_chain_mpi``, ``gather_all_chains``, ``iter_*_chains``, ``get_chain`` and
+attribute surface as the reference.  What changed underneath:
+
+  * the population (current positions, cached log-likelihoods, running moments and the
+    full history) lives in torch CUDA tensors; ``am_chains[i]`` are lazy views;
+  * ``_mcmc_run`` (demc.py:63-151) issues a few CUDA kernels per generation through the
+    C-ABI (include/bipymc_b200.h) instead of looping over chains in Python;
+  * the mpi4py rank-per-chain-group layout (demc.py:39,93,116) becomes one process per
+    GPU under ``torch.distributed`` (NCCL): each rank owns the contiguous chain block
+    ``np.array_split(range(N), world)[rank]`` and keeps a replica of the whole
+    population that is refreshed by an all-gather after each half-phase.
+
+Likelihood plug-ins, fastest first:
+  1. ``ln_like_fn`` is ``obj.ln_like`` of a built-in target (bipymc_b200.targets): the
+     likelihood is evaluated inside the generation kernels;
+  2. ``ln_like_batched=f``: ``f(theta)`` takes a CUDA float64 tensor ``[n, dim]`` and
+     returns ``[n]`` log-likelihoods (torch ops on the current stream);
+  3. any scalar ``ln_like_fn(theta, **ln_kwargs) -> float`` exactly as in the reference
+     (samplers.py:36-43): proposals make a host round trip per half-phase -- correct,
+     not fast.
+
+There is no CPU fallback: constructing a sampler without a CUDA device raises.
+"""
+from __future__ import print_function, division
+import ctypes as C
+import sys
+
+import numpy as np
+
+from . import _lib
+from .chain import McmcChain
+from .targets import resolve_device_target
+from .util import var_ball_batch
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class _SingleComm(object):
+    """Stand-in for MPI.COMM_WORLD when neither mpi4py nor torch.distributed is in use."""
+    size, rank = 1, 0
+
+    def Get_size(self):
+        return 1
+
+    def Get_rank(self):
+        return 0
+
+    def Barrier(self):
+        pass
+
+
+class _TorchComm(object):
+    """rank / size / Barrier facade over an initialised torch.distributed group."""
+    def __init__(self, dist):
+        self._dist = dist
+        self.size = dist.get_world_size()
+        self.rank = dist.get_rank()
+
+    def Get_size(self):
+        return self.size
+
+    def Get_rank(self):
+        return self.rank
+
+    def Barrier(self):
+        self._dist.barrier()
+
+
+def _default_comm():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return _TorchComm(dist)
+    except Exception:
+        pass
+    return _SingleComm()
+
+
+class GaussianProposalStub(object):
+    """The reference instantiates a GaussianProposal in every sampler ctor
+    (samplers.py:27) but never calls it on the DE-MC / DREAM path; keep the attribute."""
+    def __init__(self, frozen_ln_like_fn):
+        self._frozen_ln_like_fn = frozen_ln_like_fn
+        self._cov_init = False
+        self._mu = None
+        self._cov = None
+
+
+class HistoryStore(object):
+    """Device history ``[T][n_local][ld]`` in growable chunks.
+
+    Flattened to ``(T * n_local, d)`` a chunk *is* the reference's interlaced super
+    chain (demc.py:260-268).  ``policy``: "full" keeps every generation (drop-in
+    default); "none" keeps only the rows present at construction / load time (running
+    moments still see every generation).  ``length`` is the LOGICAL chain length
+    (generations + 1, what ``len(chain.chain)`` is in the reference); ``stored`` the
+    number of rows physically kept."""
+    def __init__(self, n_local, dim, ld, device, policy="full", chunk_bytes=1 << 28):
+        import torch
+        if policy not in ("full", "none"):
+            raise ValueError("history must be 'full' or 'none'")
+        self._torch = torch
+        self.n_local, self.dim, self.ld, self.device = n_local, dim, ld, device
+        self.policy = policy
+        self.row_bytes = n_local * ld * 8
+        self.chunk_rows = max(1, int(chunk_bytes // self.row_bytes))
+        self.chunks = []      # list of [rows, n_local, ld] tensors
+        self.stored = 0
+        self.length = 0
+        self._current = None  # [n_local, ld] view of the live population rows
+
+    def _used_in_last(self):
+        return self.stored - sum(c.shape[0] for c in self.chunks[:-1]) if self.chunks else 0
+
+    def reserve(self, rows):
+        """Room for up to `rows` more generations: returns (base_address, rows_available),
+        base_address being where row 0 of one flat [T][n_local][ld] array would sit so
+        that row `length` lands on the next free row of the last chunk.  (None, rows)
+        when nothing is kept."""
+        if self.policy != "full":
+            return None, rows
+        torch = self._torch
+        used = self._used_in_last()
+        if not self.chunks or used == self.chunks[-1].shape[0]:
+            n = min(self.chunk_rows, max(rows, 1))
+            self.chunks.append(torch.empty((n, self.n_local, self.ld), dtype=torch.float64,
+                                           device=self.device))
+            used = 0
+        last = self.chunks[-1]
+        base = last.data_ptr() - (self.length - used) * self.row_bytes
+        return base, last.shape[0] - used
+
+    def advance(self, rows):
+        self.length += rows
+        if self.policy == "full":
+            self.stored += rows
+
+    def set_initial(self, state):
+        """state: [n_local, ld] device tensor = row 0 of every chain."""
+        torch = self._torch
+        self.chunks = [torch.empty((1, self.n_local, self.ld), dtype=torch.float64, device=self.device)]
+        self.chunks[0][0].copy_(state)
+        self.stored = self.length = 1
+
+    def tensor(self):
+        """[stored, n_local, ld] (concatenates chunks when there are several)."""
+        torch = self._torch
+        parts, left = [], self.stored
+        for c in self.chunks:
+            take = min(left, c.shape[0])
+            if take > 0:
+                parts.append(c[:take])
+            left -= take
+        if len(parts) > 1:          # coalesce once so later reads are free
+            whole = torch.cat(parts, dim=0)
+            self.chunks = [whole]
+            return whole
+        return parts[0]
+
+    def chain_host(self, li):
+        return self.tensor()[:, li, :self.dim].cpu().numpy()
+
+    def set_chain_host(self, li, arr):
+        t = self.tensor()
+        if arr.shape[0] != t.shape[0]:
+            raise ValueError("chain length mismatch: use the sampler's load_history() to replace "
+                             "histories of a different length")
+        t[:, li, :self.dim] = self._torch.from_numpy(np.ascontiguousarray(arr)).to(self.device)
+
+    def current_host(self, li):
+        return self._current[li, :self.dim].cpu().numpy()
+
+    def load(self, hist):
+        """hist: numpy (T, n_local, dim) -> replaces the stored history."""
+        torch = self._torch
+        T = hist.shape[0]
+        t = torch.zeros((T, self.n_local, self.ld), dtype=torch.float64, device=self.device)
+        t[:, :, :self.dim] = torch.from_numpy(np.ascontiguousarray(hist)).to(self.device)
+        self.chunks = [t]
+        self.stored = self.length = T
+
+
+class _ChainList(object):
+    """``am_chains``: a sequence of lazily created McmcChain views (one per local chain)."""
+    def __init__(self, sampler):
+        self._s = sampler
+        self._cache = {}
+
+    def __len__(self):
+        return len(self._s.rank_chain_ids)
+
+    def __bool__(self):
+        return len(self) > 0
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        ch = self._cache.get(i)
+        if ch is None:
+            ch = McmcChain(None, global_id=int(self._s.rank_chain_ids[i]), _store=self._s._hist,
+                           _local_index=i)
+            self._cache[i] = ch
+        return ch
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
+
+
+class DeMcMpi(object):
+    """Parallel DE-MC (emcee-style a/b pools) on B200; mirrors bipymc/demc.py:10."""
+    _algo = _lib.BPM_ALGO_DEMC
+
+    def __init__(self, ln_like_fn, theta_0=None, varepsilon=1e-6, n_chains=8,
+                 mpi_comm=None, ln_kwargs={}, **kwargs):
+        varepsilon = np.asarray(varepsilon)
+        assert n_chains >= 4                                   # samplers.py:249
+        self.n_chains = n_chains
+        self.comm = mpi_comm if (mpi_comm is not None and hasattr(mpi_comm, "rank")) else _default_comm()
+        self.local_n_accepted = 0
+        self.local_n_rejected = 1                               # demc.py:19-20
+        if theta_0 is not None:
+            self.dim = len(np.asarray(theta_0))
+        else:
+            self.dim = kwargs.get("dim", 1)
+        self.h5_file = kwargs.get("h5_file", "sampler_checkpoint.h5")
+        self.warm_start = kwargs.get("warm_start", False)
+        self.checkpoint = kwargs.get("checkpoint", 0)
+        # McmcSampler.__init__ (samplers.py:16-31)
+        self.log_like_fn = ln_like_fn
+        self._ln_kwargs = dict(ln_kwargs)
+        self._freeze_ln_like_fn(**ln_kwargs)
+        self.mcmc_proposal = GaussianProposalStub(self.frozen_ln_like_fn)
+        self.n_accepted, self.n_rejected = 1, 0
+        # B200 extensions (all optional)
+        self._seed = kwargs.get("seed", None)
+        self._history_policy = kwargs.get("history", "full")
+        self._ln_like_batched = kwargs.get("ln_like_batched", None)
+        self._device_index = kwargs.get("device", None)
+        self._fused = kwargs.get("fused", True)
+        self._chunk_bytes = int(kwargs.get("history_chunk_bytes", 1 << 30))
+        self._setup_device()
+        if not self.warm_start:
+            self.init_chains(theta_0, varepsilon, **kwargs)
+        else:
+            self.init_warmstart_chain(self.h5_file)
+
+    # ------------------------------------------------------------------ plumbing
+    def _freeze_ln_like_fn(self, **kwargs):
+        self._frozen_ln_like_fn = lambda theta: self.log_like_fn(theta, **kwargs)
+
+    @property
+    def frozen_ln_like_fn(self):
+        return self._frozen_ln_like_fn
+
+    def _setup_device(self):
+        torch = _torch()
+        self._libh = _lib.load()                       # raises if the CUDA library is missing
+        if not torch.cuda.is_available():
+            raise RuntimeError("bipymc_b200 needs a CUDA device (B200); there is no CPU fallback")
+        if self._device_index is None:
+            self._device_index = torch.cuda.current_device() if self.comm.size == 1 else \
+                self.comm.rank % torch.cuda.device_count()
+        self._device = torch.device("cuda", self._device_index)
+        torch.cuda.set_device(self._device)
+        self._handle = None
+        self._hist = None
+
+    def _dream_cfg(self):
+        return dict(del_pairs=1, n_cr=1, burnin_gen=0, n_cr_gen=0, gamma_scale=1.0)
+
+    def _create_handle(self):
+        d = self.dim
+        self._ld = d if d <= 4 else ((d + 3) // 4) * 4
+        ids = np.array_split(np.array(range(self.n_chains)), self.comm.size)[self.comm.rank]
+        self.rank_chain_ids = ids                                   # demc.py:39-40
+        if self._seed is None:
+            # keep np.random.seed(...) meaningful for the native stream as well
+            self._seed = int(np.random.randint(0, 2 ** 31 - 1))
+            if self.comm.size > 1:
+                self._seed = self._bcast_int(self._seed)
+        dc = self._dream_cfg()
+        cfg = _lib.Config(algo=self._algo, n_chains=self.n_chains, dim=d, ld=self._ld,
+                          del_pairs=dc["del_pairs"], n_cr=dc["n_cr"], burnin_gen=dc["burnin_gen"],
+                          n_cr_gen=dc["n_cr_gen"], shuffle=1, chain_lo=int(ids[0]),
+                          chain_hi=int(ids[-1]) + 1, device=self._device_index,
+                          gamma_scale=dc["gamma_scale"], flip=0.5, epsilon=0.0, u_epsilon=0.0,
+                          gamma=0.0, seed=self._seed)
+        h = C.c_void_p()
+        _lib.check(self._libh.bpm_create(C.byref(cfg), C.byref(h)))
+        self._handle = h
+        _lib.check(self._libh.bpm_set_fused(h, 1 if self._fused else 0))
+        self._target = resolve_device_target(self.log_like_fn, self._ln_kwargs)
+        if self._target is not None:
+            if self._target.dim != d:
+                raise ValueError("target dimension %d != theta_0 dimension %d" % (self._target.dim, d))
+            p = self._target.params
+            _lib.check(self._libh.bpm_set_target(h, self._target.target_id, _lib.dptr(p), p.size))
+
+    def _bcast_int(self, v):
+        torch = _torch()
+        import torch.distributed as dist
+        t = torch.tensor([v], dtype=torch.int64, device=self._device)
+        dist.broadcast(t, src=0)
+        return int(t.item())
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None:
+                self._libh.bpm_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ chains
+    def init_chains(self, theta_0, varepsilon=1e-6, **kwargs):
+        """demc.py:34-44 + chain.py:25-29: chain c starts at theta_0 + N(0, varepsilon).
+
+        The jitter is drawn on the host from numpy's global stream, chain after chain, so
+        a seeded run starts from the reference's initial states.  (``inflate`` is accepted
+        and ignored, as in the reference.)"""
+        torch = _torch()
+        theta_0 = np.asarray(theta_0, dtype=float).flatten()
+        self.dim = len(theta_0)
+        if self._handle is None:
+            self._create_handle()
+        assert np.all(np.asarray(varepsilon) >= 0.0)
+        N, d, ld = self.n_chains, self.dim, self._ld
+        # every rank draws the jitter of ALL chains so the replicas agree (demc.py seeds
+        # every rank identically as well, tests/test_banana.py:17)
+        x0 = theta_0[None, :] + var_ball_batch(varepsilon, d, N)
+        if self.comm.size > 1:
+            x0t = torch.from_numpy(x0).to(self._device)
+            import torch.distributed as dist
+            dist.broadcast(x0t, src=0)
+            x0 = x0t.cpu().numpy()
+        self._set_population(x0)
+
+    def _set_population(self, x0, history=None):
+        torch = _torch()
+        N, d, ld = self.n_chains, self.dim, self._ld
+        lo, hi = int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
+        nl = hi - lo
+        self._X = torch.zeros((N, ld), dtype=torch.float64, device=self._device)
+        self._X[:, :d] = torch.from_numpy(np.ascontiguousarray(x0)).to(self._device)
+        self._lnl = torch.zeros((N,), dtype=torch.float64, device=self._device)
+        self._mean = self._X[lo:hi].clone()
+        self._m2 = torch.zeros((nl, ld), dtype=torch.float64, device=self._device)
+        self._hist = HistoryStore(nl, d, ld, self._device, policy=self._history_policy,
+                                  chunk_bytes=self._chunk_bytes)
+        self._hist._current = self._X[lo:hi]
+        if history is None:
+            self._hist.set_initial(self._X[lo:hi])
+        else:
+            self._hist.load(history)
+            self._rebuild_moments()
+        self.am_chains = _ChainList(self)
+        self._lnl_valid = False
+        self._moments_len = self._hist.length
+
+    def init_warmstart_chain(self, h5_file):
+        """demc.py:46-51."""
+        self.init_chains(np.zeros(self.dim))
+        self.load_state(h5_file)
+
+    def _get_local_chain_state(self):
+        """demc.py:53-57."""
+        lo, hi = int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
+        return self._X[lo:hi, :self.dim].cpu().numpy()
+
+    # ------------------------------------------------------------------ C-ABI helpers
+    def _stream(self):
+        torch = _torch()
+        return C.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
+
+    def _state(self, hist_base=None):
+        st = _lib.State()
+        st.X = self._X.data_ptr()
+        st.lnl = self._lnl.data_ptr()
+        st.mean = self._mean.data_ptr()
+        st.m2 = self._m2.data_ptr()
+        st.history = hist_base
+        st.hist_len = self._hist.length
+        return st
+
+    def _rebuild_moments(self):
+        """Running mean / M2 of every local chain from the stored history."""
+        h = self._hist.tensor()
+        self._mean = h.mean(dim=0)
+        self._m2 = ((h - self._mean[None]) ** 2).sum(dim=0)
+        self._moments_len = self._hist.length
+
+    def _mode(self):
+        if self._target is not None:
+            return "device"
+        if self._ln_like_batched is not None:
+            return "batched"
+        return "scalar"
+
+    def _eval_lnl_rows(self, rows):
+        """ln_like of a dense [n, ld] device tensor through the active plug-in."""
+        torch = _torch()
+        n = rows.shape[0]
+        mode = self._mode()
+        if mode == "device":
+            out = torch.empty((n,), dtype=torch.float64, device=self._device)
+            _lib.check(self._libh.bpm_eval_lnl(self._handle, rows.data_ptr(), n, out.data_ptr(),
+                                               self._stream()))
+            return out
+        if mode == "batched":
+            out = self._ln_like_batched(rows[:, :self.dim])
+            return out.to(torch.float64).reshape(n).contiguous()
+        host = rows[:, :self.dim].cpu().numpy()
+        vals = np.array([float(self._frozen_ln_like_fn(host[i])) for i in range(n)])
+        return torch.from_numpy(vals).to(self._device)
+
+    def _init_lnl(self):
+        lo, hi = int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
+        self._lnl[lo:hi] = self._eval_lnl_rows(self._X[lo:hi])
+        self._lnl_valid = True
+
+    def _run_params(self, kwargs):
+        flip = float(np.clip(kwargs.get("flip", 0.5), 0.0, 1.0))       # demc.py:73
+        shuffle = 1 if kwargs.get("shuffle", True) else 0               # demc.py:74
+        epsilon = float(kwargs.get("epsilon", 1e-15))                   # demc.py:161
+        gamma = float(kwargs.get("gamma", 0.0) or 0.0)                  # demc.py:162
+        return flip, shuffle, epsilon, 0.0, gamma
+
+    # ------------------------------------------------------------------ sampling
+    def run_mcmc(self, n, **kwargs):
+        self._mcmc_run(n, **kwargs)
+
+    def _n_generations(self, n):
+        """Generations the reference's `while j < int((n - N) / size)` loop performs
+        (demc.py:78-79, j advances by n_local per generation)."""
+        limit = int((n - self.n_chains) / self.comm.size)
+        n_local = len(self.rank_chain_ids)
+        if limit <= 0:
+            return 0
+        return -(-limit // n_local)
+
+    def _mcmc_run(self, n, **kwargs):
+        if not self.am_chains:
+            raise RuntimeError("ERROR: chains not initilized")
+        torch = _torch()
+        self.local_n_accepted = 0
+        self.local_n_rejected = 1
+        _lib.check(self._libh.bpm_reset_counters(self._handle))
+        _lib.check(self._libh.bpm_set_run_params(self._handle, *self._run_params(kwargs)))
+        if not self._lnl_valid:
+            self._init_lnl()
+        if self._moments_len != self._hist.length:
+            self._rebuild_moments()
+        G = self._n_generations(n)
+        replay = kwargs.get("_replay", None)
+        trace = kwargs.get("_trace", None)
+        if replay is not None:
+            G = min(G, len(replay))
+        k_gen = 0
+        k_off = int(kwargs.get("_k_gen0", 0))     # testing hook: start the schedule at k_off
+        mode = self._mode()
+        while k_gen < G:
+            base, avail = self._hist.reserve(G - k_gen)
+            avail = min(avail, G - k_gen)
+            if self.checkpoint > 0:
+                avail = min(avail, self.checkpoint - (k_gen % self.checkpoint))
+            st = self._state(base)
+            if replay is not None:
+                self._replay_generation(st, replay[k_gen], k_gen + k_off, trace)
+                done = 1
+            elif mode == "device" and self.comm.size == 1:
+                done = avail
+                _lib.check(self._libh.bpm_step_generations(self._handle, C.byref(st), k_gen + k_off, done,
+                                                           self._stream()))
+            else:
+                self._split_generation(st, k_gen + k_off)
+                done = 1
+            self._hist.advance(done)
+            self._moments_len = self._hist.length
+            k_gen += done
+            if self.checkpoint > 0 and k_gen % self.checkpoint == 0:        # demc.py:138-140
+                self.save_state(self.h5_file)
+        torch.cuda.synchronize(self._device)
+        self._collect_counters()
+        self.comm.Barrier()
+
+    def _collect_counters(self):
+        """demc.py:143-150 (and the reference's `local_n_rejected = 1` start)."""
+        acc, rej, nan = C.c_uint64(), C.c_uint64(), C.c_int32()
+        _lib.check(self._libh.bpm_get_counters(self._handle, C.byref(acc), C.byref(rej), C.byref(nan)))
+        if nan.value:
+            raise ValueError("probabilities contain NaN")       # numpy's message at samplers.py:336
+        self.local_n_accepted = int(acc.value)
+        self.local_n_rejected = 1 + int(rej.value)
+        if self.comm.size > 1:
+            torch = _torch()
+            import torch.distributed as dist
+            t = torch.tensor([self.local_n_accepted, self.local_n_rejected], dtype=torch.int64,
+                             device=self._device)
+            dist.all_reduce(t)
+            self.n_accepted, self.n_rejected = int(t[0].item()), int(t[1].item())
+        else:
+            self.n_accepted, self.n_rejected = self.local_n_accepted, self.local_n_rejected
+
+    # -- one generation through the split API (user likelihoods, multi-rank) ---------
+    def _split_generation(self, st, k_gen, rp=None):
+        torch = _torch()
+        s = self._stream()
+        lib, h = self._libh, self._handle
+        _lib.check(lib.bpm_begin_generation(h, C.byref(st), k_gen, rp, s))
+        for phase in (0, 1):
+            if self._mode() == "device":
+                # built-in likelihood: the whole half-phase stays inside the library
+                _lib.check(lib.bpm_phase(h, C.byref(st), phase, s))
+                if self.comm.size > 1:
+                    self._allgather_population()
+                continue
+            prop_p, n_p = C.c_void_p(), C.c_int32()
+            _lib.check(lib.bpm_propose(h, C.byref(st), phase, C.byref(prop_p), C.byref(n_p), s))
+            n = n_p.value
+            rows = self._wrap_rows(prop_p.value, n)
+            lnl_prop = self._eval_lnl_rows(rows)
+            if self.comm.size > 1:
+                # rows of chains owned by other ranks were not proposed here; their
+                # likelihood values are ignored by bpm_accept (ownership check in-kernel)
+                pass
+            _lib.check(lib.bpm_accept(h, C.byref(st), phase, lnl_prop.data_ptr(), None, s))
+            if self.comm.size > 1:
+                self._allgather_population()
+        _lib.check(lib.bpm_end_generation(h, C.byref(st), s))
+        if self.comm.size > 1 and self._algo == _lib.BPM_ALGO_DREAM:
+            self._allreduce_cr()
+
+    def _wrap_device(self, ptr, shape):
+        """torch view of library-owned device memory (no copy)."""
+        torch = _torch()
+
+        class _Iface(object):
+            pass
+        o = _Iface()
+        o.__cuda_array_interface__ = dict(shape=tuple(shape), typestr="<f8", data=(int(ptr), False),
+                                          version=2, strides=None)
+        return torch.as_tensor(o, device=self._device)
+
+    def _wrap_rows(self, ptr, n):
+        return self._wrap_device(ptr, (n, self._ld))
+
+    def _allgather_population(self):
+        import torch.distributed as dist
+        lo, hi = int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
+        dist.all_gather_into_tensor(self._X.view(-1), self._X[lo:hi].reshape(-1))
+
+    def _allreduce_cr(self):
+        torch = _torch()
+        import torch.distributed as dist
+        p = C.c_void_p()
+        _lib.check(self._libh.bpm_cr_partials(self._handle, C.byref(p)))
+        t = self._wrap_device(p.value, (2 * self.n_cr,))
+        dist.all_reduce(t)
+        _lib.check(self._libh.bpm_apply_cr(self._handle, self._stream()))
+
+    # -- RNG replay (testing hook: `_replay=[trace, ...]` from oracle/demc_dream.py) ---
+    def _replay_generation(self, st, tr, k_gen, trace_sink):
+        torch = _torch()
+        dev = self._device
+        keep = []
+
+        def dev_arr(a, dt):
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=dt))).to(dev)
+            keep.append(t)
+            return t.data_ptr()
+        rp = _lib.Replay()
+        rp.flip = 1 if tr["flip"] else 0
+        rp.shuffle_idx = dev_arr(tr["shuffle_idx"], np.int32)
+        rp.pairs = dev_arr(tr["pairs"], np.int32)
+        rp.gamma_u = dev_arr(np.nan_to_num(tr["gamma_u"], nan=2.0), np.float64)
+        nrm = np.asarray(tr["nrm"], dtype=np.float64)
+        rp.nrm = dev_arr(nrm, np.float64)
+        rp.accept_u = dev_arr(tr["accept_u"], np.float64)
+        if self._algo == _lib.BPM_ALGO_DREAM:
+            rp.cr_idx = dev_arr(tr["cr_idx"], np.int32)
+            rp.z = dev_arr(tr["z"], np.float64)
+            rp.fallback_dim = dev_arr(tr["fallback_dim"], np.int32)
+            rp.e = dev_arr(tr["e"], np.float64)
+        tro = None
+        if trace_sink is not None:
+            N, d = self.n_chains, self.dim
+            acc = torch.zeros((N,), dtype=torch.int32, device=dev)
+            lp = torch.zeros((N,), dtype=torch.float64, device=dev)
+            pr = torch.zeros((N, d), dtype=torch.float64, device=dev)
+            tro = _lib.TraceOut(acc.data_ptr(), lp.data_ptr(), pr.data_ptr())
+        if self._mode() == "device":
+            _lib.check(self._libh.bpm_step_generation_replay(
+                self._handle, C.byref(st), C.byref(rp), k_gen,
+                C.byref(tro) if tro is not None else None, self._stream()))
+        else:
+            self._split_generation(st, k_gen, rp=C.byref(rp))
+        torch.cuda.synchronize(dev)
+        if trace_sink is not None:
+            trace_sink.append(dict(accept=acc.cpu().numpy(), lnl_prop=lp.cpu().numpy(),
+                                   prop=pr.cpu().numpy(), state=self._X[:, :self.dim].cpu().numpy()))
+
+    def _dump_native_draws(self, k_gen):
+        """Testing / provenance hook: the draws the native Philox stream WILL use for the
+        next generation (absolute index = current chain length), as a trace dict with the
+        keys oracle/replay.py consumes."""
+        torch = _torch()
+        dev, N, d = self._device, self.n_chains, self.dim
+        npair = self._dream_cfg()["del_pairs"] if self._algo == _lib.BPM_ALGO_DREAM else 1
+        i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=dev)      # noqa: E731
+        f64 = lambda *s: torch.zeros(s, dtype=torch.float64, device=dev)    # noqa: E731
+        t = dict(shuffle_idx=i32(N), cr_idx=i32(N), z=f64(N, d), fallback_dim=i32(N),
+                 pairs=i32(N, npair, 2), gamma_u=f64(N), e=f64(N, d), nrm=f64(N, d), accept_u=f64(N))
+        rp = _lib.Replay()
+        for k, v in t.items():
+            setattr(rp, k, v.data_ptr())
+        flip = C.c_int32()
+        st = self._state(None)
+        _lib.check(self._libh.bpm_dump_draws(self._handle, C.byref(st), k_gen, C.byref(rp),
+                                             C.byref(flip), self._stream()))
+        torch.cuda.synchronize(dev)
+        out = dict((k, v.cpu().numpy()) for k, v in t.items())
+        out["flip"] = bool(flip.value)
+        return out
+
+    # ------------------------------------------------------------------ results
+    @property
+    def chain(self):
+        return self.am_chains[0]
+
+    @property
+    def current_pos(self):
+        return self.chain.current_pos
+
+    @property
+    def acceptance_fraction(self):
+        """samplers.py:76-80."""
+        return self.n_accepted / (self.n_accepted + self.n_rejected)
+
+    def param_est(self, n_burn, collection_rank=0):
+        """demc.py:235-248: mean / std over super-chain rows [n_burn:]."""
+        self.comm.Barrier()
+        chain_slice = self.super_chain_mpi(collection_rank)
+        if self.comm.rank == collection_rank:
+            chain_slice = chain_slice[n_burn:, :]
+            return np.mean(chain_slice, axis=0), np.std(chain_slice, axis=0), chain_slice
+        return None, None, None
+
+    def param_est_device(self, n_burn):
+        """Same estimate computed on the GPU without moving the history to the host;
+        returns (mean, std) as numpy arrays of length dim (rank-local chains when sharded)."""
+        h = self._hist.tensor()
+        flat = h[:, :, :self.dim].reshape(-1, self.dim)[n_burn:]
+        return flat.mean(dim=0).cpu().numpy(), flat.std(dim=0, unbiased=False).cpu().numpy()
+
+    def super_chain_mpi(self, collection_rank=0):
+        return self._super_chain(collection_rank)
+
+    @property
+    def super_chain(self):
+        return self._super_chain()
+
+    def _super_chain(self, collection_rank=0):
+        """demc.py:260-270: row t*N + i = chain i at time t."""
+        torch = _torch()
+        h = self._hist.tensor()[:, :, :self.dim]
+        if self.comm.size == 1:
+            return h.reshape(-1, self.dim).cpu().numpy()
+        import torch.distributed as dist
+        parts = [torch.empty_like(h) for _ in range(self.comm.size)]
+        dist.all_gather(parts, h.contiguous())
+        if self.comm.rank != collection_rank:
+            return None
+        full = torch.cat(parts, dim=1)
+        return full.reshape(-1, self.dim).cpu().numpy()
+
+    def gather_all_chains(self, collection_rank=0):
+        return list(self.iter_all_chains(collection_rank))
+
+    def iter_local_chains(self):
+        for chain in self.am_chains:
+            yield chain
+
+    def iter_all_chains(self, collection_rank=0, verbose=0):
+        if verbose:
+            print("Iter all chains on rank: ", self.comm.rank)
+        sys.stdout.flush()
+        for c_id in range(self.n_chains):
+            yield self.get_chain(c_id, collection_rank)
+
+    def get_chain(self, c_id, collection_rank=0, verbose=0):
+        """demc.py:296-325.  Single rank: the local view.  Multi rank: a free-standing
+        host McmcChain on the collection rank, None elsewhere."""
+        assert 0 <= c_id < self.n_chains
+        if self.comm.size == 1:
+            return self.am_chains[c_id]
+        sc = self._super_chain(collection_rank)
+        if self.comm.rank != collection_rank:
+            return None
+        ch = McmcChain(np.zeros(self.dim), varepsilon=0.0, global_id=int(c_id))
+        ch.chain = sc[c_id::self.n_chains, :]
+        return ch
+
+    def get_chain_rank(self, c_id):
+        assert 0 <= c_id < self.n_chains
+        for r, ids in enumerate(np.array_split(np.array(range(self.n_chains)), self.comm.size)):
+            if c_id in ids:
+                return r
+        raise RuntimeError("ERROR: c_id not in global chain ids")
+
+    # ------------------------------------------------------------------ checkpoint
+    def save_state(self, h5_file=""):
+        """demc.py:198-215: one gzip dataset /chains/chain_id_<id> of shape (T, dim)."""
+        import h5py  # lazy: optional dependency
+        if not h5_file:
+            h5_file = self.h5_file
+        sc = self._super_chain(0)
+        if self.comm.rank == 0:
+            with h5py.File(h5_file, "w") as h5f:
+                for c_id in range(self.n_chains):
+                    h5f.create_dataset("/chains/chain_id_" + str(c_id), data=sc[c_id::self.n_chains, :],
+                                       compression="gzip")
+        self.comm.Barrier()
+
+    def load_state(self, h5_file=""):
+        """demc.py:217-233."""
+        import h5py
+        if not h5_file:
+            h5_file = self.h5_file
+        with h5py.File(h5_file, "r") as h5f:
+            chains = [h5f["/chains/chain_id_" + str(int(c))][:] for c in range(self.n_chains)]
+        k_gen = len(chains[0])
+        for ch in chains:
+            if len(ch) != k_gen:
+                raise RuntimeError
+        self.load_history(np.stack(chains, axis=1))
+        self.comm.Barrier()
+
+    def load_history(self, hist):
+        """hist: (T, N, dim) array of every chain's history (what load_state reads)."""
+        hist = np.asarray(hist, dtype=float)
+        assert hist.shape[1] == self.n_chains and hist.shape[2] == self.dim
+        lo, hi = int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
+        self._set_population(hist[-1], history=hist[:, lo:hi, :])

@@ -1,0 +1,229 @@
+"""Native-RNG (Philox) mode on the GPU.
+
+(1) step parity: the device dumps the draws its counter-based stream will use
+    (bpm_dump_draws); the oracle replays them on the CPU; the device's native step must
+    land on the same states (1e-12 relative).
+(2) posterior quality: the reference's own statistical gates (tests/test_banana.py:66-72,
+    tests/test_dblgauss.py:67-69, tests/test_100dgauss.py:67-69) plus Gelman-Rubin
+    R-hat < 1.01.
+(3) size-independent properties at BASELINE.json's full size (10^5 chains x 100-D):
+    fused == split path bit for bit, cached likelihoods == fresh evaluation, history
+    rows == states, running moments == moments of the history, counters add up.
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import replay as orp
+from oracle import targets as otargets
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def _cfg(s):
+    dream = s._algo == 1
+    return dict(algo="dream" if dream else "demc", del_pairs=getattr(s, "del_pairs", 1),
+                n_cr=getattr(s, "n_cr", 1), gamma_scale=getattr(s, "gamma_scale", 1.0), gamma=None,
+                burnin_gen=getattr(s, "burnin_gen", 0), n_cr_gen=getattr(s, "p_cr_update_gen", 0))
+
+
+def _native_vs_oracle(s, oracle_lnl, gens, k0=0, run_kwargs=None):
+    run_kwargs = run_kwargs or {}
+    cfg = _cfg(s)
+    cfg["gamma"] = run_kwargs.get("gamma")
+    N = s.n_chains
+    cr = orp.CrState(cfg["n_cr"]) if cfg["algo"] == "dream" else None
+    if cr is not None:
+        cr.p_cr, cr.delta_m, cr.n_cr_updates = s.p_cr, s.delta_m, s.n_cr_updates
+    lnl = orp.scalar_batch(oracle_lnl)
+    n_acc = 0
+    for g in range(gens):
+        k = k0 + g
+        # run_mcmc sets the run parameters; make the dump see the same ones
+        s.run_mcmc(N, **run_kwargs)                       # zero generations, sets params
+        tr = s._dump_native_draws(k)
+        pre = s._X[:, :s.dim].cpu().numpy()
+        hist = s._hist.tensor()[:, :, :s.dim].cpu().numpy()
+        hv = None
+        if cfg["algo"] == "dream" and hist.shape[0] > cfg["n_cr_gen"]:
+            hv = np.std(hist, axis=0) ** 2.0
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = orp.replay_generation(pre, tr, cfg, lnl, k, hist_var=hv, cr=cr)
+        s.run_mcmc(2 * N, _k_gen0=k, **run_kwargs)         # exactly one native generation
+        got = s._X[:, :s.dim].cpu().numpy()
+        err = np.abs(got - want["state"]) / np.maximum(1.0, np.abs(want["state"]))
+        assert err.max() <= RTOL, "generation %d: max rel err %.3e" % (k, err.max())
+        assert s.n_accepted == int(want["accept"].sum())
+        assert s.n_rejected == 1 + N - int(want["accept"].sum())
+        n_acc += s.n_accepted
+        if cr is not None:
+            np.testing.assert_allclose(s.p_cr, cr.p_cr, rtol=1e-10)
+            assert np.array_equal(s.n_cr_updates, cr.n_cr_updates)
+    return n_acc
+
+
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "split"])
+def test_native_dream_banana_matches_oracle_replay(fused):
+    from bipymc_b200 import DreamMpi, targets
+    np.random.seed(1)
+    s = DreamMpi(targets.Banana_2D().ln_like, [0.0, 0.0], n_chains=11, n_cr_gen=3, burnin_gen=12,
+                 seed=123, fused=fused, varepsilon=0.05)
+    acc = _native_vs_oracle(s, otargets.Banana2D().ln_like, gens=16)
+    assert acc > 0
+
+
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "split"])
+def test_native_demc_bimodal_matches_oracle_replay(fused):
+    from bipymc_b200 import DeMcMpi, targets
+    np.random.seed(2)
+    s = DeMcMpi(targets.BimodeGauss_2D().ln_like, [0.0, 0.0], n_chains=20, seed=7, fused=fused,
+                varepsilon=0.01)
+    _native_vs_oracle(s, otargets.BimodeGauss2D().ln_like, gens=12, run_kwargs=dict(epsilon=1e-6))
+
+
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "split"])
+@pytest.mark.parametrize("dim,n", [(7, 9), (100, 40), (33, 17)])
+def test_native_dream_gauss_matches_oracle_replay(dim, n, fused):
+    from bipymc_b200 import DreamMpi, targets
+    np.random.seed(3)
+    s = DreamMpi(targets.Gauss_100D(dim=dim).ln_like, np.zeros(dim), n_chains=n, n_cr_gen=2,
+                 burnin_gen=1000, seed=99, fused=fused, varepsilon=0.5)
+    _native_vs_oracle(s, otargets.GaussND(dim=dim).ln_like, gens=8, k0=3)
+
+
+def test_native_linefit_matches_oracle_replay():
+    from bipymc_b200 import DreamMpi, targets
+    np.random.seed(4)
+    s = DreamMpi(targets.LineFit().ln_like, [-0.8, 4.5, 0.2], n_chains=12, n_cr_gen=2, burnin_gen=50,
+                 seed=5, varepsilon=1e-4)
+    _native_vs_oracle(s, otargets.LineFit().ln_like, gens=10)
+
+
+def test_seed_reproducible_and_seed_sensitive():
+    from bipymc_b200 import DreamMpi, targets
+    outs = []
+    for seed in (11, 11, 12):
+        np.random.seed(0)
+        s = DreamMpi(targets.Banana_2D().ln_like, [0.0, 0.0], n_chains=64, seed=seed)
+        s.run_mcmc(64 * 40)
+        outs.append(s._hist.tensor().cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+    assert not np.array_equal(outs[0], outs[2])
+
+
+# ---------------------------------------------------------------- posterior gates
+def test_banana_posterior_gates_like_reference_test():
+    """tests/test_banana.py:43-44,66-72: fraction of post-burn-in samples inside the
+    pdf > 0.18 / pdf > 0.018 regions within 0.05 of the truth, DE-MC 20 / DREAM 10 chains."""
+    from bipymc_b200 import DeMcMpi, DreamMpi, targets
+    banana = targets.Banana_2D(sigma1=1.0, sigma2=1.0)
+    np.random.seed(42)
+    y1, y2 = banana.rvs(1000000)
+    f50 = np.count_nonzero(banana.check_prob_lvl(y1, y2, 0.18)) / y1.size
+    f95 = np.count_nonzero(banana.check_prob_lvl(y1, y2, 0.018)) / y1.size
+    n_samples, n_burn = 100000, 20000
+    for s in (DeMcMpi(banana.ln_like, [0.0, 0.0], n_chains=20, seed=1),
+              DreamMpi(banana.ln_like, [0.0, 0.0], n_chains=10, n_cr_gen=50, burnin_gen=2000, seed=2)):
+        s.run_mcmc(n_samples)
+        theta, sig, chain = s.param_est(n_burn=n_burn)
+        assert chain.shape == (n_samples - n_burn, 2)
+        g50 = np.count_nonzero(banana.check_prob_lvl(chain[:, 0], chain[:, 1], 0.18)) / chain.shape[0]
+        g95 = np.count_nonzero(banana.check_prob_lvl(chain[:, 0], chain[:, 1], 0.018)) / chain.shape[0]
+        assert abs(g50 - f50) < 0.05 and abs(g95 - f95) < 0.05
+        assert 0.1 < s.acceptance_fraction < 0.6
+
+
+def test_bimodal_posterior_mean_like_reference_test():
+    """tests/test_dblgauss.py:43-44,67-69: mean = (1.5, 1.5) +- 0.1."""
+    from bipymc_b200 import DeMcMpi, DreamMpi, targets
+    tgt = targets.BimodeGauss_2D()
+    for s in (DeMcMpi(tgt.ln_like, [0.0, 0.0], n_chains=20, seed=3),
+              DreamMpi(tgt.ln_like, [0.0, 0.0], n_chains=10, n_cr_gen=50, burnin_gen=2000, seed=4)):
+        s.run_mcmc(100000)
+        theta, sig, chain = s.param_est(n_burn=40000)
+        assert abs(theta[0] - 1.5) < 0.1 and abs(theta[1] - 1.5) < 0.1
+
+
+def test_large_population_posterior_and_rhat():
+    """Many chains, few generations: mean / covariance of the 2-D banana's underlying
+    Gaussian coordinates within Monte-Carlo error, R-hat < 1.01 over the second half."""
+    from bipymc_b200 import DreamMpi, targets
+    from bipymc_b200.diagnostics import gelman_rubin
+    banana = targets.Banana_2D()
+    np.random.seed(0)
+    N, G = 4096, 1500
+    s = DreamMpi(banana.ln_like, [0.0, 0.0], n_chains=N, seed=21, burnin_gen=300, n_cr_gen=50,
+                 varepsilon=1.0)
+    s.run_mcmc(N * (G + 1))
+    h = s._hist.tensor()[G // 2:, :, :2]
+    rhat = gelman_rubin(h)
+    assert np.all(rhat < 1.01), rhat
+    flat = h.reshape(-1, 2).cpu().numpy()
+    x1, x2 = banana.inv_transform(flat[:, 0], flat[:, 1])
+    # underlying N(0, [[1, .9], [.9, 1]])
+    assert abs(x1.mean()) < 0.02 and abs(x2.mean()) < 0.02
+    c = np.cov(np.stack([x1, x2]))
+    assert abs(c[0, 0] - 1.0) < 0.03 and abs(c[1, 1] - 1.0) < 0.03 and abs(c[0, 1] - 0.9) < 0.03
+
+
+def test_gauss100_posterior_like_reference_test():
+    """tests/test_100dgauss.py:67-69 (mean[0], mean[1] = 0 +- 0.2) on a wide population,
+    plus the marginal variances var_i = i + 1 of d100_gauss.py:16."""
+    from bipymc_b200 import DreamMpi, targets
+    from bipymc_b200.diagnostics import gelman_rubin
+    tgt = targets.Gauss_100D()
+    np.random.seed(0)
+    N, G = 8192, 1600
+    s = DreamMpi(tgt.ln_like, np.zeros(100), n_chains=N, seed=5, burnin_gen=400, n_cr_gen=50,
+                 varepsilon=1.0, history_chunk_bytes=1 << 32)
+    s.run_mcmc(N * (G + 1))
+    h = s._hist.tensor()[G // 2:, :, :100]
+    mean = h.mean(dim=(0, 1)).cpu().numpy()
+    var = h.reshape(-1, 100).var(dim=0).cpu().numpy()
+    assert abs(mean[0]) < 0.2 and abs(mean[1]) < 0.2
+    assert np.all(np.abs(mean) < 0.05 * np.sqrt(np.arange(100) + 1.0) + 0.05)
+    np.testing.assert_allclose(var, np.arange(100) + 1.0, rtol=0.08)
+    assert np.all(gelman_rubin(h) < 1.01)
+    assert 0.05 < s.acceptance_fraction < 0.7
+
+
+# ---------------------------------------------------------------- full-size properties
+def test_full_size_properties_1e5_chains_100d():
+    import torch
+    from bipymc_b200 import DreamMpi, targets
+    tgt = targets.Gauss_100D()
+    N, d, G = 100000, 100, 6
+    runs = []
+    for fused in (True, False):
+        np.random.seed(0)
+        s = DreamMpi(tgt.ln_like, np.zeros(d), n_chains=N, seed=77, burnin_gen=1000, n_cr_gen=2,
+                     fused=fused, varepsilon=1.0)
+        s.run_mcmc(N * (G + 1))
+        runs.append(s)
+    a, b = runs
+    ha, hb = a._hist.tensor(), b._hist.tensor()
+    assert ha.shape == (G + 1, N, d)
+    assert torch.equal(ha, hb), "fused and split paths must agree bit for bit"
+    assert torch.equal(a._lnl, b._lnl)
+    np.testing.assert_allclose(a.p_cr, b.p_cr, rtol=1e-12)
+    # history row G == live population; every chain moved at most once per generation
+    assert torch.equal(ha[G], a._X)
+    # cached likelihood == fresh evaluation of the current state
+    fresh = a._eval_lnl_rows(a._X)
+    assert torch.equal(fresh, a._lnl)
+    # counters add up: every chain stepped once per generation
+    assert a.n_accepted + a.n_rejected == N * G + 1
+    changed = int((ha[1:] != ha[:-1]).any(dim=2).sum().item())
+    assert changed == a.n_accepted
+    # running moments == moments of the stored history
+    mean = ha.mean(dim=0)
+    m2 = ((ha - mean[None]) ** 2).sum(dim=0)
+    assert torch.allclose(a._mean, mean, rtol=1e-12, atol=1e-13)
+    assert torch.allclose(a._m2, m2, rtol=1e-10, atol=1e-12)
+    # the a/b split: within a generation a chain's partners come from the other half, so a
+    # rejected chain is bit-identical to its previous row (no partial writes)
+    same = (ha[1:] == ha[:-1]).all(dim=2)
+    assert int(same.sum().item()) == N * G - a.n_accepted

@@ -1,0 +1,78 @@
+"""The oracle pin: oracle/demc_dream.py must reproduce, BIT FOR BIT, the chains the
+unmodified reference produced for the same seeds (tests/golden/ref_*.npz, written by
+oracle/make_golden.py from /root/reference).  Also pins the replay-driven batched form
+(oracle/replay.py) to the scalar oracle."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle.cases import CASES, oracle_target
+from oracle.demc_dream import OracleSampler
+from oracle import replay as orp
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def run_oracle(name, record=False):
+    case = CASES[name]
+    fn, kw = oracle_target(case["target"])
+    np.random.seed(case["seed"])
+    s = OracleSampler(fn, case["theta_0"], n_chains=case["n_chains"], algo=case["algo"],
+                      ln_kwargs=kw, **case["ctor_kwargs"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tr = s.run(case["n"], record=record, **case["run_kwargs"])
+    return s, tr
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_matches_reference_bit_for_bit(name):
+    g = np.load(os.path.join(GOLD, "ref_%s.npz" % name))
+    s, _ = run_oracle(name)
+    h = s.hist_array
+    assert h.shape == g["history"].shape
+    assert np.array_equal(h, g["history"])
+    assert int(s.n_accepted) == int(g["n_accepted"])
+    assert int(s.n_rejected) == int(g["n_rejected"])
+    assert s.acceptance_fraction == float(g["acceptance_fraction"])
+    if CASES[name]["algo"] == "dream":
+        assert np.array_equal(s.p_cr, g["p_cr"])
+        assert np.array_equal(s.delta_m, g["delta_m"])
+        assert np.array_equal(s.n_cr_updates, g["n_cr_updates"])
+    mean, std, _ = s.param_est(0)
+    assert np.array_equal(mean, g["mean"]) and np.array_equal(std, g["std"])
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_replay_form_matches_scalar_oracle(name):
+    """Feeding the recorded draws to oracle/replay.py reproduces every generation's state
+    and accept flags exactly, and p_cr at generation boundaries to rounding."""
+    case = CASES[name]
+    s, traces = run_oracle(name, record=True)
+    fn, kw = oracle_target(case["target"])
+    lnl = orp.scalar_batch(lambda th: fn(th, **kw))
+    cfg = dict(algo=case["algo"], del_pairs=case["ctor_kwargs"].get("del_pairs", 3),
+               n_cr=case["ctor_kwargs"].get("n_cr", 3),
+               gamma_scale=case["ctor_kwargs"].get("gamma_scale", 1.0),
+               gamma=case["run_kwargs"].get("gamma"),
+               burnin_gen=case["ctor_kwargs"].get("burnin_gen", 300),
+               n_cr_gen=case["ctor_kwargs"].get("n_cr_gen", 50))
+    cr = orp.CrState(cfg["n_cr"]) if case["algo"] == "dream" else None
+    hist = [s.history[0]]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for k, tr in enumerate(traces):
+            hv = None
+            if case["algo"] == "dream" and len(hist) > cfg["n_cr_gen"]:
+                hv = np.std(np.array(hist), axis=0) ** 2.0
+            out = orp.replay_generation(hist[-1], tr, cfg, lnl, k, hist_var=hv, cr=cr)
+            assert np.array_equal(out["state"], tr["state"]), "generation %d" % k
+            assert np.array_equal(out["accept"], tr["accept"])
+            assert np.array_equal(out["prop"], tr["prop"])
+            if cr is not None:
+                np.testing.assert_allclose(cr.p_cr, tr["p_cr"], rtol=1e-12)
+                np.testing.assert_allclose(cr.delta_m, tr["delta_m"], rtol=1e-12)
+                assert np.array_equal(cr.n_cr_updates, tr["n_cr_updates"])
+            hist.append(out["state"])

@@ -1,0 +1,138 @@
+"""RNG-replay parity on the GPU: the CUDA generation step, fed the numpy draws the
+reference consumed, must reproduce the reference's accept decisions step for step and
+its chain states to 1e-12 relative (fp64) -- checked against the committed golden
+histories written by the unmodified reference (tests/golden/ref_*.npz) and against the
+oracle's per-step trace."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle.cases import CASES, oracle_target
+from oracle.demc_dream import OracleSampler
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-12        # north_star: chain states within 1e-12 relative
+
+
+def device_target(name):
+    from bipymc_b200 import targets
+    if name == "banana":
+        return targets.Banana_2D(sigma1=1.0, sigma2=1.0)
+    if name == "dblgauss":
+        return targets.BimodeGauss_2D()
+    if name.startswith("gauss"):
+        return targets.Gauss_100D(dim=int(name[5:]))
+    if name == "linefit":
+        return targets.LineFit()
+    raise KeyError(name)
+
+
+def oracle_traces(name):
+    case = CASES[name]
+    fn, kw = oracle_target(case["target"])
+    np.random.seed(case["seed"])
+    s = OracleSampler(fn, case["theta_0"], n_chains=case["n_chains"], algo=case["algo"],
+                      ln_kwargs=kw, **case["ctor_kwargs"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tr = s.run(case["n"], record=True, **case["run_kwargs"])
+    return s, tr
+
+
+def make_sampler(name, mode, fused=True):
+    from bipymc_b200 import DeMcMpi, DreamMpi
+    case = CASES[name]
+    cls = DreamMpi if case["algo"] == "dream" else DeMcMpi
+    np.random.seed(case["seed"])
+    kw = dict(case["ctor_kwargs"])
+    ln_kwargs = {}
+    if mode == "device":
+        fn = device_target(case["target"]).ln_like
+    elif mode == "scalar":
+        fn, ln_kwargs = oracle_target(case["target"])        # plain Python callable
+    elif mode == "batched":
+        import torch
+        tgt = device_target(case["target"])
+        fn = tgt.ln_like
+
+        def batched(theta):                                   # torch in, torch out
+            host = theta.cpu().numpy()
+            return torch.tensor([float(tgt.ln_like(r)) for r in host], dtype=torch.float64,
+                                device=theta.device)
+        kw["ln_like_batched"] = batched
+        fn = lambda th: tgt.ln_like(th)                       # noqa: E731  hides device_target()
+    return cls(fn, np.asarray(case["theta_0"], dtype=float), n_chains=case["n_chains"],
+               ln_kwargs=ln_kwargs, fused=fused, **kw)
+
+
+def check_against_reference(name, s, sink, traces, osampler):
+    case = CASES[name]
+    g = np.load(os.path.join(GOLD, "ref_%s.npz" % name))
+    ref = g["history"]
+    hist = s._hist.tensor()[:, :, :s.dim].cpu().numpy()
+    assert hist.shape == ref.shape
+    # initial states come from the same numpy stream: exact
+    assert np.array_equal(hist[0], ref[0])
+    # accept decisions: step for step
+    n_flip = 0
+    for k, (got, tr) in enumerate(zip(sink, traces)):
+        n_flip += int(np.count_nonzero(got["accept"] != tr["accept"]))
+    assert n_flip == 0, "%d accept decisions differ from the reference" % n_flip
+    err = np.abs(hist - ref) / np.maximum(1.0, np.abs(ref))
+    assert err.max() <= RTOL, "max relative state error %.3e" % err.max()
+    # proposals and their likelihoods, every step
+    for got, tr in zip(sink, traces):
+        perr = np.abs(got["prop"] - tr["prop"]) / np.maximum(1.0, np.abs(tr["prop"]))
+        assert perr.max() <= RTOL
+        fin = np.isfinite(tr["lnl_prop"])
+        assert np.array_equal(np.isfinite(got["lnl_prop"]), fin) or case["target"] in ("banana", "dblgauss")
+        both = fin & np.isfinite(got["lnl_prop"])
+        lerr = np.abs(got["lnl_prop"][both] - tr["lnl_prop"][both])
+        assert lerr.max() <= 1e-9 * np.maximum(1.0, np.abs(tr["lnl_prop"][both])).max()
+    assert s.n_accepted == int(g["n_accepted"])
+    assert s.n_rejected == int(g["n_rejected"])
+    assert s.acceptance_fraction == float(g["acceptance_fraction"])
+    if case["algo"] == "dream":
+        np.testing.assert_allclose(s.p_cr, g["p_cr"], rtol=1e-10)
+        np.testing.assert_allclose(s.delta_m, g["delta_m"], rtol=1e-10)
+        assert np.array_equal(s.n_cr_updates, g["n_cr_updates"])
+    mean, std, sl = s.param_est(n_burn=0)
+    np.testing.assert_allclose(mean, g["mean"], rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(std, g["std"], rtol=1e-10, atol=1e-12)
+    assert sl.shape == (ref.shape[0] * ref.shape[1], ref.shape[2])
+    # McmcChain view = column of the history
+    c = s.am_chains[1]
+    assert c.global_id == 1 and np.array_equal(c.chain, hist[:, 1, :])
+    assert np.array_equal(c.current_pos, hist[-1, 1, :]) and c.chain_len == ref.shape[0]
+
+
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "split"])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_replay_device_target(name, fused):
+    osampler, traces = oracle_traces(name)
+    s = make_sampler(name, "device", fused=fused)
+    sink = []
+    s.run_mcmc(CASES[name]["n"], _replay=traces, _trace=sink, **CASES[name]["run_kwargs"])
+    check_against_reference(name, s, sink, traces, osampler)
+
+
+@pytest.mark.parametrize("mode", ["scalar", "batched"])
+@pytest.mark.parametrize("name", ["banana_demc", "banana_dream_odd", "gauss7_dream_noshuffle",
+                                  "linefit_dream"])
+def test_replay_user_likelihoods(name, mode):
+    """The reference's scalar ln_like_fn(theta, **kw) plug-in and the new batched torch
+    plug-in go through bpm_propose / bpm_accept; with a host likelihood the result is the
+    reference's to the last bit of the likelihood, so accept flags and states match."""
+    osampler, traces = oracle_traces(name)
+    s = make_sampler(name, mode)
+    assert s._mode() == mode
+    sink = []
+    s.run_mcmc(CASES[name]["n"], _replay=traces, _trace=None, **CASES[name]["run_kwargs"])
+    g = np.load(os.path.join(GOLD, "ref_%s.npz" % name))
+    hist = s._hist.tensor()[:, :, :s.dim].cpu().numpy()
+    err = np.abs(hist - g["history"]) / np.maximum(1.0, np.abs(g["history"]))
+    assert err.max() <= RTOL
+    assert s.n_accepted == int(g["n_accepted"]) and s.n_rejected == int(g["n_rejected"])
