@@ -152,7 +152,7 @@ def run_ours(args):
     K, W = args.steps, args.warmup
     s = DreamMpi(tgt.ln_like, np.zeros(DIM), n_chains=N, varepsilon=np.arange(DIM) + 1.0, seed=42,
                  n_cr_gen=50, burnin_gen=2000, device=local_rank,
-                 history=args.history, history_chunk_bytes=(K + W + SETUP_GENS + 4) * (N // world) * DIM * 8)
+                 history=args.history, history_reserve=K + W + SETUP_GENS + 8)
     lib, h = s._libh, s._handle
     n_local = len(s.rank_chain_ids)
 

@@ -59,6 +59,7 @@ struct bpm_engine {
   double* cr_dm = nullptr;
   double* cr_cnt = nullptr;
   double* cr_part = nullptr;
+  double* cr_block = nullptr;
   unsigned long long* counters = nullptr;  // [0] accepted, [1] rejected
   int32_t* nan_flag = nullptr;
   // target
@@ -67,7 +68,7 @@ struct bpm_engine {
   bpm::BimodalParams bimodal;
   double* tparams = nullptr;  // device copy of gauss / linefit parameters
   int64_t n_tparams = 0;
-  int gauss_r = 0, gauss_logpdf_flag = 0;
+  int gauss_r = 0, gauss_logpdf_flag = 0, gauss_mu_zero = 0;
   double gauss_c0 = 0.0;
   int linefit_M = 0;
   bpm_lnl_fn user_fn = nullptr;
@@ -103,7 +104,7 @@ struct bpm_engine {
 
   ~bpm_engine() {
     cudaFree(perm); cudaFree(flip); cudaFree(prop); cudaFree(lnl_prop); cudaFree(cr_delta);
-    cudaFree(cr_pick); cudaFree(p_cr); cudaFree(cr_dm); cudaFree(cr_cnt); cudaFree(cr_part);
+    cudaFree(cr_pick); cudaFree(p_cr); cudaFree(cr_dm); cudaFree(cr_cnt); cudaFree(cr_part); cudaFree(cr_block);
     cudaFree(counters); cudaFree(nan_flag); cudaFree(tparams); cudaFree(hX); cudaFree(hL);
     for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ev_pool) cudaEventDestroy(e);
@@ -123,6 +124,7 @@ struct bpm_engine {
     CU_TRY(cudaMalloc(&cr_dm, sizeof(double) * BPM_MAX_CR));
     CU_TRY(cudaMalloc(&cr_cnt, sizeof(double) * BPM_MAX_CR));
     CU_TRY(cudaMalloc(&cr_part, sizeof(double) * 2 * BPM_MAX_CR));
+    CU_TRY(cudaMalloc(&cr_block, sizeof(double) * 2 * BPM_MAX_CR * bpm::kCrBlocks));
     CU_TRY(cudaMalloc(&counters, sizeof(unsigned long long) * 2));
     CU_TRY(cudaMalloc(&nan_flag, sizeof(int32_t)));
     CU_TRY(cudaMemset(flip, 0, sizeof(int32_t)));
@@ -144,6 +146,7 @@ struct bpm_engine {
     bpm::PhaseArgs a;
     memset(&a, 0, sizeof(a));
     a.X = st->X; a.lnl = st->lnl; a.mean = st->mean; a.m2 = st->m2;
+    a.hist_base = (rp && st->history) ? st->history : nullptr;
     a.hist_row = st->history ? st->history + (size_t)st->hist_len * (cfg.chain_hi - cfg.chain_lo) * cfg.ld
                              : nullptr;
     a.perm = perm; a.flip = flip; a.phase = phase;
@@ -231,9 +234,11 @@ struct bpm_engine {
       case BPM_TARGET_GAUSS: {
         const double* mu = tparams;
         const double* W = tparams + cfg.dim;
-        if (fused_ok && bpm::gauss_rows_supported(cfg.dim, gauss_r))
-          BPM_TRY(bpm::launch_gauss_rows(P, n, ld, cfg.dim, gauss_r, mu, W, gauss_c0,
-                                         gauss_logpdf_flag, out, s));
+        if (bpm::gauss_rows_supported(cfg.dim, gauss_r)) {
+          if (bpm::launch_gauss_rows(P, n, ld, cfg.dim, gauss_r, mu, W, gauss_c0, gauss_logpdf_flag,
+                                     gauss_mu_zero, out, s))
+            return fail("gauss rows kernel launch failed");
+        }
         else
           bpm::lnl_gauss_tiled_kernel<<<cdiv(n, 64), 256, 0, s>>>(P, n, ld, cfg.dim, gauss_r, mu, W,
                                                                   gauss_c0, gauss_logpdf_flag, out);
@@ -260,8 +265,12 @@ struct bpm_engine {
   int end(cudaStream_t s) {
     if (cfg.algo != BPM_ALGO_DREAM) return 0;
     prof_begin(5, s);
-    bpm::cr_reduce_kernel<<<1, 1024, 0, s>>>(cr_delta, cr_pick, cfg.chain_lo, cfg.chain_hi, cfg.n_cr,
-                                             cr_part);
+    const int nloc = cfg.chain_hi - cfg.chain_lo;
+    int nb = cdiv(nloc, 2048);
+    if (nb > bpm::kCrBlocks) nb = bpm::kCrBlocks;
+    bpm::cr_reduce_kernel<<<nb, 256, 0, s>>>(cr_delta, cr_pick, cfg.chain_lo, cfg.chain_hi, cfg.n_cr,
+                                             cr_block);
+    bpm::cr_finish_kernel<<<1, 32, 0, s>>>(cr_block, nb, cfg.n_cr, cr_part);
     CU_TRY(cudaGetLastError());
     const bool sharded = cfg.chain_lo != 0 || cfg.chain_hi != cfg.n_chains;
     if (!sharded) {  // multi-rank hosts all-reduce cr_part first, then call bpm_apply_cr
@@ -306,6 +315,7 @@ struct bpm_engine {
     tv.r = gauss_r;
     tv.c0 = gauss_c0;
     tv.log_of_pdf = gauss_logpdf_flag;
+    tv.mu_is_zero = gauss_mu_zero;
     tv.linefit = tparams;
     tv.linefit_M = linefit_M;
     return &tv;
@@ -403,6 +413,8 @@ int bpm_set_target(bpm_handle h, int32_t target, const double* params, int64_t n
       const int r = (int)params[2];
       if (r < 1 || n != 3 + d + (int64_t)d * r) return fail("gauss: parameter count mismatch");
       h->gauss_logpdf_flag = params[0] != 0.0; h->gauss_c0 = params[1]; h->gauss_r = r;
+      h->gauss_mu_zero = 1;
+      for (int i = 0; i < d; ++i) if (params[3 + i] != 0.0) h->gauss_mu_zero = 0;
       cudaFree(h->tparams); h->tparams = nullptr;
       CU_TRY(cudaMalloc(&h->tparams, sizeof(double) * (n - 3)));
       CU_TRY(cudaMemcpy(h->tparams, params + 3, sizeof(double) * (n - 3), cudaMemcpyHostToDevice));

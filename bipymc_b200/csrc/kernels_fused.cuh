@@ -1,4 +1,22 @@
-// Fused single-kernel half-phase variants (proposal + likelihood + accept in one launch).
+// Fused half-phase kernels: RNG + proposal + likelihood + Metropolis accept + in-place
+// state / moments / history update in ONE launch (demc.py:153-196, dream.py:32-107 for a
+// whole half of the population).
+//
+//  * fused_gauss_kernel  -- correlated-Gaussian target, d <= 112 (the 100-D headline
+//    case).  One persistent 512-thread CTA per SM; its two 256-thread halves work on
+//    different 64-chain tiles with their own named barrier, sharing one copy of the
+//    whitening matrix W (d x 112 doubles) in shared memory, so the HBM gather stage of
+//    one half overlaps the FP64 quadratic-form stage of the other.
+//      stage A  warp-per-chain: Philox draws, 7 coalesced row gathers, proposal -> smem tile
+//      stage B  Y = (P - mu) W as a register-tiled DFMA GEMM straight from smem
+//               (lanes = rows, warps = 14-column strips), folded into row sums of squares.
+//               B200 measures the same 36.5 TFLOP/s through DFMA and through DMMA
+//               (mma.sync m8n8k4 f64; tcgen05 has no FP64 kind), so the plain pipe is used.
+//      stage C  accept / reject, state + lnL + Welford moments + history row written once
+//  * fused_small_kernel  -- d <= 4 analytic targets (banana, bimodal, line fit),
+//    thread-per-chain.
+// Both share every draw / arithmetic helper with the generic split path (step.cuh), so
+// the chains they produce are bit-identical to it.
 #pragma once
 #include <cuda_runtime.h>
 #include "step.cuh"
@@ -15,17 +33,540 @@ struct TargetView {
   int r;
   double c0;
   int log_of_pdf;
+  int mu_is_zero;
   const double* linefit;
   int linefit_M;
 };
 
-inline bool gauss_rows_supported(int, int) { return false; }
-inline int launch_gauss_rows(const double*, int, int, int, int, const double*, const double*, double,
-                             int, double*, cudaStream_t) { return 1; }
+constexpr int kTileRows = 64;    // chains per tile
+constexpr int kColStrip = 14;    // columns per warp in the quadratic form
+constexpr int kWld = 8 * kColStrip;  // padded row length of W in shared memory (112)
+constexpr int kHalfThreads = 256;
+
+__device__ __forceinline__ void half_barrier(int half) {
+  asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "r"(kHalfThreads) : "memory");
+}
+
+// Row sums of squares of (P - mu) . W for a 64-row tile held in shared memory.
+//   P     [64][pld]   row-major, pld odd (conflict-free column walks)
+//   Ws    [d][112]    zero-padded columns
+//   part  [8][64]     per-warp partial sums, summed in warp order by the caller
+// 256 threads: lane = row (and row + 32), warp = 14-column strip.
+template <bool CENTER>
+__device__ __forceinline__ void gauss_tile_rowsums(const double* __restrict__ P, int pld,
+                                                   const double* __restrict__ Ws,
+                                                   const double* __restrict__ mus, int d,
+                                                   double* __restrict__ part, int warp, int lane) {
+  double a0[kColStrip], a1[kColStrip];
+#pragma unroll
+  for (int q = 0; q < kColStrip; ++q) a0[q] = a1[q] = 0.0;
+  const double* p0 = P + lane * pld;
+  const double* p1 = P + (lane + 32) * pld;
+  const double2* wv = reinterpret_cast<const double2*>(Ws + warp * kColStrip);
+#pragma unroll 2
+  for (int k = 0; k < d; ++k) {
+    double x0 = p0[k], x1 = p1[k];
+    if (CENTER) {
+      const double m = mus[k];
+      x0 = __dsub_rn(x0, m);
+      x1 = __dsub_rn(x1, m);
+    }
+#pragma unroll
+    for (int q = 0; q < kColStrip / 2; ++q) {
+      const double2 b = wv[k * (kWld / 2) + q];
+      a0[2 * q] = fma(x0, b.x, a0[2 * q]);
+      a0[2 * q + 1] = fma(x0, b.y, a0[2 * q + 1]);
+      a1[2 * q] = fma(x1, b.x, a1[2 * q]);
+      a1[2 * q + 1] = fma(x1, b.y, a1[2 * q + 1]);
+    }
+  }
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+  for (int q = 0; q < kColStrip; ++q) {
+    s0 = fma(a0[q], a0[q], s0);
+    s1 = fma(a1[q], a1[q], s1);
+  }
+  part[warp * kTileRows + lane] = s0;
+  part[warp * kTileRows + lane + 32] = s1;
+}
+
+__device__ __forceinline__ double gauss_tile_finish(const double* __restrict__ part, int row, double c0,
+                                                    int log_of_pdf) {
+  double maha = part[row];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) maha = __dadd_rn(maha, part[w * kTileRows + row]);
+  return gauss_finish(c0, maha, log_of_pdf);
+}
+
+__device__ __forceinline__ void load_W_shared(double* Ws, double* mus, const double* __restrict__ W,
+                                              const double* __restrict__ mu, int d, int r, int tid,
+                                              int nthreads) {
+  for (int idx = tid; idx < d * kWld; idx += nthreads) {
+    const int k = idx / kWld, j = idx - k * kWld;
+    Ws[idx] = j < r ? W[(size_t)k * r + j] : 0.0;
+  }
+  for (int k = tid; k < d; k += nthreads) mus[k] = mu[k];
+}
+
+inline bool gauss_rows_supported(int d, int r) { return d <= 112 && r <= kWld && d >= 5; }
+inline int gauss_pld(int d) { return d | 1; }
+
+// ---- stand-alone batched likelihood with the same tile arithmetic ------------------
+template <bool CENTER>
+__global__ void __launch_bounds__(kHalfThreads, 1)
+gauss_rows_kernel(const double* __restrict__ X, int n, int ld, int d, int r, const double* __restrict__ mu,
+                  const double* __restrict__ W, double c0, int log_of_pdf, double* __restrict__ out) {
+  extern __shared__ __align__(16) double smem[];
+  const int pld = d | 1;
+  double* Ws = smem;
+  double* mus = Ws + d * kWld;
+  double* P = mus + ((d + 1) & ~1);
+  double* part = P + kTileRows * pld;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  load_W_shared(Ws, mus, W, mu, d, r, threadIdx.x, kHalfThreads);
+  const int n_tiles = (n + kTileRows - 1) / kTileRows;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < kTileRows * d; idx += kHalfThreads) {
+      const int rr = idx / d, k = idx - rr * d;
+      const int row = tile * kTileRows + rr;
+      P[rr * pld + k] = row < n ? X[(size_t)row * ld + k] : 0.0;
+    }
+    __syncthreads();
+    gauss_tile_rowsums<CENTER>(P, pld, Ws, mus, d, part, warp, lane);
+    __syncthreads();
+    if (threadIdx.x < kTileRows) {
+      const int row = tile * kTileRows + threadIdx.x;
+      if (row < n) out[row] = gauss_tile_finish(part, threadIdx.x, c0, log_of_pdf);
+    }
+  }
+}
+
+inline size_t gauss_rows_smem(int d) {
+  return sizeof(double) * ((size_t)d * kWld + ((d + 1) & ~1) + (size_t)kTileRows * gauss_pld(d) +
+                           8 * kTileRows);
+}
+
+inline int launch_gauss_rows(const double* X, int n, int ld, int d, int r, const double* mu,
+                             const double* W, double c0, int log_of_pdf, int mu_is_zero, double* out,
+                             cudaStream_t s) {
+  const size_t sm = gauss_rows_smem(d);
+  const int n_tiles = (n + kTileRows - 1) / kTileRows;
+  const int grid = n_tiles < 148 ? n_tiles : 148;
+  cudaError_t e;
+  if (mu_is_zero) {
+    e = cudaFuncSetAttribute(gauss_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return 1;
+    gauss_rows_kernel<false><<<grid, kHalfThreads, sm, s>>>(X, n, ld, d, r, mu, W, c0, log_of_pdf, out);
+  } else {
+    e = cudaFuncSetAttribute(gauss_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return 1;
+    gauss_rows_kernel<true><<<grid, kHalfThreads, sm, s>>>(X, n, ld, d, r, mu, W, c0, log_of_pdf, out);
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// ---- the fused Gaussian half-phase ----------------------------------------------------
+struct GaussArgs {
+  const double* mu;
+  const double* W;
+  int r;
+  double c0;
+  int log_of_pdf;
+};
+
+template <bool REPLAY, bool CENTER>
+__global__ void __launch_bounds__(2 * kHalfThreads, 1)
+fused_gauss_kernel(const PhaseArgs a, const GaussArgs g) {
+  extern __shared__ __align__(16) double smem[];
+  const int d = a.d, pld = d | 1;
+  double* Ws = smem;
+  double* mus = Ws + d * kWld;
+  double* half_base = mus + ((d + 1) & ~1);
+  const int half = threadIdx.x >> 8;
+  const int tid = threadIdx.x & (kHalfThreads - 1);
+  const int warp = tid >> 5, lane = tid & 31;
+  const size_t half_doubles = (size_t)kTileRows * pld + 8 * kTileRows + kTileRows + kTileRows / 2;
+  double* P = half_base + half * half_doubles;
+  double* part = P + kTileRows * pld;
+  double* lnl_s = part + 8 * kTileRows;
+  int* cid_s = reinterpret_cast<int*>(lnl_s + kTileRows);
+
+  load_W_shared(Ws, mus, g.W, g.mu, d, g.r, threadIdx.x, 2 * kHalfThreads);
+  __syncthreads();
+
+  const PhaseLists L = phase_lists(a);
+  const bool dream = a.algo == BPM_ALGO_DREAM;
+  const int npair = dream ? a.del_pairs : 1;
+  const int n_tiles = (L.n_self + kTileRows - 1) / kTileRows;
+  const double inv_T = 1.0 / (double)a.hist_len;
+  const double n1 = (double)(a.hist_len + 1);
+  const int blk = lane;                  // this lane's dimension block (4 doubles)
+  const bool has_blk = 4 * blk < d;
+  unsigned n_acc = 0, n_rej = 0;
+
+  for (int tile = blockIdx.x * 2 + half; tile < n_tiles; tile += 2 * gridDim.x) {
+    // ---------------- stage A: draws, gathers, proposal ------------------------------
+    for (int jj = 0; jj < kTileRows / 8; ++jj) {
+      const int row = warp * (kTileRows / 8) + jj;
+      const int gid = tile * kTileRows + row;
+      bool valid = gid < L.n_self;
+      const int c = valid ? L.self[gid] : 0;
+      valid = valid && c >= a.chain_lo && c < a.chain_hi;
+      double* prow = P + row * pld;
+      if (!valid) {
+        if (lane == 0) cid_s[row] = -1;
+        if (has_blk)
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (4 * blk + q < d) prow[4 * blk + q] = 0.0;
+        continue;
+      }
+      ChainDraws D;
+      chain_scalar_draws<REPLAY>(a, c, L.n_pool, D);
+      uint32_t mbits = 0xFu;
+      double gamma;
+      if (dream) {
+        mbits = 0u;
+        const double cr = __ddiv_rn((double)(D.cr_idx + 1), (double)a.n_cr);
+        if (has_blk) {
+          double z[4];
+          z4<REPLAY>(a, c, blk, z);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (4 * blk + q < d && z[q] <= cr) mbits |= 1u << q;
+        }
+        int d_prime = __reduce_add_sync(0xFFFFFFFFu, __popc(mbits));
+        if (d_prime == 0) {
+          const int fb = D.fallback < 0 ? 0 : D.fallback;
+          if ((fb >> 2) == blk) mbits |= 1u << (fb & 3);
+          d_prime = 1;
+        }
+        gamma = dream_gamma(a, d_prime, D.gamma_u);
+      } else {
+        gamma = demc_gamma(a, D.gamma_u);
+      }
+      double delta = 0.0;
+      if (has_blk) {
+        const double* xc = a.X + (size_t)c * a.ld + 4 * blk;
+        double cur[4], S[4];
+        const bool full = 4 * blk + 3 < d;
+        if (full) {
+          const double2 u0 = *reinterpret_cast<const double2*>(xc);
+          const double2 u1 = *reinterpret_cast<const double2*>(xc + 2);
+          cur[0] = u0.x; cur[1] = u0.y; cur[2] = u1.x; cur[3] = u1.y;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) cur[q] = 4 * blk + q < d ? xc[q] : 0.0;
+        }
+#pragma unroll
+        for (int p = 0; p < BPM_MAX_PAIRS; ++p) {
+          if (p < npair) {
+            const double* pa = a.X + (size_t)L.pool[D.r1[p]] * a.ld + 4 * blk;
+            const double* pb = a.X + (size_t)L.pool[D.r2[p]] * a.ld + 4 * blk;
+            double va[4], vb[4];
+            if (full) {
+              const double2 s0 = *reinterpret_cast<const double2*>(pa);
+              const double2 s1 = *reinterpret_cast<const double2*>(pa + 2);
+              const double2 t0 = *reinterpret_cast<const double2*>(pb);
+              const double2 t1 = *reinterpret_cast<const double2*>(pb + 2);
+              va[0] = s0.x; va[1] = s0.y; va[2] = s1.x; va[3] = s1.y;
+              vb[0] = t0.x; vb[1] = t0.y; vb[2] = t1.x; vb[3] = t1.y;
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                va[q] = 4 * blk + q < d ? pa[q] : 0.0;
+                vb[q] = 4 * blk + q < d ? pb[q] : 0.0;
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const double df = __dsub_rn(va[q], vb[q]);
+              S[q] = p == 0 ? df : __dadd_rn(S[q], df);
+            }
+          }
+        }
+        double e[4] = {0, 0, 0, 0}, nn[4];
+        if (dream) e4<REPLAY>(a, c, blk, e);
+        n4<REPLAY>(a, c, blk, nn);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = 4 * blk + q;
+          if (i < d) {
+            double pr;
+            if (dream) {
+              pr = dream_prop(cur[q], S[q], e[q], nn[q], gamma, (mbits >> q) & 1u ? 1.0 : 0.0);
+              if (a.adapt) delta += cr_term(cur[q], pr, cr_variance<REPLAY>(a, c, i));
+            } else {
+              pr = demc_prop(cur[q], S[q], nn[q], gamma);
+            }
+            prow[i] = pr;
+          }
+        }
+      }
+      if (dream) {
+        delta = group_sum_d<32>(delta);
+        if (lane == 0) {
+          a.cr_pick[c] = a.adapt ? D.cr_idx : -1;
+          a.cr_delta[c] = delta;
+        }
+      }
+      if (lane == 0) cid_s[row] = c;
+    }
+    half_barrier(half);
+    // ---------------- stage B: quadratic form ----------------------------------------
+    gauss_tile_rowsums<CENTER>(P, pld, Ws, mus, d, part, warp, lane);
+    half_barrier(half);
+    if (tid < kTileRows) lnl_s[tid] = gauss_tile_finish(part, tid, g.c0, g.log_of_pdf);
+    half_barrier(half);
+    // ---------------- stage C: accept / reject and the single write-back ---------------
+    for (int jj = 0; jj < kTileRows / 8; ++jj) {
+      const int row = warp * (kTileRows / 8) + jj;
+      const int c = cid_s[row];
+      if (c < 0) continue;
+      const double lp = lnl_s[row];
+      const double u = accept_uniform<REPLAY>(a, c);
+      int acc = metropolis(a.lnl[c], lp, u);
+      if (acc < 0) {
+        if (lane == 0) *a.nan_flag = 1;
+        acc = 0;
+      }
+      if (has_blk) {
+        double* xc = a.X + (size_t)c * a.ld + 4 * blk;
+        const double* prow = P + row * pld + 4 * blk;
+        const size_t o = (size_t)(c - a.chain_lo) * a.ld + 4 * blk;
+        const bool full = 4 * blk + 3 < d;
+        double s[4];
+        if (acc) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) s[q] = 4 * blk + q < d ? prow[q] : 0.0;
+          if (full) {
+            *reinterpret_cast<double2*>(xc) = make_double2(s[0], s[1]);
+            *reinterpret_cast<double2*>(xc + 2) = make_double2(s[2], s[3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (4 * blk + q < d) xc[q] = s[q];
+          }
+        } else if (a.mean || a.hist_row) {
+          if (full) {
+            const double2 u0 = *reinterpret_cast<const double2*>(xc);
+            const double2 u1 = *reinterpret_cast<const double2*>(xc + 2);
+            s[0] = u0.x; s[1] = u0.y; s[2] = u1.x; s[3] = u1.y;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s[q] = 4 * blk + q < d ? xc[q] : 0.0;
+          }
+        }
+        if (a.mean) {
+          if (full) {
+            double2 m0 = *reinterpret_cast<const double2*>(a.mean + o);
+            double2 m1 = *reinterpret_cast<const double2*>(a.mean + o + 2);
+            double2 v0 = *reinterpret_cast<const double2*>(a.m2 + o);
+            double2 v1 = *reinterpret_cast<const double2*>(a.m2 + o + 2);
+            welford_update(s[0], n1, m0.x, v0.x);
+            welford_update(s[1], n1, m0.y, v0.y);
+            welford_update(s[2], n1, m1.x, v1.x);
+            welford_update(s[3], n1, m1.y, v1.y);
+            *reinterpret_cast<double2*>(a.mean + o) = m0;
+            *reinterpret_cast<double2*>(a.mean + o + 2) = m1;
+            *reinterpret_cast<double2*>(a.m2 + o) = v0;
+            *reinterpret_cast<double2*>(a.m2 + o + 2) = v1;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (4 * blk + q < d) {
+                double mu = a.mean[o + q], v = a.m2[o + q];
+                welford_update(s[q], n1, mu, v);
+                a.mean[o + q] = mu;
+                a.m2[o + q] = v;
+              }
+          }
+        }
+        if (a.hist_row) {
+          if (full) {
+            *reinterpret_cast<double2*>(a.hist_row + o) = make_double2(s[0], s[1]);
+            *reinterpret_cast<double2*>(a.hist_row + o + 2) = make_double2(s[2], s[3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (4 * blk + q < d) a.hist_row[o + q] = s[q];
+          }
+        }
+      }
+      if (lane == 0) {
+        if (acc) a.lnl[c] = lp;
+        if (a.tr.accept) a.tr.accept[c] = acc;
+        if (a.tr.lnl_prop) a.tr.lnl_prop[c] = lp;
+        n_acc += acc;
+        n_rej += !acc;
+      }
+    }
+    half_barrier(half);   // the tile buffers are reused by the next iteration
+  }
+  if (lane == 0) {
+    if (n_acc) atomicAdd(a.n_acc, (unsigned long long)n_acc);
+    if (n_rej) atomicAdd(a.n_rej, (unsigned long long)n_rej);
+  }
+}
+
+inline size_t fused_gauss_smem(int d) {
+  const size_t half_doubles = (size_t)kTileRows * gauss_pld(d) + 8 * kTileRows + kTileRows + kTileRows / 2;
+  return sizeof(double) * ((size_t)d * kWld + ((d + 1) & ~1) + 2 * half_doubles);
+}
+
+// ---- d <= 4 analytic targets: one thread per chain ------------------------------------
+template <bool REPLAY, int TARGET>
+__global__ void __launch_bounds__(128) fused_small_kernel(const PhaseArgs a, const TargetView tv) {
+  extern __shared__ __align__(16) double sdata[];
+  if (TARGET == BPM_TARGET_LINEFIT) {
+    for (int i = threadIdx.x; i < 3 * tv.linefit_M; i += blockDim.x) sdata[i] = tv.linefit[i];
+    __syncthreads();
+  }
+  const PhaseLists L = phase_lists(a);
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = gid < L.n_self;
+  const int c = valid ? L.self[gid] : 0;
+  valid = valid && c >= a.chain_lo && c < a.chain_hi;
+  int acc = 0;
+  if (valid) {
+    const int d = a.d;
+    const bool dream = a.algo == BPM_ALGO_DREAM;
+    const int npair = dream ? a.del_pairs : 1;
+    ChainDraws D;
+    chain_scalar_draws<REPLAY>(a, c, L.n_pool, D);
+    uint32_t mbits = 0xFu;
+    double gamma;
+    if (dream) {
+      mbits = 0u;
+      const double cr = __ddiv_rn((double)(D.cr_idx + 1), (double)a.n_cr);
+      double z[4];
+      z4<REPLAY>(a, c, 0, z);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < d && z[q] <= cr) mbits |= 1u << q;
+      int d_prime = __popc(mbits);
+      if (d_prime == 0) {
+        mbits |= 1u << ((D.fallback < 0 ? 0 : D.fallback) & 3);
+        d_prime = 1;
+      }
+      gamma = dream_gamma(a, d_prime, D.gamma_u);
+    } else {
+      gamma = demc_gamma(a, D.gamma_u);
+    }
+    double* xc = a.X + (size_t)c * a.ld;
+    double cur[4] = {0, 0, 0, 0}, S[4] = {0, 0, 0, 0}, pr[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q < d) cur[q] = xc[q];
+#pragma unroll
+    for (int p = 0; p < BPM_MAX_PAIRS; ++p)
+      if (p < npair) {
+        const double* pa = a.X + (size_t)L.pool[D.r1[p]] * a.ld;
+        const double* pb = a.X + (size_t)L.pool[D.r2[p]] * a.ld;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < d) {
+            const double df = __dsub_rn(pa[q], pb[q]);
+            S[q] = p == 0 ? df : __dadd_rn(S[q], df);
+          }
+      }
+    double e[4] = {0, 0, 0, 0}, nn[4];
+    if (dream) e4<REPLAY>(a, c, 0, e);
+    n4<REPLAY>(a, c, 0, nn);
+    double delta = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q < d) {
+        if (dream) {
+          pr[q] = dream_prop(cur[q], S[q], e[q], nn[q], gamma, (mbits >> q) & 1u ? 1.0 : 0.0);
+          if (a.adapt) delta += cr_term(cur[q], pr[q], cr_variance<REPLAY>(a, c, q));
+        } else {
+          pr[q] = demc_prop(cur[q], S[q], nn[q], gamma);
+        }
+      }
+    if (dream) {
+      a.cr_pick[c] = a.adapt ? D.cr_idx : -1;
+      a.cr_delta[c] = delta;
+    }
+    double lp;
+    if (TARGET == BPM_TARGET_BANANA) lp = banana_lnl(tv.banana, pr[0], pr[1]);
+    else if (TARGET == BPM_TARGET_BIMODAL) lp = bimodal_lnl(tv.bimodal, pr[0], pr[1]);
+    else lp = linefit_lnl(sdata, sdata + tv.linefit_M, sdata + 2 * tv.linefit_M, tv.linefit_M, pr[0],
+                          pr[1], pr[2]);
+    acc = metropolis(a.lnl[c], lp, accept_uniform<REPLAY>(a, c));
+    if (acc < 0) {
+      *a.nan_flag = 1;
+      acc = 0;
+    }
+    const double n1 = (double)(a.hist_len + 1);
+    const size_t o = (size_t)(c - a.chain_lo) * a.ld;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q < d) {
+        const double s = acc ? pr[q] : cur[q];
+        if (acc) xc[q] = s;
+        if (a.mean) {
+          double mu = a.mean[o + q], v = a.m2[o + q];
+          welford_update(s, n1, mu, v);
+          a.mean[o + q] = mu;
+          a.m2[o + q] = v;
+        }
+        if (a.hist_row) a.hist_row[o + q] = s;
+      }
+    if (acc) a.lnl[c] = lp;
+    if (a.tr.accept) a.tr.accept[c] = acc;
+    if (a.tr.lnl_prop) a.tr.lnl_prop[c] = lp;
+  }
+  const unsigned am = __ballot_sync(0xFFFFFFFFu, valid && acc);
+  const unsigned rm = __ballot_sync(0xFFFFFFFFu, valid && !acc);
+  if ((threadIdx.x & 31) == 0) {
+    if (am) atomicAdd(a.n_acc, (unsigned long long)__popc(am));
+    if (rm) atomicAdd(a.n_rej, (unsigned long long)__popc(rm));
+  }
+}
 
 template <bool REPLAY>
-inline int try_fused_phase(const TargetView&, const PhaseArgs&, cudaStream_t, int* done) {
+inline int try_fused_phase(const TargetView& tv, const PhaseArgs& a, cudaStream_t s, int* done) {
   *done = 0;
+  if (tv.target == BPM_TARGET_GAUSS && gauss_rows_supported(a.d, tv.r) && (a.ld % 2) == 0) {
+    GaussArgs g;
+    g.mu = tv.mu; g.W = tv.W; g.r = tv.r; g.c0 = tv.c0; g.log_of_pdf = tv.log_of_pdf;
+    const size_t sm = fused_gauss_smem(a.d);
+    const int n_tiles = (a.nA + kTileRows - 1) / kTileRows;
+    int grid = (n_tiles + 1) / 2;
+    if (grid > 148) grid = 148;
+    if (grid < 1) grid = 1;
+    cudaError_t e;
+    if (tv.mu_is_zero) {
+      e = cudaFuncSetAttribute(fused_gauss_kernel<REPLAY, false>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      if (e != cudaSuccess) return 1;
+      fused_gauss_kernel<REPLAY, false><<<grid, 2 * kHalfThreads, sm, s>>>(a, g);
+    } else {
+      e = cudaFuncSetAttribute(fused_gauss_kernel<REPLAY, true>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      if (e != cudaSuccess) return 1;
+      fused_gauss_kernel<REPLAY, true><<<grid, 2 * kHalfThreads, sm, s>>>(a, g);
+    }
+    if (cudaGetLastError() != cudaSuccess) return 1;
+    *done = 1;
+    return 0;
+  }
+  if (a.d <= 4 && (tv.target == BPM_TARGET_BANANA || tv.target == BPM_TARGET_BIMODAL ||
+                   tv.target == BPM_TARGET_LINEFIT)) {
+    const int grid = (a.nA + 127) / 128;
+    if (tv.target == BPM_TARGET_BANANA)
+      fused_small_kernel<REPLAY, BPM_TARGET_BANANA><<<grid, 128, 0, s>>>(a, tv);
+    else if (tv.target == BPM_TARGET_BIMODAL)
+      fused_small_kernel<REPLAY, BPM_TARGET_BIMODAL><<<grid, 128, 0, s>>>(a, tv);
+    else
+      fused_small_kernel<REPLAY, BPM_TARGET_LINEFIT>
+          <<<grid, 128, sizeof(double) * 3 * tv.linefit_M, s>>>(a, tv);
+    if (cudaGetLastError() != cudaSuccess) return 1;
+    *done = 1;
+    return 0;
+  }
   return 0;
 }
 

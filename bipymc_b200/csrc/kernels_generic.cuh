@@ -72,8 +72,9 @@ __global__ void __launch_bounds__(kThreads) propose_kernel(const PhaseArgs a) {
     }
     int d_prime = group_sum_i<LPC>(__popc(mbits));
     if (d_prime == 0) {  // dream.py:55-57: one random dimension
-      const int fb = D.fallback >> 2;
-      if (valid && (fb % LPC) == sub) mbits |= 1u << (4 * (fb / LPC) + (D.fallback & 3));
+      const int fdim = D.fallback < 0 ? 0 : D.fallback;
+      const int fb = fdim >> 2;
+      if (valid && (fb % LPC) == sub) mbits |= 1u << (4 * (fb / LPC) + (fdim & 3));
       d_prime = 1;
     }
     gamma = dream_gamma(a, d_prime, D.gamma_u);
@@ -95,7 +96,6 @@ __global__ void __launch_bounds__(kThreads) propose_kernel(const PhaseArgs a) {
   }
   const double* xc = a.X + (size_t)c * a.ld;
   double* out = a.prop + (size_t)gid * a.ld;
-  const double inv_T = 1.0 / (double)a.hist_len;
   double delta = 0.0;
   if (valid) {
 #pragma unroll
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kThreads) propose_kernel(const PhaseArgs a) {
             if (dream) {
               const double mf = (mbits >> (4 * t + q)) & 1u ? 1.0 : 0.0;
               pr = dream_prop(cur, S, e[q], n[q], gamma, mf);
-              if (a.adapt) delta += cr_term(cur, pr, a.m2[(size_t)(c - a.chain_lo) * a.ld + i], inv_T);
+              if (a.adapt) delta += cr_term(cur, pr, cr_variance<REPLAY>(a, c, i));
             } else {
               pr = demc_prop(cur, S, n[q], gamma);
             }
@@ -176,11 +176,10 @@ __global__ void __launch_bounds__(kThreads) accept_kernel(const PhaseArgs a) {
             }
             if (a.mean) {  // Welford update with the appended row (chain.py:51-54)
               const size_t o = (size_t)(c - a.chain_lo) * a.ld + i;
-              const double mu = a.mean[o];
-              const double dl = s - mu;
-              const double mu2 = mu + dl / n1;
-              a.mean[o] = mu2;
-              a.m2[o] += dl * (s - mu2);
+              double mu = a.mean[o], v = a.m2[o];
+              welford_update(s, n1, mu, v);
+              a.mean[o] = mu;
+              a.m2[o] = v;
             }
             if (a.hist_row) a.hist_row[(size_t)(c - a.chain_lo) * a.ld + i] = s;
           }
@@ -286,14 +285,22 @@ __global__ void __launch_bounds__(256) lnl_gauss_tiled_kernel(const double* __re
 }
 
 // ---- CR adaptation: deterministic reduction + p_cr update (dream.py:119-140) -----
-__global__ void __launch_bounds__(1024) cr_reduce_kernel(const double* __restrict__ cr_delta,
-                                                         const int32_t* __restrict__ cr_pick, int lo,
-                                                         int hi, int n_cr, double* __restrict__ part) {
-  // part[0:n_cr) = sum of jump statistics per CR value, part[n_cr:2n_cr) = counts
-  __shared__ double sm[32];
+// Stage 1: block b sums the chains of its contiguous segment (fixed order inside the
+// block); stage 2: one warp adds the block partials in block order.
+constexpr int kCrBlocks = 148;
+__global__ void __launch_bounds__(256) cr_reduce_kernel(const double* __restrict__ cr_delta,
+                                                        const int32_t* __restrict__ cr_pick, int lo,
+                                                        int hi, int n_cr,
+                                                        double* __restrict__ block_part) {
+  // block_part[b][0:n_cr) = sum of jump statistics per CR value, [n_cr:2n_cr) = counts
+  __shared__ double sm[8];
+  const int n = hi - lo;
+  const int per = (n + gridDim.x - 1) / gridDim.x;
+  const int c0 = lo + blockIdx.x * per;
+  const int c1 = min(hi, c0 + per);
   for (int m = 0; m < n_cr; ++m) {
     double s = 0.0, k = 0.0;
-    for (int c = lo + threadIdx.x; c < hi; c += blockDim.x)
+    for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x)
       if (cr_pick[c] == m) { s += cr_delta[c]; k += 1.0; }
     for (int pass = 0; pass < 2; ++pass) {
       double v = pass == 0 ? s : k;
@@ -301,15 +308,23 @@ __global__ void __launch_bounds__(1024) cr_reduce_kernel(const double* __restric
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
       if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
       __syncthreads();
-      if (threadIdx.x < 32) {
-        double w = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xFFFFFFFFu, w, o);
-        if (threadIdx.x == 0) part[pass * n_cr + m] = w;
+      if (threadIdx.x == 0) {
+        double w = 0.0;
+        for (int i = 0; i < 8; ++i) w += sm[i];
+        block_part[(size_t)blockIdx.x * 2 * BPM_MAX_CR + pass * n_cr + m] = w;
       }
       __syncthreads();
     }
   }
+}
+
+__global__ void cr_finish_kernel(const double* __restrict__ block_part, int nb, int n_cr,
+                                 double* __restrict__ part) {
+  const int i = threadIdx.x;
+  if (i >= 2 * n_cr) return;
+  double w = 0.0;
+  for (int b = 0; b < nb; ++b) w += block_part[(size_t)b * 2 * BPM_MAX_CR + i];
+  part[i] = w;
 }
 
 __global__ void cr_apply_kernel(const double* __restrict__ part, int n_cr, double* __restrict__ dm,

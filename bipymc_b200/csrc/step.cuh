@@ -17,7 +17,8 @@ struct PhaseArgs {
   double* lnl;
   double* mean;
   double* m2;
-  double* hist_row;  // destination row block [N][ld] for this generation, or nullptr
+  double* hist_row;  // destination row block [n_local][ld] for this generation, or nullptr
+  const double* hist_base;  // row 0 of the stored history (replay mode: exact np.std), or nullptr
   // phase lists: perm[0:nA) is half "a", perm[nA:N) half "b" before the flip swap
   const int32_t* perm;
   const int32_t* flip;  // device flag (demc.py:81,98-100)
@@ -247,13 +248,52 @@ __device__ __forceinline__ double demc_gamma(const PhaseArgs& a, double gamma_u)
   return a.gamma_fixed;
 }
 
-// dream.py:128-130 contribution of one dimension: (cur - prop)^2 / std^2 with
-// std^2 = M2 / T (population variance of the chain's history), 0 -> (1e-12)^2.
-__device__ __forceinline__ double cr_term(double cur, double prop, double m2, double inv_T) {
-  double var = __dmul_rn(m2, inv_T);
+// dream.py:128-129: std_devs = np.std(chain.chain, axis=0); std_devs[std_devs == 0] = 1e-12;
+// returns std_devs ** 2 for dimension i of chain c.
+//   native mode : running (Welford) moments, var = M2 / T, O(1) per step;
+//   replay mode : numpy's own two-pass algorithm over the stored history column
+//                 (sequential sums along axis 0, mean = sum / T, var = sum((x - mean)^2) / T,
+//                 sqrt, then squared again), O(T) per step.  This matters for parity: for a
+//                 column that never moved np.std returns rounding noise (~1e-17 * |x|)
+//                 instead of 0, the reference's `== 0` guard does not fire, and the
+//                 chain's jump statistic is divided by ~1e-34.  Replay reproduces that
+//                 to the bit; native mode gets an exact 0 and the 1e-12 floor.
+template <bool REPLAY>
+__device__ __forceinline__ double cr_variance(const PhaseArgs& a, int c, int i) {
+  const int co = c - a.chain_lo;
+  if (REPLAY && a.hist_base != nullptr) {
+    const size_t stride = (size_t)(a.chain_hi - a.chain_lo) * a.ld;
+    const double* p = a.hist_base + (size_t)co * a.ld + i;
+    const double T = (double)a.hist_len;
+    double sum = p[0];
+    for (int64_t t = 1; t < a.hist_len; ++t) sum = __dadd_rn(sum, p[t * stride]);
+    const double mean = __ddiv_rn(sum, T);
+    double ss = 0.0;
+    for (int64_t t = 0; t < a.hist_len; ++t) {
+      const double dx = __dsub_rn(p[t * stride], mean);
+      ss = __dadd_rn(ss, __dmul_rn(dx, dx));
+    }
+    double sd = __dsqrt_rn(__ddiv_rn(ss, T));
+    if (sd == 0.0) sd = 1e-12;
+    return __dmul_rn(sd, sd);
+  }
+  double var = __dmul_rn(a.m2[(size_t)co * a.ld + i], 1.0 / (double)a.hist_len);
   if (!(var > 0.0)) var = 1e-12 * 1e-12;
-  double df = __dsub_rn(cur, prop);
+  return var;
+}
+
+// dream.py:130 contribution of one dimension: (cur - prop)^2 / std^2.
+__device__ __forceinline__ double cr_term(double cur, double prop, double var) {
+  const double df = __dsub_rn(cur, prop);
   return __ddiv_rn(__dmul_rn(df, df), var);
+}
+
+// Explicitly rounded Welford update (identical bits in every kernel that uses it).
+__device__ __forceinline__ void welford_update(double s, double n1, double& mu, double& m2) {
+  const double dl = __dsub_rn(s, mu);
+  const double mu2 = __dadd_rn(mu, __ddiv_rn(dl, n1));
+  m2 = __dadd_rn(m2, __dmul_rn(dl, __dsub_rn(s, mu2)));
+  mu = mu2;
 }
 
 }  // namespace bpm

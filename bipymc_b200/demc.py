@@ -101,7 +101,7 @@ class HistoryStore(object):
     moments still see every generation).  ``length`` is the LOGICAL chain length
     (generations + 1, what ``len(chain.chain)`` is in the reference); ``stored`` the
     number of rows physically kept."""
-    def __init__(self, n_local, dim, ld, device, policy="full", chunk_bytes=1 << 28):
+    def __init__(self, n_local, dim, ld, device, policy="full", chunk_bytes=1 << 28, reserve_rows=0):
         import torch
         if policy not in ("full", "none"):
             raise ValueError("history must be 'full' or 'none'")
@@ -109,7 +109,8 @@ class HistoryStore(object):
         self.n_local, self.dim, self.ld, self.device = n_local, dim, ld, device
         self.policy = policy
         self.row_bytes = n_local * ld * 8
-        self.chunk_rows = max(1, int(chunk_bytes // self.row_bytes))
+        self.chunk_rows = max(1, int(chunk_bytes // self.row_bytes), int(reserve_rows))
+        self.reserve_rows = int(reserve_rows)
         self.chunks = []      # list of [rows, n_local, ld] tensors
         self.stored = 0
         self.length = 0
@@ -128,7 +129,7 @@ class HistoryStore(object):
         torch = self._torch
         used = self._used_in_last()
         if not self.chunks or used == self.chunks[-1].shape[0]:
-            n = min(self.chunk_rows, max(rows, 1))
+            n = min(self.chunk_rows, max(rows, self.reserve_rows, 1))
             self.chunks.append(torch.empty((n, self.n_local, self.ld), dtype=torch.float64,
                                            device=self.device))
             used = 0
@@ -249,6 +250,7 @@ class DeMcMpi(object):
         self._device_index = kwargs.get("device", None)
         self._fused = kwargs.get("fused", True)
         self._chunk_bytes = int(kwargs.get("history_chunk_bytes", 1 << 30))
+        self._reserve_rows = int(kwargs.get("history_reserve", 0))   # generations to pre-allocate
         self._setup_device()
         if not self.warm_start:
             self.init_chains(theta_0, varepsilon, **kwargs)
@@ -357,7 +359,7 @@ class DeMcMpi(object):
         self._mean = self._X[lo:hi].clone()
         self._m2 = torch.zeros((nl, ld), dtype=torch.float64, device=self._device)
         self._hist = HistoryStore(nl, d, ld, self._device, policy=self._history_policy,
-                                  chunk_bytes=self._chunk_bytes)
+                                  chunk_bytes=self._chunk_bytes, reserve_rows=self._reserve_rows)
         self._hist._current = self._X[lo:hi]
         if history is None:
             self._hist.set_initial(self._X[lo:hi])

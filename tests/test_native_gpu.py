@@ -48,7 +48,10 @@ def _native_vs_oracle(s, oracle_lnl, gens, k0=0, run_kwargs=None):
         hist = s._hist.tensor()[:, :, :s.dim].cpu().numpy()
         hv = None
         if cfg["algo"] == "dream" and hist.shape[0] > cfg["n_cr_gen"]:
-            hv = np.std(hist, axis=0) ** 2.0
+            # native mode keeps running (Welford) moments: a column that never moved has
+            # variance exactly 0 (-> the 1e-12 floor), where np.std would return rounding noise
+            hv = np.var(hist, axis=0)
+            hv[np.all(hist == hist[0], axis=0)] = 0.0
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             want = orp.replay_generation(pre, tr, cfg, lnl, k, hist_var=hv, cr=cr)
