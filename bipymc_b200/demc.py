@@ -130,9 +130,19 @@ class HistoryStore(object):
         used = self._used_in_last()
         if not self.chunks or used == self.chunks[-1].shape[0]:
             n = min(self.chunk_rows, max(rows, self.reserve_rows, 1))
-            self.chunks.append(torch.empty((n, self.n_local, self.ld), dtype=torch.float64,
-                                           device=self.device))
-            used = 0
+            if len(self.chunks) == 1 and self.stored == 1:
+                # only the initial row so far: fold it into the new chunk so a single
+                # run_mcmc leaves ONE contiguous [T][n_local][ld] block (no later concat)
+                first = self.chunks[0]
+                blk = torch.empty((n + 1, self.n_local, self.ld), dtype=torch.float64,
+                                  device=self.device)
+                blk[0].copy_(first[0])
+                self.chunks = [blk]
+                used = 1
+            else:
+                self.chunks.append(torch.empty((n, self.n_local, self.ld), dtype=torch.float64,
+                                               device=self.device))
+                used = 0
         last = self.chunks[-1]
         base = last.data_ptr() - (self.length - used) * self.row_bytes
         return base, last.shape[0] - used
