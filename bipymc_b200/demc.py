@@ -344,13 +344,14 @@ class DeMcMpi(object):
         torch = _torch()
         theta_0 = np.asarray(theta_0, dtype=float).flatten()
         self.dim = len(theta_0)
-        if self._handle is None:
-            self._create_handle()
         assert np.all(np.asarray(varepsilon) >= 0.0)
-        N, d, ld = self.n_chains, self.dim, self._ld
+        N, d = self.n_chains, self.dim
         # every rank draws the jitter of ALL chains so the replicas agree (demc.py seeds
-        # every rank identically as well, tests/test_banana.py:17)
+        # every rank identically as well, tests/test_banana.py:17).  This is the FIRST use
+        # of numpy's global stream, exactly as in the reference's constructor.
         x0 = theta_0[None, :] + var_ball_batch(varepsilon, d, N)
+        if self._handle is None:
+            self._create_handle()          # draws the Philox seed AFTER the jitter
         if self.comm.size > 1:
             x0t = torch.from_numpy(x0).to(self._device)
             import torch.distributed as dist

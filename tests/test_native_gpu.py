@@ -151,45 +151,52 @@ def test_bimodal_posterior_mean_like_reference_test():
 
 
 def test_large_population_posterior_and_rhat():
-    """Many chains, few generations: mean / covariance of the 2-D banana's underlying
-    Gaussian coordinates within Monte-Carlo error, R-hat < 1.01 over the second half."""
+    """Wide population, long run: mean / covariance of the banana's underlying Gaussian
+    coordinates within Monte-Carlo error and Gelman-Rubin R-hat < 1.01 over the second
+    half of the chains (north_star's convergence gate)."""
     from bipymc_b200 import DreamMpi, targets
     from bipymc_b200.diagnostics import gelman_rubin
     banana = targets.Banana_2D()
     np.random.seed(0)
-    N, G = 4096, 1500
-    s = DreamMpi(banana.ln_like, [0.0, 0.0], n_chains=N, seed=21, burnin_gen=300, n_cr_gen=50,
+    N, G = 1024, 20000
+    s = DreamMpi(banana.ln_like, [0.0, 0.0], n_chains=N, seed=21, burnin_gen=2000, n_cr_gen=50,
                  varepsilon=1.0)
     s.run_mcmc(N * (G + 1))
     h = s._hist.tensor()[G // 2:, :, :2]
     rhat = gelman_rubin(h)
+    print("banana R-hat", rhat, "acc", s.acceptance_fraction, "p_cr", s.p_cr)
     assert np.all(rhat < 1.01), rhat
     flat = h.reshape(-1, 2).cpu().numpy()
     x1, x2 = banana.inv_transform(flat[:, 0], flat[:, 1])
     # underlying N(0, [[1, .9], [.9, 1]])
-    assert abs(x1.mean()) < 0.02 and abs(x2.mean()) < 0.02
-    c = np.cov(np.stack([x1, x2]))
-    assert abs(c[0, 0] - 1.0) < 0.03 and abs(c[1, 1] - 1.0) < 0.03 and abs(c[0, 1] - 0.9) < 0.03
+    assert abs(x1.mean()) < 0.02 and abs(x2.mean()) < 0.02, (x1.mean(), x2.mean())
+    c = np.cov(np.stack([x1[::7], x2[::7]]))
+    assert abs(c[0, 0] - 1.0) < 0.03 and abs(c[1, 1] - 1.0) < 0.03 and abs(c[0, 1] - 0.9) < 0.03, c
 
 
 def test_gauss100_posterior_like_reference_test():
-    """tests/test_100dgauss.py:67-69 (mean[0], mean[1] = 0 +- 0.2) on a wide population,
-    plus the marginal variances var_i = i + 1 of d100_gauss.py:16."""
+    """tests/test_100dgauss.py:67-69 (mean[0], mean[1] = 0 +- 0.2), plus every marginal
+    mean / variance (var_i = i + 1, d100_gauss.py:16) and R-hat < 1.01, on 1024 chains
+    started over-dispersed."""
     from bipymc_b200 import DreamMpi, targets
     from bipymc_b200.diagnostics import gelman_rubin
     tgt = targets.Gauss_100D()
     np.random.seed(0)
-    N, G = 8192, 1600
-    s = DreamMpi(tgt.ln_like, np.zeros(100), n_chains=N, seed=5, burnin_gen=400, n_cr_gen=50,
-                 varepsilon=1.0, history_chunk_bytes=1 << 32)
+    N, G = 1024, 12000
+    s = DreamMpi(tgt.ln_like, np.zeros(100), n_chains=N, seed=5, burnin_gen=2000, n_cr_gen=50,
+                 varepsilon=2.0 * (np.arange(100) + 1.0), history_reserve=G)
     s.run_mcmc(N * (G + 1))
     h = s._hist.tensor()[G // 2:, :, :100]
     mean = h.mean(dim=(0, 1)).cpu().numpy()
     var = h.reshape(-1, 100).var(dim=0).cpu().numpy()
+    rhat = gelman_rubin(h)
+    print("gauss100 max R-hat %.4f acc %.3f max|mean|/sd %.3f var ratio [%.3f, %.3f]" % (
+        rhat.max(), s.acceptance_fraction, np.max(np.abs(mean) / np.sqrt(np.arange(100) + 1.0)),
+        (var / (np.arange(100) + 1.0)).min(), (var / (np.arange(100) + 1.0)).max()))
     assert abs(mean[0]) < 0.2 and abs(mean[1]) < 0.2
-    assert np.all(np.abs(mean) < 0.05 * np.sqrt(np.arange(100) + 1.0) + 0.05)
-    np.testing.assert_allclose(var, np.arange(100) + 1.0, rtol=0.08)
-    assert np.all(gelman_rubin(h) < 1.01)
+    assert np.all(np.abs(mean) < 0.05 * np.sqrt(np.arange(100) + 1.0))
+    np.testing.assert_allclose(var, np.arange(100) + 1.0, rtol=0.05)
+    assert np.all(rhat < 1.01), rhat.max()
     assert 0.05 < s.acceptance_fraction < 0.7
 
 
