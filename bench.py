@@ -224,7 +224,7 @@ def run_ours(args):
 
     # ---- end to end through the C-ABI with HOST buffers (rank-local population) --------
     e2e = None
-    if world == 1:
+    if world == 1 and not args.no_e2e:
         Xh = torch.empty((N, s._ld), dtype=torch.float64).pin_memory()
         Lh = torch.empty((N,), dtype=torch.float64).pin_memory()
         Xh.copy_(s._X.cpu()); Lh.copy_(s._lnl.cpu())
@@ -272,6 +272,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--history", default="full", choices=["full", "none"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -27,7 +27,7 @@ class Config(C.Structure):
 
 class State(C.Structure):
     _fields_ = [("X", C.c_void_p), ("lnl", C.c_void_p), ("mean", C.c_void_p), ("m2", C.c_void_p),
-                ("history", C.c_void_p), ("hist_len", C.c_int64)]
+                ("history", C.c_void_p), ("hist_len", C.c_int64), ("mom_len", C.c_int64)]
 
 
 class Replay(C.Structure):

@@ -169,6 +169,7 @@ struct bpm_engine {
     a.adapt = cfg.algo == BPM_ALGO_DREAM && cfg.burnin_gen > k_gen && st->hist_len > cfg.n_cr_gen &&
               st->m2 != nullptr;                                                 // dream.py:92,124
     a.hist_len = st->hist_len;
+    a.mom_len = st->mom_len > 0 ? st->mom_len : st->hist_len;
     a.p_cr = p_cr; a.cr_delta = cr_delta; a.cr_pick = cr_pick;
     a.prop = prop; a.lnl_prop = lnl_prop;
     a.n_acc = counters; a.n_rej = counters + 1; a.nan_flag = nan_flag;
@@ -329,6 +330,7 @@ struct bpm_engine {
     BPM_TRY(phase<REPLAY>(st, k_gen, 1, rp, tr, s));
     BPM_TRY(end(s));
     st->hist_len += 1;
+    if (st->mom_len > 0) st->mom_len += 1;
     return 0;
   }
 };
@@ -613,6 +615,7 @@ int bpm_end_generation(bpm_handle h, bpm_state* st, bpm_stream stream) {
   CU_TRY(cudaSetDevice(h->cfg.device));
   BPM_TRY(h->end((cudaStream_t)stream));
   st->hist_len += 1;
+  if (st->mom_len > 0) st->mom_len += 1;
   h->in_generation = false;
   return 0;
 }

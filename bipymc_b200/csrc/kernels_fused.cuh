@@ -199,8 +199,7 @@ fused_gauss_kernel(const PhaseArgs a, const GaussArgs g) {
   const bool dream = a.algo == BPM_ALGO_DREAM;
   const int npair = dream ? a.del_pairs : 1;
   const int n_tiles = (L.n_self + kTileRows - 1) / kTileRows;
-  const double inv_T = 1.0 / (double)a.hist_len;
-  const double n1 = (double)(a.hist_len + 1);
+  const double n1 = (double)(a.mom_len + 1);
   const int blk = lane;                  // this lane's dimension block (4 doubles)
   const bool has_blk = 4 * blk < d;
   unsigned n_acc = 0, n_rej = 0;
@@ -499,7 +498,7 @@ __global__ void __launch_bounds__(128) fused_small_kernel(const PhaseArgs a, con
       *a.nan_flag = 1;
       acc = 0;
     }
-    const double n1 = (double)(a.hist_len + 1);
+    const double n1 = (double)(a.mom_len + 1);
     const size_t o = (size_t)(c - a.chain_lo) * a.ld;
 #pragma unroll
     for (int q = 0; q < 4; ++q)

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kThreads) accept_kernel(const PhaseArgs a) {
     }
     double* xc = a.X + (size_t)c * a.ld;
     const double* pr = a.prop + (size_t)gid * a.ld;
-    const double n1 = (double)(a.hist_len + 1);
+    const double n1 = (double)(a.mom_len + 1);
 #pragma unroll
     for (int t = 0; t < kMaxBlocksPerLane; ++t) {
       const int b = sub + t * LPC;

@@ -35,6 +35,7 @@ struct PhaseArgs {
   double u_eps;        // box jitter half-width
   int32_t adapt;       // burnin_gen > k && hist_len > n_cr_gen (dream.py:92,124)
   int64_t hist_len;    // rows in every chain's history BEFORE this generation's append
+  int64_t mom_len;     // rows covered by the running moments BEFORE this generation
   // CR state
   const double* p_cr;  // [n_cr]
   double* cr_delta;    // [N] per-chain jump statistic of this generation (or untouched)
@@ -277,7 +278,7 @@ __device__ __forceinline__ double cr_variance(const PhaseArgs& a, int c, int i) 
     if (sd == 0.0) sd = 1e-12;
     return __dmul_rn(sd, sd);
   }
-  double var = __dmul_rn(a.m2[(size_t)co * a.ld + i], 1.0 / (double)a.hist_len);
+  double var = __dmul_rn(a.m2[(size_t)co * a.ld + i], 1.0 / (double)a.mom_len);
   if (!(var > 0.0)) var = 1e-12 * 1e-12;
   return var;
 }

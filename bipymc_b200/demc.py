@@ -379,7 +379,7 @@ class DeMcMpi(object):
             self._rebuild_moments()
         self.am_chains = _ChainList(self)
         self._lnl_valid = False
-        self._moments_len = self._hist.length
+        self._mom_len = self._hist.length
 
     def init_warmstart_chain(self, h5_file):
         """demc.py:46-51."""
@@ -404,6 +404,7 @@ class DeMcMpi(object):
         st.m2 = self._m2.data_ptr()
         st.history = hist_base
         st.hist_len = self._hist.length
+        st.mom_len = self._mom_len
         return st
 
     def _rebuild_moments(self):
@@ -411,7 +412,53 @@ class DeMcMpi(object):
         h = self._hist.tensor()
         self._mean = h.mean(dim=0)
         self._m2 = ((h - self._mean[None]) ** 2).sum(dim=0)
-        self._moments_len = self._hist.length
+        self._mom_len = self._hist.length
+
+    # -- streaming diagnostics (no history needed) ------------------------------------
+    def reset_moments(self):
+        """Restart the per-chain running mean / M2 at the current state (e.g. after
+        burn-in), so ``rhat()`` and ``moment_estimates()`` cover only what follows.  The
+        reference has no counterpart; note DREAM's CR adaptation then sees the standard
+        deviation of the post-reset history only."""
+        lo, hi = int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
+        self._mean.copy_(self._X[lo:hi])
+        self._m2.zero_()
+        self._mom_len = 1
+
+    def _gathered_moments(self):
+        """(mean, m2) of ALL chains, [N, d] each (all-gathered when sharded)."""
+        torch = _torch()
+        mean, m2 = self._mean[:, :self.dim].contiguous(), self._m2[:, :self.dim].contiguous()
+        if self.comm.size > 1:
+            import torch.distributed as dist
+            pm = [torch.empty_like(mean) for _ in range(self.comm.size)]
+            p2 = [torch.empty_like(m2) for _ in range(self.comm.size)]
+            dist.all_gather(pm, mean)
+            dist.all_gather(p2, m2)
+            mean, m2 = torch.cat(pm, dim=0), torch.cat(p2, dim=0)
+        return mean, m2
+
+    def rhat(self):
+        """Gelman-Rubin R-hat per dimension from the running moments of every chain
+        (rows since construction / the last reset_moments()); needs no stored history."""
+        torch = _torch()
+        T = float(self._mom_len)
+        if T < 2:
+            raise RuntimeError("rhat() needs at least two rows in the running moments")
+        mean, m2 = self._gathered_moments()
+        W = (m2 / (T - 1.0)).mean(dim=0)
+        B_over_T = mean.var(dim=0, unbiased=True)
+        return torch.sqrt(((T - 1.0) / T * W + B_over_T) / W).cpu().numpy()
+
+    def moment_estimates(self):
+        """Posterior mean and standard deviation pooled over every chain and every row the
+        running moments cover (what param_est(0) computes from the history, without one)."""
+        torch = _torch()
+        T = float(self._mom_len)
+        mean, m2 = self._gathered_moments()
+        gm = mean.mean(dim=0)
+        var = (m2.sum(dim=0) + T * ((mean - gm[None]) ** 2).sum(dim=0)) / (T * mean.shape[0])
+        return gm.cpu().numpy(), torch.sqrt(var).cpu().numpy()
 
     def _mode(self):
         if self._target is not None:
@@ -472,8 +519,6 @@ class DeMcMpi(object):
         _lib.check(self._libh.bpm_set_run_params(self._handle, *self._run_params(kwargs)))
         if not self._lnl_valid:
             self._init_lnl()
-        if self._moments_len != self._hist.length:
-            self._rebuild_moments()
         G = self._n_generations(n)
         replay = kwargs.get("_replay", None)
         trace = kwargs.get("_trace", None)
@@ -499,7 +544,7 @@ class DeMcMpi(object):
                 self._split_generation(st, k_gen + k_off)
                 done = 1
             self._hist.advance(done)
-            self._moments_len = self._hist.length
+            self._mom_len += done
             k_gen += done
             if self.checkpoint > 0 and k_gen % self.checkpoint == 0:        # demc.py:138-140
                 self.save_state(self.h5_file)

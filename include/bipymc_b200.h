@@ -77,6 +77,9 @@ typedef struct bpm_state {
   double* history;  /* [>= hist_len + n_gen][n_local][ld] or NULL: row t = state after
                        generation t-1, i.e. McmcChain.chain[t] (chain.py:51-54)         */
   int64_t hist_len; /* rows already in every chain's history (len(chain.chain))         */
+  int64_t mom_len;  /* rows the running moments (mean, m2) currently cover; equals hist_len
+                       for the reference's np.std-over-the-whole-history semantics, smaller
+                       after a diagnostics reset.  0 is read as hist_len.              */
 } bpm_state;
 
 /* RNG-replay buffers for ONE generation: the reference's numpy draws, indexed by
