@@ -170,6 +170,8 @@ struct bpm_engine {
               st->m2 != nullptr;                                                 // dream.py:92,124
     a.hist_len = st->hist_len;
     a.mom_len = st->mom_len > 0 ? st->mom_len : st->hist_len;
+    a.inv_mom = 1.0 / (double)a.mom_len;
+    a.inv_n1 = 1.0 / (double)(a.mom_len + 1);
     a.p_cr = p_cr; a.cr_delta = cr_delta; a.cr_pick = cr_pick;
     a.prop = prop; a.lnl_prop = lnl_prop;
     a.n_acc = counters; a.n_rej = counters + 1; a.nan_flag = nan_flag;

@@ -175,6 +175,20 @@ struct GaussArgs {
   int log_of_pdf;
 };
 
+// Per-half shared-memory scratch for one 64-chain tile.
+struct TileScratch {
+  double part[8 * kTileRows];   // per-warp partial row sums of squares
+  double lnl[kTileRows];        // ln_like(proposal)
+  double gamma_u[kTileRows];
+  double accept_u[kTileRows];
+  int cid[kTileRows];           // global chain id, -1 = empty row
+  int cr_idx[kTileRows];
+  int fallback[kTileRows];
+  int acc[kTileRows];
+  int pa[kTileRows][BPM_MAX_PAIRS];   // GLOBAL chain ids of the partner rows
+  int pb[kTileRows][BPM_MAX_PAIRS];
+};
+
 template <bool REPLAY, bool CENTER>
 __global__ void __launch_bounds__(2 * kHalfThreads, 1)
 fused_gauss_kernel(const PhaseArgs a, const GaussArgs g) {
@@ -182,74 +196,107 @@ fused_gauss_kernel(const PhaseArgs a, const GaussArgs g) {
   const int d = a.d, pld = d | 1;
   double* Ws = smem;
   double* mus = Ws + d * kWld;
-  double* half_base = mus + ((d + 1) & ~1);
+  double* gam = mus + ((d + 1) & ~1);            // gamma_base[d'] for d' = 0..d (dream.py:61)
+  double* cdf = gam + ((d + 2) & ~1);            // normalised CR cdf (dream.py:51)
+  double* crv = cdf + BPM_MAX_CR;                // CR values (dream.py:113)
+  double* half_base = crv + BPM_MAX_CR;
   const int half = threadIdx.x >> 8;
   const int tid = threadIdx.x & (kHalfThreads - 1);
   const int warp = tid >> 5, lane = tid & 31;
-  const size_t half_doubles = (size_t)kTileRows * pld + 8 * kTileRows + kTileRows + kTileRows / 2;
+  const size_t scratch_doubles = (sizeof(TileScratch) + 7) / 8;
+  const size_t half_doubles = (size_t)kTileRows * pld + 1 + scratch_doubles;
   double* P = half_base + half * half_doubles;
-  double* part = P + kTileRows * pld;
-  double* lnl_s = part + 8 * kTileRows;
-  int* cid_s = reinterpret_cast<int*>(lnl_s + kTileRows);
+  TileScratch& T = *reinterpret_cast<TileScratch*>(P + ((kTileRows * pld + 1) & ~1));
 
+  const bool dream = a.algo == BPM_ALGO_DREAM;
+  const int npair = dream ? a.del_pairs : 1;
   load_W_shared(Ws, mus, g.W, g.mu, d, g.r, threadIdx.x, 2 * kHalfThreads);
+  for (int dp = threadIdx.x; dp <= d; dp += 2 * kHalfThreads)
+    gam[dp] = dp == 0 ? 0.0
+                      : __ddiv_rn(a.gamma_num, __dsqrt_rn(__dmul_rn(__dmul_rn(2.0, (double)a.del_pairs),
+                                                                    (double)dp)));
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int m = 0; m < a.n_cr; ++m) tot = __dadd_rn(tot, a.p_cr[m]);
+    double acc = 0.0;
+    for (int m = 0; m < a.n_cr; ++m) {
+      acc = __dadd_rn(acc, a.p_cr[m]);
+      cdf[m] = __ddiv_rn(acc, tot);
+      crv[m] = __ddiv_rn((double)(m + 1), (double)a.n_cr);
+    }
+  }
   __syncthreads();
 
   const PhaseLists L = phase_lists(a);
-  const bool dream = a.algo == BPM_ALGO_DREAM;
-  const int npair = dream ? a.del_pairs : 1;
   const int n_tiles = (L.n_self + kTileRows - 1) / kTileRows;
-  const double n1 = (double)(a.mom_len + 1);
+  const int nslots = 2 + npair;
   const int blk = lane;                  // this lane's dimension block (4 doubles)
   const bool has_blk = 4 * blk < d;
+  const bool full = 4 * blk + 3 < d;
   unsigned n_acc = 0, n_rej = 0;
 
   for (int tile = blockIdx.x * 2 + half; tile < n_tiles; tile += 2 * gridDim.x) {
-    // ---------------- stage A: draws, gathers, proposal ------------------------------
-    for (int jj = 0; jj < kTileRows / 8; ++jj) {
-      const int row = warp * (kTileRows / 8) + jj;
+    // ---------------- stage D: per-chain scalar draws, one thread per (chain, slot) --------
+    for (int idx = tid; idx < kTileRows * nslots; idx += kHalfThreads) {
+      const int row = idx / nslots, slot = idx - row * nslots;
       const int gid = tile * kTileRows + row;
       bool valid = gid < L.n_self;
       const int c = valid ? L.self[gid] : 0;
       valid = valid && c >= a.chain_lo && c < a.chain_hi;
+      if (slot == 0) T.cid[row] = valid ? c : -1;
+      if (!valid) continue;
+      if (REPLAY) {
+        if (slot == 0) {
+          T.cr_idx[row] = dream ? a.rp.cr_idx[c] : 0;
+          T.accept_u[row] = a.rp.accept_u[c];
+        } else if (slot == 1) {
+          T.gamma_u[row] = a.rp.gamma_u[c];
+          T.fallback[row] = dream ? a.rp.fallback_dim[c] : -1;
+        } else {
+          const int p = slot - 2;
+          T.pa[row][p] = L.pool[a.rp.pairs[((size_t)c * npair + p) * 2 + 0]];
+          T.pb[row][p] = L.pool[a.rp.pairs[((size_t)c * npair + p) * 2 + 1]];
+        }
+      } else {
+        const Philox4 q = draw4(a.rng, (uint32_t)c, RNG_SCALAR, (uint32_t)slot);
+        if (slot == 0) {
+          int m = 0;
+          if (dream) {
+            const double u = slot0_cr_u(q);
+            for (int j = 0; j < a.n_cr; ++j)
+              if (cdf[j] <= u) m = j + 1;
+            m = m < a.n_cr ? m : a.n_cr - 1;
+          }
+          T.cr_idx[row] = m;
+          T.accept_u[row] = slot0_accept_u(q);
+        } else if (slot == 1) {
+          T.gamma_u[row] = slot1_gamma_u(q);
+          T.fallback[row] = slot1_fallback(q, d);
+        } else {
+          int r1, r2;
+          slot_pair(q, L.n_pool, r1, r2);
+          T.pa[row][slot - 2] = L.pool[r1];
+          T.pb[row][slot - 2] = L.pool[r2];
+        }
+      }
+    }
+    half_barrier(half);
+    // ---------------- stage A: mask, gathers, proposal (warp per chain) -----------------
+    for (int jj = 0; jj < kTileRows / 8; ++jj) {
+      const int row = warp * (kTileRows / 8) + jj;
+      const int c = T.cid[row];
       double* prow = P + row * pld;
-      if (!valid) {
-        if (lane == 0) cid_s[row] = -1;
+      if (c < 0) {
         if (has_blk)
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             if (4 * blk + q < d) prow[4 * blk + q] = 0.0;
         continue;
       }
-      ChainDraws D;
-      chain_scalar_draws<REPLAY>(a, c, L.n_pool, D);
-      uint32_t mbits = 0xFu;
-      double gamma;
-      if (dream) {
-        mbits = 0u;
-        const double cr = __ddiv_rn((double)(D.cr_idx + 1), (double)a.n_cr);
-        if (has_blk) {
-          double z[4];
-          z4<REPLAY>(a, c, blk, z);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (4 * blk + q < d && z[q] <= cr) mbits |= 1u << q;
-        }
-        int d_prime = __reduce_add_sync(0xFFFFFFFFu, __popc(mbits));
-        if (d_prime == 0) {
-          const int fb = D.fallback < 0 ? 0 : D.fallback;
-          if ((fb >> 2) == blk) mbits |= 1u << (fb & 3);
-          d_prime = 1;
-        }
-        gamma = dream_gamma(a, d_prime, D.gamma_u);
-      } else {
-        gamma = demc_gamma(a, D.gamma_u);
-      }
-      double delta = 0.0;
+      // issue the row gathers first: they do not depend on the mask draws
+      double cur[4] = {0, 0, 0, 0}, S[4] = {0, 0, 0, 0};
       if (has_blk) {
         const double* xc = a.X + (size_t)c * a.ld + 4 * blk;
-        double cur[4], S[4];
-        const bool full = 4 * blk + 3 < d;
         if (full) {
           const double2 u0 = *reinterpret_cast<const double2*>(xc);
           const double2 u1 = *reinterpret_cast<const double2*>(xc + 2);
@@ -261,8 +308,8 @@ fused_gauss_kernel(const PhaseArgs a, const GaussArgs g) {
 #pragma unroll
         for (int p = 0; p < BPM_MAX_PAIRS; ++p) {
           if (p < npair) {
-            const double* pa = a.X + (size_t)L.pool[D.r1[p]] * a.ld + 4 * blk;
-            const double* pb = a.X + (size_t)L.pool[D.r2[p]] * a.ld + 4 * blk;
+            const double* pa = a.X + (size_t)T.pa[row][p] * a.ld + 4 * blk;
+            const double* pb = a.X + (size_t)T.pb[row][p] * a.ld + 4 * blk;
             double va[4], vb[4];
             if (full) {
               const double2 s0 = *reinterpret_cast<const double2*>(pa);
@@ -285,9 +332,35 @@ fused_gauss_kernel(const PhaseArgs a, const GaussArgs g) {
             }
           }
         }
-        double e[4] = {0, 0, 0, 0}, nn[4];
-        if (dream) e4<REPLAY>(a, c, blk, e);
-        n4<REPLAY>(a, c, blk, nn);
+      }
+      uint32_t mbits = 0xFu;
+      double gamma;
+      const double gu = T.gamma_u[row];
+      if (dream) {
+        mbits = 0u;
+        const double cr = crv[T.cr_idx[row]];
+        if (has_blk) {
+          double z[4];
+          z4<REPLAY>(a, c, blk, z);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (4 * blk + q < d && z[q] <= cr) mbits |= 1u << q;
+        }
+        int d_prime = __reduce_add_sync(0xFFFFFFFFu, __popc(mbits));
+        if (d_prime == 0) {
+          const int fb = T.fallback[row] < 0 ? 0 : T.fallback[row];
+          if ((fb >> 2) == blk) mbits |= 1u << (fb & 3);
+          d_prime = 1;
+        }
+        gamma = gam[d_prime];
+        if (a.gamma_jump) gamma = gu < a.gamma_p0 ? gamma : 1.0;
+      } else {
+        gamma = demc_gamma(a, gu);
+      }
+      double delta = 0.0;
+      if (has_blk) {
+        double e[4], nn[4];
+        en4<REPLAY>(a, c, blk, e, nn);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int i = 4 * blk + q;
@@ -306,99 +379,101 @@ fused_gauss_kernel(const PhaseArgs a, const GaussArgs g) {
       if (dream) {
         delta = group_sum_d<32>(delta);
         if (lane == 0) {
-          a.cr_pick[c] = a.adapt ? D.cr_idx : -1;
+          a.cr_pick[c] = a.adapt ? T.cr_idx[row] : -1;
           a.cr_delta[c] = delta;
         }
       }
-      if (lane == 0) cid_s[row] = c;
     }
     half_barrier(half);
     // ---------------- stage B: quadratic form ----------------------------------------
-    gauss_tile_rowsums<CENTER>(P, pld, Ws, mus, d, part, warp, lane);
+    gauss_tile_rowsums<CENTER>(P, pld, Ws, mus, d, T.part, warp, lane);
     half_barrier(half);
-    if (tid < kTileRows) lnl_s[tid] = gauss_tile_finish(part, tid, g.c0, g.log_of_pdf);
-    half_barrier(half);
-    // ---------------- stage C: accept / reject and the single write-back ---------------
-    for (int jj = 0; jj < kTileRows / 8; ++jj) {
-      const int row = warp * (kTileRows / 8) + jj;
-      const int c = cid_s[row];
-      if (c < 0) continue;
-      const double lp = lnl_s[row];
-      const double u = accept_uniform<REPLAY>(a, c);
-      int acc = metropolis(a.lnl[c], lp, u);
-      if (acc < 0) {
-        if (lane == 0) *a.nan_flag = 1;
-        acc = 0;
-      }
-      if (has_blk) {
-        double* xc = a.X + (size_t)c * a.ld + 4 * blk;
-        const double* prow = P + row * pld + 4 * blk;
-        const size_t o = (size_t)(c - a.chain_lo) * a.ld + 4 * blk;
-        const bool full = 4 * blk + 3 < d;
-        double s[4];
-        if (acc) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) s[q] = 4 * blk + q < d ? prow[q] : 0.0;
-          if (full) {
-            *reinterpret_cast<double2*>(xc) = make_double2(s[0], s[1]);
-            *reinterpret_cast<double2*>(xc + 2) = make_double2(s[2], s[3]);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (4 * blk + q < d) xc[q] = s[q];
-          }
-        } else if (a.mean || a.hist_row) {
-          if (full) {
-            const double2 u0 = *reinterpret_cast<const double2*>(xc);
-            const double2 u1 = *reinterpret_cast<const double2*>(xc + 2);
-            s[0] = u0.x; s[1] = u0.y; s[2] = u1.x; s[3] = u1.y;
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) s[q] = 4 * blk + q < d ? xc[q] : 0.0;
-          }
+    if (tid < kTileRows) {
+      const int c = T.cid[tid];
+      int acc = 0;
+      if (c >= 0) {
+        const double lp = gauss_tile_finish(T.part, tid, g.c0, g.log_of_pdf);
+        acc = metropolis(a.lnl[c], lp, T.accept_u[tid]);
+        if (acc < 0) {
+          *a.nan_flag = 1;
+          acc = 0;
         }
-        if (a.mean) {
-          if (full) {
-            double2 m0 = *reinterpret_cast<const double2*>(a.mean + o);
-            double2 m1 = *reinterpret_cast<const double2*>(a.mean + o + 2);
-            double2 v0 = *reinterpret_cast<const double2*>(a.m2 + o);
-            double2 v1 = *reinterpret_cast<const double2*>(a.m2 + o + 2);
-            welford_update(s[0], n1, m0.x, v0.x);
-            welford_update(s[1], n1, m0.y, v0.y);
-            welford_update(s[2], n1, m1.x, v1.x);
-            welford_update(s[3], n1, m1.y, v1.y);
-            *reinterpret_cast<double2*>(a.mean + o) = m0;
-            *reinterpret_cast<double2*>(a.mean + o + 2) = m1;
-            *reinterpret_cast<double2*>(a.m2 + o) = v0;
-            *reinterpret_cast<double2*>(a.m2 + o + 2) = v1;
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (4 * blk + q < d) {
-                double mu = a.mean[o + q], v = a.m2[o + q];
-                welford_update(s[q], n1, mu, v);
-                a.mean[o + q] = mu;
-                a.m2[o + q] = v;
-              }
-          }
-        }
-        if (a.hist_row) {
-          if (full) {
-            *reinterpret_cast<double2*>(a.hist_row + o) = make_double2(s[0], s[1]);
-            *reinterpret_cast<double2*>(a.hist_row + o + 2) = make_double2(s[2], s[3]);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (4 * blk + q < d) a.hist_row[o + q] = s[q];
-          }
-        }
-      }
-      if (lane == 0) {
         if (acc) a.lnl[c] = lp;
         if (a.tr.accept) a.tr.accept[c] = acc;
         if (a.tr.lnl_prop) a.tr.lnl_prop[c] = lp;
-        n_acc += acc;
-        n_rej += !acc;
+      }
+      T.acc[tid] = acc;
+      const unsigned am = __ballot_sync(0xFFFFFFFFu, c >= 0 && acc);
+      const unsigned rm = __ballot_sync(0xFFFFFFFFu, c >= 0 && !acc);
+      n_acc += __popc(am);
+      n_rej += __popc(rm);
+    }
+    half_barrier(half);
+    // ---------------- stage C: the single write-back ------------------------------------
+    for (int jj = 0; jj < kTileRows / 8; ++jj) {
+      const int row = warp * (kTileRows / 8) + jj;
+      const int c = T.cid[row];
+      if (c < 0 || !has_blk) continue;
+      const int acc = T.acc[row];
+      double* xc = a.X + (size_t)c * a.ld + 4 * blk;
+      const double* prow = P + row * pld + 4 * blk;
+      const size_t o = (size_t)(c - a.chain_lo) * a.ld + 4 * blk;
+      double s[4] = {0, 0, 0, 0};
+      if (acc) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s[q] = 4 * blk + q < d ? prow[q] : 0.0;
+        if (full) {
+          *reinterpret_cast<double2*>(xc) = make_double2(s[0], s[1]);
+          *reinterpret_cast<double2*>(xc + 2) = make_double2(s[2], s[3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (4 * blk + q < d) xc[q] = s[q];
+        }
+      } else if (a.mean || a.hist_row) {
+        if (full) {
+          const double2 u0 = *reinterpret_cast<const double2*>(xc);
+          const double2 u1 = *reinterpret_cast<const double2*>(xc + 2);
+          s[0] = u0.x; s[1] = u0.y; s[2] = u1.x; s[3] = u1.y;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) s[q] = 4 * blk + q < d ? xc[q] : 0.0;
+        }
+      }
+      if (a.mean) {
+        if (full) {
+          double2 m0 = *reinterpret_cast<const double2*>(a.mean + o);
+          double2 m1 = *reinterpret_cast<const double2*>(a.mean + o + 2);
+          double2 v0 = *reinterpret_cast<const double2*>(a.m2 + o);
+          double2 v1 = *reinterpret_cast<const double2*>(a.m2 + o + 2);
+          welford_update(s[0], a.inv_n1, m0.x, v0.x);
+          welford_update(s[1], a.inv_n1, m0.y, v0.y);
+          welford_update(s[2], a.inv_n1, m1.x, v1.x);
+          welford_update(s[3], a.inv_n1, m1.y, v1.y);
+          *reinterpret_cast<double2*>(a.mean + o) = m0;
+          *reinterpret_cast<double2*>(a.mean + o + 2) = m1;
+          *reinterpret_cast<double2*>(a.m2 + o) = v0;
+          *reinterpret_cast<double2*>(a.m2 + o + 2) = v1;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (4 * blk + q < d) {
+              double mu = a.mean[o + q], v = a.m2[o + q];
+              welford_update(s[q], a.inv_n1, mu, v);
+              a.mean[o + q] = mu;
+              a.m2[o + q] = v;
+            }
+        }
+      }
+      if (a.hist_row) {
+        if (full) {
+          *reinterpret_cast<double2*>(a.hist_row + o) = make_double2(s[0], s[1]);
+          *reinterpret_cast<double2*>(a.hist_row + o + 2) = make_double2(s[2], s[3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (4 * blk + q < d) a.hist_row[o + q] = s[q];
+        }
       }
     }
     half_barrier(half);   // the tile buffers are reused by the next iteration
@@ -410,8 +485,10 @@ fused_gauss_kernel(const PhaseArgs a, const GaussArgs g) {
 }
 
 inline size_t fused_gauss_smem(int d) {
-  const size_t half_doubles = (size_t)kTileRows * gauss_pld(d) + 8 * kTileRows + kTileRows + kTileRows / 2;
-  return sizeof(double) * ((size_t)d * kWld + ((d + 1) & ~1) + 2 * half_doubles);
+  const size_t scratch_doubles = (sizeof(TileScratch) + 7) / 8;
+  const size_t half_doubles = (size_t)kTileRows * gauss_pld(d) + 1 + scratch_doubles;
+  return sizeof(double) * ((size_t)d * kWld + ((d + 1) & ~1) + ((d + 2) & ~1) + 2 * BPM_MAX_CR +
+                           2 * half_doubles);
 }
 
 // ---- d <= 4 analytic targets: one thread per chain ------------------------------------
@@ -470,9 +547,8 @@ __global__ void __launch_bounds__(128) fused_small_kernel(const PhaseArgs a, con
             S[q] = p == 0 ? df : __dadd_rn(S[q], df);
           }
       }
-    double e[4] = {0, 0, 0, 0}, nn[4];
-    if (dream) e4<REPLAY>(a, c, 0, e);
-    n4<REPLAY>(a, c, 0, nn);
+    double e[4], nn[4];
+    en4<REPLAY>(a, c, 0, e, nn);
     double delta = 0.0;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -498,7 +574,6 @@ __global__ void __launch_bounds__(128) fused_small_kernel(const PhaseArgs a, con
       *a.nan_flag = 1;
       acc = 0;
     }
-    const double n1 = (double)(a.mom_len + 1);
     const size_t o = (size_t)(c - a.chain_lo) * a.ld;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -507,7 +582,7 @@ __global__ void __launch_bounds__(128) fused_small_kernel(const PhaseArgs a, con
         if (acc) xc[q] = s;
         if (a.mean) {
           double mu = a.mean[o + q], v = a.m2[o + q];
-          welford_update(s, n1, mu, v);
+          welford_update(s, a.inv_n1, mu, v);
           a.mean[o + q] = mu;
           a.m2[o + q] = v;
         }

@@ -102,9 +102,8 @@ __global__ void __launch_bounds__(kThreads) propose_kernel(const PhaseArgs a) {
     for (int t = 0; t < kMaxBlocksPerLane; ++t) {
       const int b = sub + t * LPC;
       if (b < nblk) {
-        double e[4] = {0, 0, 0, 0}, n[4];
-        if (dream) e4<REPLAY>(a, c, b, e);
-        n4<REPLAY>(a, c, b, n);
+        double e[4], n[4];
+        en4<REPLAY>(a, c, b, e, n);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int i = 4 * b + q;
@@ -160,7 +159,6 @@ __global__ void __launch_bounds__(kThreads) accept_kernel(const PhaseArgs a) {
     }
     double* xc = a.X + (size_t)c * a.ld;
     const double* pr = a.prop + (size_t)gid * a.ld;
-    const double n1 = (double)(a.mom_len + 1);
 #pragma unroll
     for (int t = 0; t < kMaxBlocksPerLane; ++t) {
       const int b = sub + t * LPC;
@@ -177,7 +175,7 @@ __global__ void __launch_bounds__(kThreads) accept_kernel(const PhaseArgs a) {
             if (a.mean) {  // Welford update with the appended row (chain.py:51-54)
               const size_t o = (size_t)(c - a.chain_lo) * a.ld + i;
               double mu = a.mean[o], v = a.m2[o];
-              welford_update(s, n1, mu, v);
+              welford_update(s, a.inv_n1, mu, v);
               a.mean[o] = mu;
               a.m2[o] = v;
             }
@@ -391,8 +389,7 @@ __global__ void dump_draws_kernel(const PhaseArgs a, bpm_replay out) {
   for (int b = 0; b < nblk; ++b) {
     double z[4], e[4], n[4];
     z4<false>(a, c, b, z);
-    e4<false>(a, c, b, e);
-    n4<false>(a, c, b, n);
+    en4<false>(a, c, b, e, n);
     for (int q = 0; q < 4; ++q) {
       const int i = 4 * b + q;
       if (i < a.d) {

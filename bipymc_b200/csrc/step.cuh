@@ -36,6 +36,8 @@ struct PhaseArgs {
   int32_t adapt;       // burnin_gen > k && hist_len > n_cr_gen (dream.py:92,124)
   int64_t hist_len;    // rows in every chain's history BEFORE this generation's append
   int64_t mom_len;     // rows covered by the running moments BEFORE this generation
+  double inv_mom;      // 1 / mom_len
+  double inv_n1;       // 1 / (mom_len + 1)
   // CR state
   const double* p_cr;  // [n_cr]
   double* cr_delta;    // [N] per-chain jump statistic of this generation (or untouched)
@@ -120,6 +122,25 @@ struct ChainDraws {
   int r1[BPM_MAX_PAIRS], r2[BPM_MAX_PAIRS];  // POOL-LOCAL partner indices
 };
 
+// Layout of the per-chain scalar stream RNG_SCALAR (one Philox call per slot):
+//   slot 0   words x,y -> uniform behind the CR choice   | z,w -> uniform behind accept
+//   slot 1   words x,y -> uniform behind the gamma choice | z,w -> fallback dimension
+//   slot 2+p pair p: x,y -> first partner, z,w -> second partner (distinct, ordered:
+//            the law of np.random.permutation(P)[:2], demc.py:169 / dream.py:66)
+__device__ __forceinline__ double slot0_cr_u(const Philox4& q) { return u53(q.x, q.y); }
+__device__ __forceinline__ double slot0_accept_u(const Philox4& q) { return u53(q.z, q.w); }
+__device__ __forceinline__ double slot1_gamma_u(const Philox4& q) { return u53(q.x, q.y); }
+__device__ __forceinline__ int slot1_fallback(const Philox4& q, int d) {
+  return (int)below64(q.z, q.w, (uint32_t)d);
+}
+__device__ __forceinline__ void slot_pair(const Philox4& q, int n_pool, int& r1, int& r2) {
+  uint32_t i = below64(q.x, q.y, (uint32_t)n_pool);
+  uint32_t j = below64(q.z, q.w, (uint32_t)(n_pool - 1));
+  j += (j >= i);
+  r1 = (int)i;
+  r2 = (int)j;
+}
+
 template <bool REPLAY>
 __device__ __forceinline__ void chain_scalar_draws(const PhaseArgs& a, int c, int n_pool,
                                                    ChainDraws& D) {
@@ -135,30 +156,21 @@ __device__ __forceinline__ void chain_scalar_draws(const PhaseArgs& a, int c, in
         D.r2[p] = a.rp.pairs[((size_t)c * npair + p) * 2 + 1];
       }
   } else {
-    Philox4 s0 = draw4(a.rng, (uint32_t)c, RNG_SCALAR, 0);
-    Philox4 s1 = draw4(a.rng, (uint32_t)c, RNG_SCALAR, 1);
-    D.cr_idx = a.algo == BPM_ALGO_DREAM ? pick_cr(a.p_cr, a.n_cr, u53(s0.x, s0.y)) : 0;
-    D.gamma_u = u53(s1.x, s1.y);
-    D.fallback = (int)below64(s1.z, s1.w, (uint32_t)a.d);
+    const Philox4 s0 = draw4(a.rng, (uint32_t)c, RNG_SCALAR, 0);
+    const Philox4 s1 = draw4(a.rng, (uint32_t)c, RNG_SCALAR, 1);
+    D.cr_idx = a.algo == BPM_ALGO_DREAM ? pick_cr(a.p_cr, a.n_cr, slot0_cr_u(s0)) : 0;
+    D.gamma_u = slot1_gamma_u(s1);
+    D.fallback = slot1_fallback(s1, a.d);
 #pragma unroll
     for (int p = 0; p < BPM_MAX_PAIRS; ++p)
-      if (p < npair) {
-        Philox4 q = draw4(a.rng, (uint32_t)c, RNG_SCALAR, 2 + p);
-        // distinct pair, uniform over ordered pairs: same law as permutation(P)[:2]
-        uint32_t i = below64(q.x, q.y, (uint32_t)n_pool);
-        uint32_t j = below64(q.z, q.w, (uint32_t)(n_pool - 1));
-        j += (j >= i);
-        D.r1[p] = (int)i;
-        D.r2[p] = (int)j;
-      }
+      if (p < npair) slot_pair(draw4(a.rng, (uint32_t)c, RNG_SCALAR, 2 + p), n_pool, D.r1[p], D.r2[p]);
   }
 }
 
 template <bool REPLAY>
 __device__ __forceinline__ double accept_uniform(const PhaseArgs& a, int c) {
   if (REPLAY) return a.rp.accept_u[c];
-  Philox4 s0 = draw4(a.rng, (uint32_t)c, RNG_SCALAR, 0);
-  return u53(s0.z, s0.w);
+  return slot0_accept_u(draw4(a.rng, (uint32_t)c, RNG_SCALAR, 0));
 }
 
 // Four per-dimension draws for dims 4b .. 4b+3 of chain c.
@@ -175,47 +187,41 @@ __device__ __forceinline__ void z4(const PhaseArgs& a, int c, int b, double z[4]
     z[0] = u32d(q.x); z[1] = u32d(q.y); z[2] = u32d(q.z); z[3] = u32d(q.w);
   }
 }
+// Box jitter e (dream.py:83, var_box) and Gaussian jitter n (demc.py:182 / dream.py:84,
+// var_ball) for dims 4b .. 4b+3 from ONE Philox call: words x,y give four 16-bit
+// uniforms for e (a +-u_eps box on a 65536-point grid), words z,w two Box-Muller pairs for
+// n (sd epsilon ~ 1e-12: its shape only has to be Gaussian to fp32 accuracy).
 template <bool REPLAY>
-__device__ __forceinline__ void e4(const PhaseArgs& a, int c, int b, double e[4]) {
+__device__ __forceinline__ void en4(const PhaseArgs& a, int c, int b, double e[4], double n[4]) {
   if (REPLAY) {
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       int i = 4 * b + t;
       e[t] = (i < a.d && a.rp.e) ? a.rp.e[(size_t)c * a.d + i] : 0.0;
-    }
-  } else {
-    if (a.u_eps > 0.0) {
-      Philox4 q = draw4(a.rng, (uint32_t)c, RNG_E, (uint32_t)b);
-      const double lo = -a.u_eps, w = __dsub_rn(a.u_eps, lo);  // numpy: low + (high-low)*u
-      e[0] = __dadd_rn(lo, __dmul_rn(w, u32d(q.x)));
-      e[1] = __dadd_rn(lo, __dmul_rn(w, u32d(q.y)));
-      e[2] = __dadd_rn(lo, __dmul_rn(w, u32d(q.z)));
-      e[3] = __dadd_rn(lo, __dmul_rn(w, u32d(q.w)));
-    } else {
-      e[0] = e[1] = e[2] = e[3] = 0.0;  // var_box returns 0. and draws nothing (util.py:24-28)
-    }
-  }
-}
-template <bool REPLAY>
-__device__ __forceinline__ void n4(const PhaseArgs& a, int c, int b, double n[4]) {
-  if (REPLAY) {
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      int i = 4 * b + t;
       n[t] = (i < a.d && a.rp.nrm) ? a.rp.nrm[(size_t)c * a.d + i] : 0.0;
     }
   } else {
-    if (a.eps > 0.0) {
-      Philox4 q = draw4(a.rng, (uint32_t)c, RNG_N, (uint32_t)b);
-      float f0, f1, f2, f3;
-      normal2(q.x, q.y, f0, f1);
-      normal2(q.z, q.w, f2, f3);
-      n[0] = __dmul_rn(a.eps, (double)f0);
-      n[1] = __dmul_rn(a.eps, (double)f1);
-      n[2] = __dmul_rn(a.eps, (double)f2);
-      n[3] = __dmul_rn(a.eps, (double)f3);
-    } else {
-      n[0] = n[1] = n[2] = n[3] = 0.0;  // var_ball returns 0. and draws nothing (util.py:11-16)
+    e[0] = e[1] = e[2] = e[3] = 0.0;  // var_box returns 0. and draws nothing (util.py:24-28)
+    n[0] = n[1] = n[2] = n[3] = 0.0;  // var_ball returns 0. and draws nothing (util.py:11-16)
+    if (a.u_eps > 0.0 || a.eps > 0.0) {
+      const Philox4 q = draw4(a.rng, (uint32_t)c, RNG_EN, (uint32_t)b);
+      if (a.u_eps > 0.0) {
+        const double lo = -a.u_eps, w = __dsub_rn(a.u_eps, lo);  // numpy: low + (high-low)*u
+        const double k = 1.0 / 65536.0;
+        e[0] = __dadd_rn(lo, __dmul_rn(w, ((double)(q.x & 0xFFFFu) + 0.5) * k));
+        e[1] = __dadd_rn(lo, __dmul_rn(w, ((double)(q.x >> 16) + 0.5) * k));
+        e[2] = __dadd_rn(lo, __dmul_rn(w, ((double)(q.y & 0xFFFFu) + 0.5) * k));
+        e[3] = __dadd_rn(lo, __dmul_rn(w, ((double)(q.y >> 16) + 0.5) * k));
+      }
+      if (a.eps > 0.0) {
+        float f0, f1, f2, f3;
+        normal2_16(q.z, f0, f1);
+        normal2_16(q.w, f2, f3);
+        n[0] = __dmul_rn(a.eps, (double)f0);
+        n[1] = __dmul_rn(a.eps, (double)f1);
+        n[2] = __dmul_rn(a.eps, (double)f2);
+        n[3] = __dmul_rn(a.eps, (double)f3);
+      }
     }
   }
 }
@@ -278,7 +284,7 @@ __device__ __forceinline__ double cr_variance(const PhaseArgs& a, int c, int i) 
     if (sd == 0.0) sd = 1e-12;
     return __dmul_rn(sd, sd);
   }
-  double var = __dmul_rn(a.m2[(size_t)co * a.ld + i], 1.0 / (double)a.mom_len);
+  double var = __dmul_rn(a.m2[(size_t)co * a.ld + i], a.inv_mom);
   if (!(var > 0.0)) var = 1e-12 * 1e-12;
   return var;
 }
@@ -290,9 +296,9 @@ __device__ __forceinline__ double cr_term(double cur, double prop, double var) {
 }
 
 // Explicitly rounded Welford update (identical bits in every kernel that uses it).
-__device__ __forceinline__ void welford_update(double s, double n1, double& mu, double& m2) {
+__device__ __forceinline__ void welford_update(double s, double inv_n1, double& mu, double& m2) {
   const double dl = __dsub_rn(s, mu);
-  const double mu2 = __dadd_rn(mu, __ddiv_rn(dl, n1));
+  const double mu2 = __dadd_rn(mu, __dmul_rn(dl, inv_n1));   // inv_n1 = 1 / (rows + 1), from the host
   m2 = __dadd_rn(m2, __dmul_rn(dl, __dsub_rn(s, mu2)));
   mu = mu2;
 }
