@@ -152,7 +152,7 @@ def run_ours(args):
     K, W = args.steps, args.warmup
     s = DreamMpi(tgt.ln_like, np.zeros(DIM), n_chains=N, varepsilon=np.arange(DIM) + 1.0, seed=42,
                  n_cr_gen=50, burnin_gen=2000, device=local_rank,
-                 history=args.history, history_reserve=K + W + SETUP_GENS + 8)
+                 history=args.history, history_reserve=K + W + SETUP_GENS + 8, fused=args.fused)
     lib, h = s._libh, s._handle
     n_local = len(s.rank_chain_ids)
 
@@ -271,6 +271,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--history", default="full", choices=["full", "none"])
+    ap.add_argument("--fused", type=int, default=1, help="1 warp-specialised fused kernel (default), 2 two-halves fused kernel, 0 split path")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     args = ap.parse_args()

@@ -291,7 +291,7 @@ struct bpm_engine {
     if (fused_ok && !a.tr.prop) {
       int done = 0;
       prof_begin(4, s);
-      BPM_TRY(bpm::try_fused_phase<REPLAY>(*this_target(), a, s, &done));
+      BPM_TRY(bpm::try_fused_phase<REPLAY>(*this_target(), a, s, fused_ok, &done));
       if (done) { prof_end(s); return 0; }
       if (prof_on) { ev_pool.push_back(recs.back().a); ev_pool.push_back(recs.back().b); recs.pop_back(); }
     }

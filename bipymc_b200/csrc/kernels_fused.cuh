@@ -175,10 +175,9 @@ struct GaussArgs {
   int log_of_pdf;
 };
 
-// Per-half shared-memory scratch for one 64-chain tile.
+// Shared-memory scratch of one 64-chain tile.
 struct TileScratch {
   double part[8 * kTileRows];   // per-warp partial row sums of squares
-  double lnl[kTileRows];        // ln_like(proposal)
   double gamma_u[kTileRows];
   double accept_u[kTileRows];
   int cid[kTileRows];           // global chain id, -1 = empty row
@@ -189,293 +188,342 @@ struct TileScratch {
   int pb[kTileRows][BPM_MAX_PAIRS];
 };
 
-template <bool REPLAY, bool CENTER>
-__global__ void __launch_bounds__(2 * kHalfThreads, 1)
-fused_gauss_kernel(const PhaseArgs a, const GaussArgs g) {
-  extern __shared__ __align__(16) double smem[];
-  const int d = a.d, pld = d | 1;
-  double* Ws = smem;
-  double* mus = Ws + d * kWld;
-  double* gam = mus + ((d + 1) & ~1);            // gamma_base[d'] for d' = 0..d (dream.py:61)
-  double* cdf = gam + ((d + 2) & ~1);            // normalised CR cdf (dream.py:51)
-  double* crv = cdf + BPM_MAX_CR;                // CR values (dream.py:113)
-  double* half_base = crv + BPM_MAX_CR;
-  const int half = threadIdx.x >> 8;
-  const int tid = threadIdx.x & (kHalfThreads - 1);
-  const int warp = tid >> 5, lane = tid & 31;
-  const size_t scratch_doubles = (sizeof(TileScratch) + 7) / 8;
-  const size_t half_doubles = (size_t)kTileRows * pld + 1 + scratch_doubles;
-  double* P = half_base + half * half_doubles;
-  TileScratch& T = *reinterpret_cast<TileScratch*>(P + ((kTileRows * pld + 1) & ~1));
+// Kernel-lifetime tables in shared memory.
+struct GaussTables {
+  double* Ws;    // [d][112] whitening matrix, zero-padded columns
+  double* mus;   // [d]
+  double* gam;   // gamma_base[d'] for d' = 0..d (dream.py:61)
+  double* cdf;   // normalised CR cdf (dream.py:51)
+  double* crv;   // CR values (dream.py:113)
+};
+__host__ __device__ inline size_t gauss_table_doubles(int d) {
+  return (size_t)d * kWld + ((d + 1) & ~1) + ((d + 2) & ~1) + 2 * BPM_MAX_CR;
+}
+__host__ __device__ inline size_t gauss_tile_doubles(int d) {
+  return (((size_t)kTileRows * (d | 1) + 1) & ~(size_t)1) + (sizeof(TileScratch) + 7) / 8;
+}
 
-  const bool dream = a.algo == BPM_ALGO_DREAM;
-  const int npair = dream ? a.del_pairs : 1;
-  load_W_shared(Ws, mus, g.W, g.mu, d, g.r, threadIdx.x, 2 * kHalfThreads);
-  for (int dp = threadIdx.x; dp <= d; dp += 2 * kHalfThreads)
-    gam[dp] = dp == 0 ? 0.0
-                      : __ddiv_rn(a.gamma_num, __dsqrt_rn(__dmul_rn(__dmul_rn(2.0, (double)a.del_pairs),
-                                                                    (double)dp)));
-  if (threadIdx.x == 0) {
+__device__ __forceinline__ GaussTables carve_tables(double* smem, int d) {
+  GaussTables t;
+  t.Ws = smem;
+  t.mus = t.Ws + d * kWld;
+  t.gam = t.mus + ((d + 1) & ~1);
+  t.cdf = t.gam + ((d + 2) & ~1);
+  t.crv = t.cdf + BPM_MAX_CR;
+  return t;
+}
+
+__device__ __forceinline__ void fill_tables(const PhaseArgs& a, const GaussArgs& g, const GaussTables& t,
+                                            int tid, int nthreads) {
+  load_W_shared(t.Ws, t.mus, g.W, g.mu, a.d, g.r, tid, nthreads);
+  for (int dp = tid; dp <= a.d; dp += nthreads)
+    t.gam[dp] = dp == 0 ? 0.0
+                        : __ddiv_rn(a.gamma_num, __dsqrt_rn(__dmul_rn(__dmul_rn(2.0, (double)a.del_pairs),
+                                                                      (double)dp)));
+  if (tid == 0) {
     double tot = 0.0;
     for (int m = 0; m < a.n_cr; ++m) tot = __dadd_rn(tot, a.p_cr[m]);
     double acc = 0.0;
     for (int m = 0; m < a.n_cr; ++m) {
       acc = __dadd_rn(acc, a.p_cr[m]);
-      cdf[m] = __ddiv_rn(acc, tot);
-      crv[m] = __ddiv_rn((double)(m + 1), (double)a.n_cr);
+      t.cdf[m] = __ddiv_rn(acc, tot);
+      t.crv[m] = __ddiv_rn((double)(m + 1), (double)a.n_cr);
     }
   }
-  __syncthreads();
+}
 
-  const PhaseLists L = phase_lists(a);
-  const int n_tiles = (L.n_self + kTileRows - 1) / kTileRows;
+// stage D: per-chain scalar draws, one thread per (chain, slot)
+template <bool REPLAY>
+__device__ __forceinline__ void tile_stage_draws(const PhaseArgs& a, const PhaseLists& L,
+                                                 const GaussTables& tb, TileScratch& T, int tile,
+                                                 int gtid, int gthreads) {
+  const bool dream = a.algo == BPM_ALGO_DREAM;
+  const int npair = dream ? a.del_pairs : 1;
   const int nslots = 2 + npair;
+  for (int idx = gtid; idx < kTileRows * nslots; idx += gthreads) {
+    const int row = idx / nslots, slot = idx - row * nslots;
+    const int gid = tile * kTileRows + row;
+    bool valid = gid < L.n_self;
+    const int c = valid ? L.self[gid] : 0;
+    valid = valid && c >= a.chain_lo && c < a.chain_hi;
+    if (slot == 0) T.cid[row] = valid ? c : -1;
+    if (!valid) continue;
+    if (REPLAY) {
+      if (slot == 0) {
+        T.cr_idx[row] = dream ? a.rp.cr_idx[c] : 0;
+        T.accept_u[row] = a.rp.accept_u[c];
+      } else if (slot == 1) {
+        T.gamma_u[row] = a.rp.gamma_u[c];
+        T.fallback[row] = dream ? a.rp.fallback_dim[c] : -1;
+      } else {
+        const int p = slot - 2;
+        T.pa[row][p] = L.pool[a.rp.pairs[((size_t)c * npair + p) * 2 + 0]];
+        T.pb[row][p] = L.pool[a.rp.pairs[((size_t)c * npair + p) * 2 + 1]];
+      }
+    } else {
+      const Philox4 q = draw4(a.rng, (uint32_t)c, RNG_SCALAR, (uint32_t)slot);
+      if (slot == 0) {
+        int m = 0;
+        if (dream) {
+          const double u = slot0_cr_u(q);
+          for (int j = 0; j < a.n_cr; ++j)
+            if (tb.cdf[j] <= u) m = j + 1;
+          m = m < a.n_cr ? m : a.n_cr - 1;
+        }
+        T.cr_idx[row] = m;
+        T.accept_u[row] = slot0_accept_u(q);
+      } else if (slot == 1) {
+        T.gamma_u[row] = slot1_gamma_u(q);
+        T.fallback[row] = slot1_fallback(q, a.d);
+      } else {
+        int r1, r2;
+        slot_pair(q, L.n_pool, r1, r2);
+        T.pa[row][slot - 2] = L.pool[r1];
+        T.pb[row][slot - 2] = L.pool[r2];
+      }
+    }
+  }
+}
+
+// stage A: crossover mask, row gathers, proposal -> P tile (a warp per chain row)
+template <bool REPLAY>
+__device__ __forceinline__ void tile_stage_propose(const PhaseArgs& a, const GaussTables& tb,
+                                                   TileScratch& T, double* __restrict__ P, int pld,
+                                                   int gwarp, int gwarps, int lane) {
+  const int d = a.d;
+  const bool dream = a.algo == BPM_ALGO_DREAM;
+  const int npair = dream ? a.del_pairs : 1;
   const int blk = lane;                  // this lane's dimension block (4 doubles)
   const bool has_blk = 4 * blk < d;
   const bool full = 4 * blk + 3 < d;
-  unsigned n_acc = 0, n_rej = 0;
-
-  for (int tile = blockIdx.x * 2 + half; tile < n_tiles; tile += 2 * gridDim.x) {
-    // ---------------- stage D: per-chain scalar draws, one thread per (chain, slot) --------
-    for (int idx = tid; idx < kTileRows * nslots; idx += kHalfThreads) {
-      const int row = idx / nslots, slot = idx - row * nslots;
-      const int gid = tile * kTileRows + row;
-      bool valid = gid < L.n_self;
-      const int c = valid ? L.self[gid] : 0;
-      valid = valid && c >= a.chain_lo && c < a.chain_hi;
-      if (slot == 0) T.cid[row] = valid ? c : -1;
-      if (!valid) continue;
-      if (REPLAY) {
-        if (slot == 0) {
-          T.cr_idx[row] = dream ? a.rp.cr_idx[c] : 0;
-          T.accept_u[row] = a.rp.accept_u[c];
-        } else if (slot == 1) {
-          T.gamma_u[row] = a.rp.gamma_u[c];
-          T.fallback[row] = dream ? a.rp.fallback_dim[c] : -1;
-        } else {
-          const int p = slot - 2;
-          T.pa[row][p] = L.pool[a.rp.pairs[((size_t)c * npair + p) * 2 + 0]];
-          T.pb[row][p] = L.pool[a.rp.pairs[((size_t)c * npair + p) * 2 + 1]];
-        }
-      } else {
-        const Philox4 q = draw4(a.rng, (uint32_t)c, RNG_SCALAR, (uint32_t)slot);
-        if (slot == 0) {
-          int m = 0;
-          if (dream) {
-            const double u = slot0_cr_u(q);
-            for (int j = 0; j < a.n_cr; ++j)
-              if (cdf[j] <= u) m = j + 1;
-            m = m < a.n_cr ? m : a.n_cr - 1;
-          }
-          T.cr_idx[row] = m;
-          T.accept_u[row] = slot0_accept_u(q);
-        } else if (slot == 1) {
-          T.gamma_u[row] = slot1_gamma_u(q);
-          T.fallback[row] = slot1_fallback(q, d);
-        } else {
-          int r1, r2;
-          slot_pair(q, L.n_pool, r1, r2);
-          T.pa[row][slot - 2] = L.pool[r1];
-          T.pb[row][slot - 2] = L.pool[r2];
-        }
-      }
+  for (int row = gwarp; row < kTileRows; row += gwarps) {
+    const int c = T.cid[row];
+    double* prow = P + row * pld;
+    if (c < 0) {
+      if (has_blk)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (4 * blk + q < d) prow[4 * blk + q] = 0.0;
+      continue;
     }
-    half_barrier(half);
-    // ---------------- stage A: mask, gathers, proposal (warp per chain) -----------------
-    for (int jj = 0; jj < kTileRows / 8; ++jj) {
-      const int row = warp * (kTileRows / 8) + jj;
-      const int c = T.cid[row];
-      double* prow = P + row * pld;
-      if (c < 0) {
-        if (has_blk)
+    // issue the row gathers first: they do not depend on the mask draws
+    double cur[4] = {0, 0, 0, 0}, S[4] = {0, 0, 0, 0};
+    if (has_blk) {
+      const double* xc = a.X + (size_t)c * a.ld + 4 * blk;
+      if (full) {
+        const double2 u0 = *reinterpret_cast<const double2*>(xc);
+        const double2 u1 = *reinterpret_cast<const double2*>(xc + 2);
+        cur[0] = u0.x; cur[1] = u0.y; cur[2] = u1.x; cur[3] = u1.y;
+      } else {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (4 * blk + q < d) prow[4 * blk + q] = 0.0;
-        continue;
+        for (int q = 0; q < 4; ++q) cur[q] = 4 * blk + q < d ? xc[q] : 0.0;
       }
-      // issue the row gathers first: they do not depend on the mask draws
-      double cur[4] = {0, 0, 0, 0}, S[4] = {0, 0, 0, 0};
-      if (has_blk) {
-        const double* xc = a.X + (size_t)c * a.ld + 4 * blk;
-        if (full) {
-          const double2 u0 = *reinterpret_cast<const double2*>(xc);
-          const double2 u1 = *reinterpret_cast<const double2*>(xc + 2);
-          cur[0] = u0.x; cur[1] = u0.y; cur[2] = u1.x; cur[3] = u1.y;
-        } else {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) cur[q] = 4 * blk + q < d ? xc[q] : 0.0;
-        }
-#pragma unroll
-        for (int p = 0; p < BPM_MAX_PAIRS; ++p) {
-          if (p < npair) {
-            const double* pa = a.X + (size_t)T.pa[row][p] * a.ld + 4 * blk;
-            const double* pb = a.X + (size_t)T.pb[row][p] * a.ld + 4 * blk;
-            double va[4], vb[4];
-            if (full) {
-              const double2 s0 = *reinterpret_cast<const double2*>(pa);
-              const double2 s1 = *reinterpret_cast<const double2*>(pa + 2);
-              const double2 t0 = *reinterpret_cast<const double2*>(pb);
-              const double2 t1 = *reinterpret_cast<const double2*>(pb + 2);
-              va[0] = s0.x; va[1] = s0.y; va[2] = s1.x; va[3] = s1.y;
-              vb[0] = t0.x; vb[1] = t0.y; vb[2] = t1.x; vb[3] = t1.y;
-            } else {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                va[q] = 4 * blk + q < d ? pa[q] : 0.0;
-                vb[q] = 4 * blk + q < d ? pb[q] : 0.0;
-              }
-            }
+      for (int p = 0; p < BPM_MAX_PAIRS; ++p) {
+        if (p < npair) {
+          const double* pa = a.X + (size_t)T.pa[row][p] * a.ld + 4 * blk;
+          const double* pb = a.X + (size_t)T.pb[row][p] * a.ld + 4 * blk;
+          double va[4], vb[4];
+          if (full) {
+            const double2 s0 = *reinterpret_cast<const double2*>(pa);
+            const double2 s1 = *reinterpret_cast<const double2*>(pa + 2);
+            const double2 t0 = *reinterpret_cast<const double2*>(pb);
+            const double2 t1 = *reinterpret_cast<const double2*>(pb + 2);
+            va[0] = s0.x; va[1] = s0.y; va[2] = s1.x; va[3] = s1.y;
+            vb[0] = t0.x; vb[1] = t0.y; vb[2] = t1.x; vb[3] = t1.y;
+          } else {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const double df = __dsub_rn(va[q], vb[q]);
-              S[q] = p == 0 ? df : __dadd_rn(S[q], df);
+              va[q] = 4 * blk + q < d ? pa[q] : 0.0;
+              vb[q] = 4 * blk + q < d ? pb[q] : 0.0;
             }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const double df = __dsub_rn(va[q], vb[q]);
+            S[q] = p == 0 ? df : __dadd_rn(S[q], df);
           }
         }
       }
-      uint32_t mbits = 0xFu;
-      double gamma;
-      const double gu = T.gamma_u[row];
-      if (dream) {
-        mbits = 0u;
-        const double cr = crv[T.cr_idx[row]];
-        if (has_blk) {
-          double z[4];
-          z4<REPLAY>(a, c, blk, z);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (4 * blk + q < d && z[q] <= cr) mbits |= 1u << q;
-        }
-        int d_prime = __reduce_add_sync(0xFFFFFFFFu, __popc(mbits));
-        if (d_prime == 0) {
-          const int fb = T.fallback[row] < 0 ? 0 : T.fallback[row];
-          if ((fb >> 2) == blk) mbits |= 1u << (fb & 3);
-          d_prime = 1;
-        }
-        gamma = gam[d_prime];
-        if (a.gamma_jump) gamma = gu < a.gamma_p0 ? gamma : 1.0;
-      } else {
-        gamma = demc_gamma(a, gu);
-      }
-      double delta = 0.0;
+    }
+    uint32_t mbits = 0xFu;
+    double gamma;
+    const double gu = T.gamma_u[row];
+    if (dream) {
+      mbits = 0u;
+      const double cr = tb.crv[T.cr_idx[row]];
       if (has_blk) {
-        double e[4], nn[4];
-        en4<REPLAY>(a, c, blk, e, nn);
+        double z[4];
+        z4<REPLAY>(a, c, blk, z);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int i = 4 * blk + q;
-          if (i < d) {
-            double pr;
-            if (dream) {
-              pr = dream_prop(cur[q], S[q], e[q], nn[q], gamma, (mbits >> q) & 1u ? 1.0 : 0.0);
-              if (a.adapt) delta += cr_term(cur[q], pr, cr_variance<REPLAY>(a, c, i));
-            } else {
-              pr = demc_prop(cur[q], S[q], nn[q], gamma);
-            }
-            prow[i] = pr;
+        for (int q = 0; q < 4; ++q)
+          if (4 * blk + q < d && z[q] <= cr) mbits |= 1u << q;
+      }
+      int d_prime = __reduce_add_sync(0xFFFFFFFFu, __popc(mbits));
+      if (d_prime == 0) {
+        const int fb = T.fallback[row] < 0 ? 0 : T.fallback[row];
+        if ((fb >> 2) == blk) mbits |= 1u << (fb & 3);
+        d_prime = 1;
+      }
+      gamma = tb.gam[d_prime];
+      if (a.gamma_jump) gamma = gu < a.gamma_p0 ? gamma : 1.0;
+    } else {
+      gamma = demc_gamma(a, gu);
+    }
+    double delta = 0.0;
+    if (has_blk) {
+      double e[4], nn[4];
+      en4<REPLAY>(a, c, blk, e, nn);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = 4 * blk + q;
+        if (i < d) {
+          double pr;
+          if (dream) {
+            pr = dream_prop(cur[q], S[q], e[q], nn[q], gamma, (mbits >> q) & 1u ? 1.0 : 0.0);
+            if (a.adapt) delta += cr_term(cur[q], pr, cr_variance<REPLAY>(a, c, i));
+          } else {
+            pr = demc_prop(cur[q], S[q], nn[q], gamma);
           }
-        }
-      }
-      if (dream) {
-        delta = group_sum_d<32>(delta);
-        if (lane == 0) {
-          a.cr_pick[c] = a.adapt ? T.cr_idx[row] : -1;
-          a.cr_delta[c] = delta;
+          prow[i] = pr;
         }
       }
     }
-    half_barrier(half);
-    // ---------------- stage B: quadratic form ----------------------------------------
-    gauss_tile_rowsums<CENTER>(P, pld, Ws, mus, d, T.part, warp, lane);
-    half_barrier(half);
-    if (tid < kTileRows) {
-      const int c = T.cid[tid];
-      int acc = 0;
-      if (c >= 0) {
-        const double lp = gauss_tile_finish(T.part, tid, g.c0, g.log_of_pdf);
-        acc = metropolis(a.lnl[c], lp, T.accept_u[tid]);
-        if (acc < 0) {
-          *a.nan_flag = 1;
-          acc = 0;
-        }
-        if (acc) a.lnl[c] = lp;
-        if (a.tr.accept) a.tr.accept[c] = acc;
-        if (a.tr.lnl_prop) a.tr.lnl_prop[c] = lp;
-      }
-      T.acc[tid] = acc;
-      const unsigned am = __ballot_sync(0xFFFFFFFFu, c >= 0 && acc);
-      const unsigned rm = __ballot_sync(0xFFFFFFFFu, c >= 0 && !acc);
-      n_acc += __popc(am);
-      n_rej += __popc(rm);
-    }
-    half_barrier(half);
-    // ---------------- stage C: the single write-back ------------------------------------
-    for (int jj = 0; jj < kTileRows / 8; ++jj) {
-      const int row = warp * (kTileRows / 8) + jj;
-      const int c = T.cid[row];
-      if (c < 0 || !has_blk) continue;
-      const int acc = T.acc[row];
-      double* xc = a.X + (size_t)c * a.ld + 4 * blk;
-      const double* prow = P + row * pld + 4 * blk;
-      const size_t o = (size_t)(c - a.chain_lo) * a.ld + 4 * blk;
-      double s[4] = {0, 0, 0, 0};
-      if (acc) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) s[q] = 4 * blk + q < d ? prow[q] : 0.0;
-        if (full) {
-          *reinterpret_cast<double2*>(xc) = make_double2(s[0], s[1]);
-          *reinterpret_cast<double2*>(xc + 2) = make_double2(s[2], s[3]);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (4 * blk + q < d) xc[q] = s[q];
-        }
-      } else if (a.mean || a.hist_row) {
-        if (full) {
-          const double2 u0 = *reinterpret_cast<const double2*>(xc);
-          const double2 u1 = *reinterpret_cast<const double2*>(xc + 2);
-          s[0] = u0.x; s[1] = u0.y; s[2] = u1.x; s[3] = u1.y;
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) s[q] = 4 * blk + q < d ? xc[q] : 0.0;
-        }
-      }
-      if (a.mean) {
-        if (full) {
-          double2 m0 = *reinterpret_cast<const double2*>(a.mean + o);
-          double2 m1 = *reinterpret_cast<const double2*>(a.mean + o + 2);
-          double2 v0 = *reinterpret_cast<const double2*>(a.m2 + o);
-          double2 v1 = *reinterpret_cast<const double2*>(a.m2 + o + 2);
-          welford_update(s[0], a.inv_n1, m0.x, v0.x);
-          welford_update(s[1], a.inv_n1, m0.y, v0.y);
-          welford_update(s[2], a.inv_n1, m1.x, v1.x);
-          welford_update(s[3], a.inv_n1, m1.y, v1.y);
-          *reinterpret_cast<double2*>(a.mean + o) = m0;
-          *reinterpret_cast<double2*>(a.mean + o + 2) = m1;
-          *reinterpret_cast<double2*>(a.m2 + o) = v0;
-          *reinterpret_cast<double2*>(a.m2 + o + 2) = v1;
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (4 * blk + q < d) {
-              double mu = a.mean[o + q], v = a.m2[o + q];
-              welford_update(s[q], a.inv_n1, mu, v);
-              a.mean[o + q] = mu;
-              a.m2[o + q] = v;
-            }
-        }
-      }
-      if (a.hist_row) {
-        if (full) {
-          *reinterpret_cast<double2*>(a.hist_row + o) = make_double2(s[0], s[1]);
-          *reinterpret_cast<double2*>(a.hist_row + o + 2) = make_double2(s[2], s[3]);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (4 * blk + q < d) a.hist_row[o + q] = s[q];
-        }
+    if (dream) {
+      delta = group_sum_d<32>(delta);
+      if (lane == 0) {
+        a.cr_pick[c] = a.adapt ? T.cr_idx[row] : -1;
+        a.cr_delta[c] = delta;
       }
     }
+  }
+}
+
+// after stage B: likelihood value + Metropolis decision of chain row `row` (one thread each);
+// must be called by whole warps (ballots).  Adds to the caller's accept / reject tallies.
+__device__ __forceinline__ void tile_stage_decide(const PhaseArgs& a, const GaussArgs& g, TileScratch& T,
+                                                  int row, unsigned& n_acc, unsigned& n_rej) {
+  const int c = T.cid[row];
+  int acc = 0;
+  if (c >= 0) {
+    const double lp = gauss_tile_finish(T.part, row, g.c0, g.log_of_pdf);
+    acc = metropolis(a.lnl[c], lp, T.accept_u[row]);
+    if (acc < 0) {
+      *a.nan_flag = 1;
+      acc = 0;
+    }
+    if (acc) a.lnl[c] = lp;
+    if (a.tr.accept) a.tr.accept[c] = acc;
+    if (a.tr.lnl_prop) a.tr.lnl_prop[c] = lp;
+  }
+  T.acc[row] = acc;
+  n_acc += __popc(__ballot_sync(0xFFFFFFFFu, c >= 0 && acc));
+  n_rej += __popc(__ballot_sync(0xFFFFFFFFu, c >= 0 && !acc));
+}
+
+// stage C: the single write-back (state, running moments, history row)
+__device__ __forceinline__ void tile_stage_writeback(const PhaseArgs& a, const TileScratch& T,
+                                                     const double* __restrict__ P, int pld, int gwarp,
+                                                     int gwarps, int lane) {
+  const int d = a.d;
+  const int blk = lane;
+  if (4 * blk >= d) return;
+  const bool full = 4 * blk + 3 < d;
+  for (int row = gwarp; row < kTileRows; row += gwarps) {
+    const int c = T.cid[row];
+    if (c < 0) continue;
+    const int acc = T.acc[row];
+    double* xc = a.X + (size_t)c * a.ld + 4 * blk;
+    const double* prow = P + row * pld + 4 * blk;
+    const size_t o = (size_t)(c - a.chain_lo) * a.ld + 4 * blk;
+    double s[4] = {0, 0, 0, 0};
+    if (acc) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s[q] = 4 * blk + q < d ? prow[q] : 0.0;
+      if (full) {
+        *reinterpret_cast<double2*>(xc) = make_double2(s[0], s[1]);
+        *reinterpret_cast<double2*>(xc + 2) = make_double2(s[2], s[3]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (4 * blk + q < d) xc[q] = s[q];
+      }
+    } else if (a.mean || a.hist_row) {
+      if (full) {
+        const double2 u0 = *reinterpret_cast<const double2*>(xc);
+        const double2 u1 = *reinterpret_cast<const double2*>(xc + 2);
+        s[0] = u0.x; s[1] = u0.y; s[2] = u1.x; s[3] = u1.y;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s[q] = 4 * blk + q < d ? xc[q] : 0.0;
+      }
+    }
+    if (a.mean) {
+      if (full) {
+        double2 m0 = *reinterpret_cast<const double2*>(a.mean + o);
+        double2 m1 = *reinterpret_cast<const double2*>(a.mean + o + 2);
+        double2 v0 = *reinterpret_cast<const double2*>(a.m2 + o);
+        double2 v1 = *reinterpret_cast<const double2*>(a.m2 + o + 2);
+        welford_update(s[0], a.inv_n1, m0.x, v0.x);
+        welford_update(s[1], a.inv_n1, m0.y, v0.y);
+        welford_update(s[2], a.inv_n1, m1.x, v1.x);
+        welford_update(s[3], a.inv_n1, m1.y, v1.y);
+        *reinterpret_cast<double2*>(a.mean + o) = m0;
+        *reinterpret_cast<double2*>(a.mean + o + 2) = m1;
+        *reinterpret_cast<double2*>(a.m2 + o) = v0;
+        *reinterpret_cast<double2*>(a.m2 + o + 2) = v1;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (4 * blk + q < d) {
+            double mu = a.mean[o + q], v = a.m2[o + q];
+            welford_update(s[q], a.inv_n1, mu, v);
+            a.mean[o + q] = mu;
+            a.m2[o + q] = v;
+          }
+      }
+    }
+    if (a.hist_row) {
+      if (full) {
+        *reinterpret_cast<double2*>(a.hist_row + o) = make_double2(s[0], s[1]);
+        *reinterpret_cast<double2*>(a.hist_row + o + 2) = make_double2(s[2], s[3]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (4 * blk + q < d) a.hist_row[o + q] = s[q];
+      }
+    }
+  }
+}
+
+// Variant 1: two symmetric 256-thread halves per CTA, each running D -> A -> B -> C on its
+// own tile with its own named barrier (kept for A/B measurements: bpm_set_fused(h, 2)).
+template <bool REPLAY, bool CENTER>
+__global__ void __launch_bounds__(2 * kHalfThreads, 1)
+fused_gauss_kernel(const PhaseArgs a, const GaussArgs g) {
+  extern __shared__ __align__(16) double smem[];
+  const int d = a.d, pld = d | 1;
+  const GaussTables tb = carve_tables(smem, d);
+  const int half = threadIdx.x >> 8;
+  const int tid = threadIdx.x & (kHalfThreads - 1);
+  const int warp = tid >> 5, lane = tid & 31;
+  double* P = smem + gauss_table_doubles(d) + half * gauss_tile_doubles(d);
+  TileScratch& T = *reinterpret_cast<TileScratch*>(P + (((size_t)kTileRows * pld + 1) & ~(size_t)1));
+  fill_tables(a, g, tb, threadIdx.x, 2 * kHalfThreads);
+  __syncthreads();
+  const PhaseLists L = phase_lists(a);
+  const int n_tiles = (L.n_self + kTileRows - 1) / kTileRows;
+  unsigned n_acc = 0, n_rej = 0;
+  for (int tile = blockIdx.x * 2 + half; tile < n_tiles; tile += 2 * gridDim.x) {
+    tile_stage_draws<REPLAY>(a, L, tb, T, tile, tid, kHalfThreads);
+    half_barrier(half);
+    tile_stage_propose<REPLAY>(a, tb, T, P, pld, warp, 8, lane);
+    half_barrier(half);
+    gauss_tile_rowsums<CENTER>(P, pld, tb.Ws, tb.mus, d, T.part, warp, lane);
+    half_barrier(half);
+    if (tid < kTileRows) tile_stage_decide(a, g, T, tid, n_acc, n_rej);
+    half_barrier(half);
+    tile_stage_writeback(a, T, P, pld, warp, 8, lane);
     half_barrier(half);   // the tile buffers are reused by the next iteration
   }
   if (lane == 0) {
@@ -485,10 +533,89 @@ fused_gauss_kernel(const PhaseArgs a, const GaussArgs g) {
 }
 
 inline size_t fused_gauss_smem(int d) {
-  const size_t scratch_doubles = (sizeof(TileScratch) + 7) / 8;
-  const size_t half_doubles = (size_t)kTileRows * gauss_pld(d) + 1 + scratch_doubles;
-  return sizeof(double) * ((size_t)d * kWld + ((d + 1) & ~1) + ((d + 2) & ~1) + 2 * BPM_MAX_CR +
-                           2 * half_doubles);
+  return sizeof(double) * (gauss_table_doubles(d) + 2 * gauss_tile_doubles(d));
+}
+
+// Variant 2 (default): warp-specialised producer / consumer pipeline.
+//   8 consumer warps (128 registers each) run nothing but the FP64 tile GEMM + the
+//   Metropolis decision; 12 producer warps (72 registers each) run the latency-bound
+//   stages -- draws, row gathers, proposal, write-back.  Two tile buffers rotate between
+//   the groups through named barriers (FULL[b]: producers -> consumers, DONE[b]: back), so
+//   the FP64 pipe works on tile i while the producers finalise tile i-1 and gather tile
+//   i+1.  setmaxnreg moves registers from the producer to the consumer warpgroups.
+constexpr int kConsWarps = 8, kProdWarps = 12;
+constexpr int kWsThreads = 32 * (kConsWarps + kProdWarps);   // 640
+constexpr int kProdThreads = 32 * kProdWarps;
+constexpr int kConsThreads = 32 * kConsWarps;
+enum { BAR_PROD = 1, BAR_CONS = 2, BAR_FULL0 = 3, BAR_FULL1 = 4, BAR_DONE0 = 5, BAR_DONE1 = 6 };
+
+__device__ __forceinline__ void nbar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void nbar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+template <bool REPLAY, bool CENTER>
+__global__ void __launch_bounds__(kWsThreads, 1)
+fused_gauss_ws_kernel(const PhaseArgs a, const GaussArgs g) {
+  extern __shared__ __align__(16) double smem[];
+  const int d = a.d, pld = d | 1;
+  const GaussTables tb = carve_tables(smem, d);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* P0 = smem + gauss_table_doubles(d);
+  double* P1 = P0 + gauss_tile_doubles(d);
+  const size_t t_off = ((size_t)kTileRows * pld + 1) & ~(size_t)1;
+  fill_tables(a, g, tb, threadIdx.x, kWsThreads);
+  __syncthreads();
+  const PhaseLists L = phase_lists(a);
+  const int n_tiles = (L.n_self + kTileRows - 1) / kTileRows;
+  const int n_my = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+
+  if (warp < kConsWarps) {
+    // ------------------------------ consumers ------------------------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+    unsigned n_acc = 0, n_rej = 0;
+    for (int i = 0; i < n_my; ++i) {
+      const int b = i & 1;
+      double* P = b ? P1 : P0;
+      TileScratch& T = *reinterpret_cast<TileScratch*>(P + t_off);
+      nbar_sync(BAR_FULL0 + b, kWsThreads);            // producers filled buffer b
+      gauss_tile_rowsums<CENTER>(P, pld, tb.Ws, tb.mus, d, T.part, warp, lane);
+      nbar_sync(BAR_CONS, kConsThreads);
+      if (threadIdx.x < kTileRows) tile_stage_decide(a, g, T, threadIdx.x, n_acc, n_rej);
+      nbar_arrive(BAR_DONE0 + b, kWsThreads);          // decisions of buffer b are in T.acc
+    }
+    if (lane == 0) {
+      if (n_acc) atomicAdd(a.n_acc, (unsigned long long)n_acc);
+      if (n_rej) atomicAdd(a.n_rej, (unsigned long long)n_rej);
+    }
+  } else {
+    // ------------------------------ producers ------------------------------------------
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    const int pw = warp - kConsWarps;
+    const int ptid = threadIdx.x - kConsThreads;
+    for (int i = 0; i <= n_my; ++i) {
+      if (i < n_my) {
+        const int b = i & 1;
+        double* P = b ? P1 : P0;
+        TileScratch& T = *reinterpret_cast<TileScratch*>(P + t_off);
+        const int tile = blockIdx.x + i * gridDim.x;
+        tile_stage_draws<REPLAY>(a, L, tb, T, tile, ptid, kProdThreads);
+        nbar_sync(BAR_PROD, kProdThreads);
+        tile_stage_propose<REPLAY>(a, tb, T, P, pld, pw, kProdWarps, lane);
+        nbar_arrive(BAR_FULL0 + b, kWsThreads);
+      }
+      if (i >= 1) {
+        const int b2 = (i - 1) & 1;
+        double* P = b2 ? P1 : P0;
+        const TileScratch& T = *reinterpret_cast<const TileScratch*>(P + t_off);
+        nbar_sync(BAR_DONE0 + b2, kWsThreads);          // consumers decided tile i-1
+        tile_stage_writeback(a, T, P, pld, pw, kProdWarps, lane);
+      }
+      nbar_sync(BAR_PROD, kProdThreads);   // buffer (i-1)&1 is free again before it is redrawn
+    }
+  }
 }
 
 // ---- d <= 4 analytic targets: one thread per chain ------------------------------------
@@ -601,27 +728,42 @@ __global__ void __launch_bounds__(128) fused_small_kernel(const PhaseArgs a, con
 }
 
 template <bool REPLAY>
-inline int try_fused_phase(const TargetView& tv, const PhaseArgs& a, cudaStream_t s, int* done) {
+inline int try_fused_phase(const TargetView& tv, const PhaseArgs& a, cudaStream_t s, int variant,
+                           int* done) {
   *done = 0;
   if (tv.target == BPM_TARGET_GAUSS && gauss_rows_supported(a.d, tv.r) && (a.ld % 2) == 0) {
     GaussArgs g;
     g.mu = tv.mu; g.W = tv.W; g.r = tv.r; g.c0 = tv.c0; g.log_of_pdf = tv.log_of_pdf;
     const size_t sm = fused_gauss_smem(a.d);
     const int n_tiles = (a.nA + kTileRows - 1) / kTileRows;
-    int grid = (n_tiles + 1) / 2;
-    if (grid > 148) grid = 148;
-    if (grid < 1) grid = 1;
     cudaError_t e;
-    if (tv.mu_is_zero) {
-      e = cudaFuncSetAttribute(fused_gauss_kernel<REPLAY, false>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-      if (e != cudaSuccess) return 1;
-      fused_gauss_kernel<REPLAY, false><<<grid, 2 * kHalfThreads, sm, s>>>(a, g);
+    if (variant == 2) {
+      int grid = (n_tiles + 1) / 2;
+      grid = grid > 148 ? 148 : (grid < 1 ? 1 : grid);
+      if (tv.mu_is_zero) {
+        e = cudaFuncSetAttribute(fused_gauss_kernel<REPLAY, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return 1;
+        fused_gauss_kernel<REPLAY, false><<<grid, 2 * kHalfThreads, sm, s>>>(a, g);
+      } else {
+        e = cudaFuncSetAttribute(fused_gauss_kernel<REPLAY, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return 1;
+        fused_gauss_kernel<REPLAY, true><<<grid, 2 * kHalfThreads, sm, s>>>(a, g);
+      }
     } else {
-      e = cudaFuncSetAttribute(fused_gauss_kernel<REPLAY, true>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-      if (e != cudaSuccess) return 1;
-      fused_gauss_kernel<REPLAY, true><<<grid, 2 * kHalfThreads, sm, s>>>(a, g);
+      const int grid = n_tiles > 148 ? 148 : (n_tiles < 1 ? 1 : n_tiles);
+      if (tv.mu_is_zero) {
+        e = cudaFuncSetAttribute(fused_gauss_ws_kernel<REPLAY, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return 1;
+        fused_gauss_ws_kernel<REPLAY, false><<<grid, kWsThreads, sm, s>>>(a, g);
+      } else {
+        e = cudaFuncSetAttribute(fused_gauss_ws_kernel<REPLAY, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return 1;
+        fused_gauss_ws_kernel<REPLAY, true><<<grid, kWsThreads, sm, s>>>(a, g);
+      }
     }
     if (cudaGetLastError() != cudaSuccess) return 1;
     *done = 1;

@@ -311,7 +311,7 @@ class DeMcMpi(object):
         h = C.c_void_p()
         _lib.check(self._libh.bpm_create(C.byref(cfg), C.byref(h)))
         self._handle = h
-        _lib.check(self._libh.bpm_set_fused(h, 1 if self._fused else 0))
+        _lib.check(self._libh.bpm_set_fused(h, int(self._fused)))   # 0 split, 1 fused, 2 fused (two-halves variant)
         self._target = resolve_device_target(self.log_like_fn, self._ln_kwargs)
         if self._target is not None:
             if self._target.dim != d:

@@ -87,8 +87,8 @@ def test_native_demc_bimodal_matches_oracle_replay(fused):
     _native_vs_oracle(s, otargets.BimodeGauss2D().ln_like, gens=12, run_kwargs=dict(epsilon=1e-6))
 
 
-@pytest.mark.parametrize("fused", [True, False], ids=["fused", "split"])
-@pytest.mark.parametrize("dim,n", [(7, 9), (100, 40), (33, 17)])
+@pytest.mark.parametrize("fused", [1, 0, 2], ids=["fused", "split", "fused-halves"])
+@pytest.mark.parametrize("dim,n", [(7, 9), (100, 40), (33, 17), (100, 200)])
 def test_native_dream_gauss_matches_oracle_replay(dim, n, fused):
     from bipymc_b200 import DreamMpi, targets
     np.random.seed(3)
@@ -227,17 +227,19 @@ def test_full_size_properties_1e5_chains_100d():
     tgt = targets.Gauss_100D()
     N, d, G = 100000, 100, 6
     runs = []
-    for fused in (True, False):
+    for fused in (1, 0, 2):
         np.random.seed(0)
         s = DreamMpi(tgt.ln_like, np.zeros(d), n_chains=N, seed=77, burnin_gen=1000, n_cr_gen=2,
                      fused=fused, varepsilon=1.0)
         s.run_mcmc(N * (G + 1))
         runs.append(s)
-    a, b = runs
+    a, b, c2 = runs
     ha, hb = a._hist.tensor(), b._hist.tensor()
     assert ha.shape == (G + 1, N, d)
     assert torch.equal(ha, hb), "fused and split paths must agree bit for bit"
-    assert torch.equal(a._lnl, b._lnl)
+    assert torch.equal(ha, c2._hist.tensor()), "both fused variants must agree bit for bit"
+    assert torch.equal(a._lnl, b._lnl) and torch.equal(a._lnl, c2._lnl)
+    del c2
     np.testing.assert_allclose(a.p_cr, b.p_cr, rtol=1e-12)
     # history row G == live population; every chain moved at most once per generation
     assert torch.equal(ha[G], a._X)
