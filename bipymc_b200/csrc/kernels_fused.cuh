@@ -177,7 +177,6 @@ struct GaussArgs {
 
 // Shared-memory scratch of one 64-chain tile.
 struct TileScratch {
-  double part[8 * kTileRows];   // per-warp partial row sums of squares
   double gamma_u[kTileRows];
   double accept_u[kTileRows];
   int cid[kTileRows];           // global chain id, -1 = empty row
@@ -199,9 +198,11 @@ struct GaussTables {
 __host__ __device__ inline size_t gauss_table_doubles(int d) {
   return (size_t)d * kWld + ((d + 1) & ~1) + ((d + 2) & ~1) + 2 * BPM_MAX_CR;
 }
-__host__ __device__ inline size_t gauss_tile_doubles(int d) {
-  return (((size_t)kTileRows * (d | 1) + 1) & ~(size_t)1) + (sizeof(TileScratch) + 7) / 8;
+// one proposal tile: P[64][pld] followed by the consumers' partial sums part[8][64]
+__host__ __device__ inline size_t gauss_ptile_doubles(int d) {
+  return (((size_t)kTileRows * (d | 1) + 1) & ~(size_t)1) + 8 * kTileRows;
 }
+__host__ __device__ inline size_t gauss_scratch_doubles() { return (sizeof(TileScratch) + 7) / 8; }
 
 __device__ __forceinline__ GaussTables carve_tables(double* smem, int d) {
   GaussTables t;
@@ -232,6 +233,20 @@ __device__ __forceinline__ void fill_tables(const PhaseArgs& a, const GaussArgs&
   }
 }
 
+// One instruction pulls a whole row into L2 (no registers, no shared memory): issued for
+// every row a tile will touch, one pipeline step ahead of its use.
+__device__ __forceinline__ void l2_prefetch_row(const double* p, int bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// Streaming (evict-first) access for arrays that are touched once per generation -- running
+// moments and history -- so they do not push the randomly gathered population out of L2.
+__device__ __forceinline__ double2 ld_stream2(const double* p) {
+  return __ldcs(reinterpret_cast<const double2*>(p));
+}
+__device__ __forceinline__ void st_stream2(double* p, double x, double y) {
+  __stcs(reinterpret_cast<double2*>(p), make_double2(x, y));
+}
+
 // stage D: per-chain scalar draws, one thread per (chain, slot)
 template <bool REPLAY>
 __device__ __forceinline__ void tile_stage_draws(const PhaseArgs& a, const PhaseLists& L,
@@ -248,6 +263,13 @@ __device__ __forceinline__ void tile_stage_draws(const PhaseArgs& a, const Phase
     valid = valid && c >= a.chain_lo && c < a.chain_hi;
     if (slot == 0) T.cid[row] = valid ? c : -1;
     if (!valid) continue;
+    const int row_bytes = a.ld * 8;
+    if (slot == 0) {
+      l2_prefetch_row(a.X + (size_t)c * a.ld, row_bytes);
+      if (a.mean) l2_prefetch_row(a.mean + (size_t)(c - a.chain_lo) * a.ld, row_bytes);
+    } else if (slot == 1) {
+      if (a.m2) l2_prefetch_row(a.m2 + (size_t)(c - a.chain_lo) * a.ld, row_bytes);
+    }
     if (REPLAY) {
       if (slot == 0) {
         T.cr_idx[row] = dream ? a.rp.cr_idx[c] : 0;
@@ -259,6 +281,8 @@ __device__ __forceinline__ void tile_stage_draws(const PhaseArgs& a, const Phase
         const int p = slot - 2;
         T.pa[row][p] = L.pool[a.rp.pairs[((size_t)c * npair + p) * 2 + 0]];
         T.pb[row][p] = L.pool[a.rp.pairs[((size_t)c * npair + p) * 2 + 1]];
+        l2_prefetch_row(a.X + (size_t)T.pa[row][p] * a.ld, row_bytes);
+        l2_prefetch_row(a.X + (size_t)T.pb[row][p] * a.ld, row_bytes);
       }
     } else {
       const Philox4 q = draw4(a.rng, (uint32_t)c, RNG_SCALAR, (uint32_t)slot);
@@ -278,8 +302,11 @@ __device__ __forceinline__ void tile_stage_draws(const PhaseArgs& a, const Phase
       } else {
         int r1, r2;
         slot_pair(q, L.n_pool, r1, r2);
-        T.pa[row][slot - 2] = L.pool[r1];
-        T.pb[row][slot - 2] = L.pool[r2];
+        const int ga = L.pool[r1], gb = L.pool[r2];
+        T.pa[row][slot - 2] = ga;
+        T.pb[row][slot - 2] = gb;
+        l2_prefetch_row(a.X + (size_t)ga * a.ld, row_bytes);
+        l2_prefetch_row(a.X + (size_t)gb * a.ld, row_bytes);
       }
     }
   }
@@ -307,9 +334,20 @@ __device__ __forceinline__ void tile_stage_propose(const PhaseArgs& a, const Gau
       continue;
     }
     // issue the row gathers first: they do not depend on the mask draws
-    double cur[4] = {0, 0, 0, 0}, S[4] = {0, 0, 0, 0};
+    double cur[4] = {0, 0, 0, 0}, S[4] = {0, 0, 0, 0}, var[4] = {0, 0, 0, 0};
+    const bool welford_var = dream && a.adapt && !(REPLAY && a.hist_base != nullptr);
     if (has_blk) {
       const double* xc = a.X + (size_t)c * a.ld + 4 * blk;
+      if (welford_var) {   // same arithmetic as cr_variance(), loads issued with the gathers
+        const double* mp = a.m2 + (size_t)(c - a.chain_lo) * a.ld + 4 * blk;
+        if (full) {
+          const double2 w0 = ld_stream2(mp), w1 = ld_stream2(mp + 2);
+          var[0] = w0.x; var[1] = w0.y; var[2] = w1.x; var[3] = w1.y;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) var[q] = 4 * blk + q < d ? mp[q] : 0.0;
+        }
+      }
       if (full) {
         const double2 u0 = *reinterpret_cast<const double2*>(xc);
         const double2 u1 = *reinterpret_cast<const double2*>(xc + 2);
@@ -381,7 +419,16 @@ __device__ __forceinline__ void tile_stage_propose(const PhaseArgs& a, const Gau
           double pr;
           if (dream) {
             pr = dream_prop(cur[q], S[q], e[q], nn[q], gamma, (mbits >> q) & 1u ? 1.0 : 0.0);
-            if (a.adapt) delta += cr_term(cur[q], pr, cr_variance<REPLAY>(a, c, i));
+            if (a.adapt) {
+              double v;
+              if (welford_var) {
+                v = __dmul_rn(var[q], a.inv_mom);
+                if (!(v > 0.0)) v = 1e-12 * 1e-12;
+              } else {
+                v = cr_variance<REPLAY>(a, c, i);
+              }
+              delta += cr_term(cur[q], pr, v);
+            }
           } else {
             pr = demc_prop(cur[q], S[q], nn[q], gamma);
           }
@@ -402,11 +449,12 @@ __device__ __forceinline__ void tile_stage_propose(const PhaseArgs& a, const Gau
 // after stage B: likelihood value + Metropolis decision of chain row `row` (one thread each);
 // must be called by whole warps (ballots).  Adds to the caller's accept / reject tallies.
 __device__ __forceinline__ void tile_stage_decide(const PhaseArgs& a, const GaussArgs& g, TileScratch& T,
-                                                  int row, unsigned& n_acc, unsigned& n_rej) {
+                                                  const double* __restrict__ part, int row,
+                                                  unsigned& n_acc, unsigned& n_rej) {
   const int c = T.cid[row];
   int acc = 0;
   if (c >= 0) {
-    const double lp = gauss_tile_finish(T.part, row, g.c0, g.log_of_pdf);
+    const double lp = gauss_tile_finish(part, row, g.c0, g.log_of_pdf);
     acc = metropolis(a.lnl[c], lp, T.accept_u[row]);
     if (acc < 0) {
       *a.nan_flag = 1;
@@ -460,18 +508,16 @@ __device__ __forceinline__ void tile_stage_writeback(const PhaseArgs& a, const T
     }
     if (a.mean) {
       if (full) {
-        double2 m0 = *reinterpret_cast<const double2*>(a.mean + o);
-        double2 m1 = *reinterpret_cast<const double2*>(a.mean + o + 2);
-        double2 v0 = *reinterpret_cast<const double2*>(a.m2 + o);
-        double2 v1 = *reinterpret_cast<const double2*>(a.m2 + o + 2);
+        double2 m0 = ld_stream2(a.mean + o), m1 = ld_stream2(a.mean + o + 2);
+        double2 v0 = ld_stream2(a.m2 + o), v1 = ld_stream2(a.m2 + o + 2);
         welford_update(s[0], a.inv_n1, m0.x, v0.x);
         welford_update(s[1], a.inv_n1, m0.y, v0.y);
         welford_update(s[2], a.inv_n1, m1.x, v1.x);
         welford_update(s[3], a.inv_n1, m1.y, v1.y);
-        *reinterpret_cast<double2*>(a.mean + o) = m0;
-        *reinterpret_cast<double2*>(a.mean + o + 2) = m1;
-        *reinterpret_cast<double2*>(a.m2 + o) = v0;
-        *reinterpret_cast<double2*>(a.m2 + o + 2) = v1;
+        st_stream2(a.mean + o, m0.x, m0.y);
+        st_stream2(a.mean + o + 2, m1.x, m1.y);
+        st_stream2(a.m2 + o, v0.x, v0.y);
+        st_stream2(a.m2 + o + 2, v1.x, v1.y);
       } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -485,8 +531,8 @@ __device__ __forceinline__ void tile_stage_writeback(const PhaseArgs& a, const T
     }
     if (a.hist_row) {
       if (full) {
-        *reinterpret_cast<double2*>(a.hist_row + o) = make_double2(s[0], s[1]);
-        *reinterpret_cast<double2*>(a.hist_row + o + 2) = make_double2(s[2], s[3]);
+        st_stream2(a.hist_row + o, s[0], s[1]);
+        st_stream2(a.hist_row + o + 2, s[2], s[3]);
       } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -507,8 +553,11 @@ fused_gauss_kernel(const PhaseArgs a, const GaussArgs g) {
   const int half = threadIdx.x >> 8;
   const int tid = threadIdx.x & (kHalfThreads - 1);
   const int warp = tid >> 5, lane = tid & 31;
-  double* P = smem + gauss_table_doubles(d) + half * gauss_tile_doubles(d);
-  TileScratch& T = *reinterpret_cast<TileScratch*>(P + (((size_t)kTileRows * pld + 1) & ~(size_t)1));
+  double* P = smem + gauss_table_doubles(d) + half * gauss_ptile_doubles(d);
+  double* part = P + (((size_t)kTileRows * pld + 1) & ~(size_t)1);
+  TileScratch& T = *reinterpret_cast<TileScratch*>(smem + gauss_table_doubles(d) +
+                                                   2 * gauss_ptile_doubles(d) +
+                                                   half * gauss_scratch_doubles());
   fill_tables(a, g, tb, threadIdx.x, 2 * kHalfThreads);
   __syncthreads();
   const PhaseLists L = phase_lists(a);
@@ -519,9 +568,9 @@ fused_gauss_kernel(const PhaseArgs a, const GaussArgs g) {
     half_barrier(half);
     tile_stage_propose<REPLAY>(a, tb, T, P, pld, warp, 8, lane);
     half_barrier(half);
-    gauss_tile_rowsums<CENTER>(P, pld, tb.Ws, tb.mus, d, T.part, warp, lane);
+    gauss_tile_rowsums<CENTER>(P, pld, tb.Ws, tb.mus, d, part, warp, lane);
     half_barrier(half);
-    if (tid < kTileRows) tile_stage_decide(a, g, T, tid, n_acc, n_rej);
+    if (tid < kTileRows) tile_stage_decide(a, g, T, part, tid, n_acc, n_rej);
     half_barrier(half);
     tile_stage_writeback(a, T, P, pld, warp, 8, lane);
     half_barrier(half);   // the tile buffers are reused by the next iteration
@@ -532,8 +581,9 @@ fused_gauss_kernel(const PhaseArgs a, const GaussArgs g) {
   }
 }
 
+// shared memory of both fused variants: tables, 2 proposal tiles, 3 scratch blocks
 inline size_t fused_gauss_smem(int d) {
-  return sizeof(double) * (gauss_table_doubles(d) + 2 * gauss_tile_doubles(d));
+  return sizeof(double) * (gauss_table_doubles(d) + 2 * gauss_ptile_doubles(d) + 3 * gauss_scratch_doubles());
 }
 
 // Variant 2 (default): warp-specialised producer / consumer pipeline.
@@ -563,9 +613,11 @@ fused_gauss_ws_kernel(const PhaseArgs a, const GaussArgs g) {
   const int d = a.d, pld = d | 1;
   const GaussTables tb = carve_tables(smem, d);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* P0 = smem + gauss_table_doubles(d);
-  double* P1 = P0 + gauss_tile_doubles(d);
-  const size_t t_off = ((size_t)kTileRows * pld + 1) & ~(size_t)1;
+  double* Pbuf = smem + gauss_table_doubles(d);
+  const size_t p_stride = gauss_ptile_doubles(d);
+  const size_t part_off = ((size_t)kTileRows * pld + 1) & ~(size_t)1;
+  double* Tbuf = Pbuf + 2 * p_stride;
+  const size_t t_stride = gauss_scratch_doubles();
   fill_tables(a, g, tb, threadIdx.x, kWsThreads);
   __syncthreads();
   const PhaseLists L = phase_lists(a);
@@ -574,17 +626,18 @@ fused_gauss_ws_kernel(const PhaseArgs a, const GaussArgs g) {
 
   if (warp < kConsWarps) {
     // ------------------------------ consumers ------------------------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     unsigned n_acc = 0, n_rej = 0;
     for (int i = 0; i < n_my; ++i) {
       const int b = i & 1;
-      double* P = b ? P1 : P0;
-      TileScratch& T = *reinterpret_cast<TileScratch*>(P + t_off);
+      double* P = Pbuf + b * p_stride;
+      double* part = P + part_off;
+      TileScratch& T = *reinterpret_cast<TileScratch*>(Tbuf + (i % 3) * t_stride);
       nbar_sync(BAR_FULL0 + b, kWsThreads);            // producers filled buffer b
-      gauss_tile_rowsums<CENTER>(P, pld, tb.Ws, tb.mus, d, T.part, warp, lane);
+      gauss_tile_rowsums<CENTER>(P, pld, tb.Ws, tb.mus, d, part, warp, lane);
       nbar_sync(BAR_CONS, kConsThreads);
-      if (threadIdx.x < kTileRows) tile_stage_decide(a, g, T, threadIdx.x, n_acc, n_rej);
-      nbar_arrive(BAR_DONE0 + b, kWsThreads);          // decisions of buffer b are in T.acc
+      if (threadIdx.x < kTileRows) tile_stage_decide(a, g, T, part, threadIdx.x, n_acc, n_rej);
+      nbar_arrive(BAR_DONE0 + b, kWsThreads);          // decisions of tile i are in T.acc
     }
     if (lane == 0) {
       if (n_acc) atomicAdd(a.n_acc, (unsigned long long)n_acc);
@@ -592,28 +645,35 @@ fused_gauss_ws_kernel(const PhaseArgs a, const GaussArgs g) {
     }
   } else {
     // ------------------------------ producers ------------------------------------------
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    // software pipeline, one iteration = draws + L2 prefetch of tile i+1 | proposal of
+    // tile i | write-back of tile i-1
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     const int pw = warp - kConsWarps;
     const int ptid = threadIdx.x - kConsThreads;
+    if (n_my > 0)
+      tile_stage_draws<REPLAY>(a, L, tb, *reinterpret_cast<TileScratch*>(Tbuf), blockIdx.x, ptid,
+                               kProdThreads);
+    nbar_sync(BAR_PROD, kProdThreads);
     for (int i = 0; i <= n_my; ++i) {
+      if (i + 1 < n_my)
+        tile_stage_draws<REPLAY>(a, L, tb, *reinterpret_cast<TileScratch*>(Tbuf + ((i + 1) % 3) * t_stride),
+                                 blockIdx.x + (i + 1) * gridDim.x, ptid, kProdThreads);
       if (i < n_my) {
         const int b = i & 1;
-        double* P = b ? P1 : P0;
-        TileScratch& T = *reinterpret_cast<TileScratch*>(P + t_off);
-        const int tile = blockIdx.x + i * gridDim.x;
-        tile_stage_draws<REPLAY>(a, L, tb, T, tile, ptid, kProdThreads);
-        nbar_sync(BAR_PROD, kProdThreads);
+        double* P = Pbuf + b * p_stride;
+        TileScratch& T = *reinterpret_cast<TileScratch*>(Tbuf + (i % 3) * t_stride);
         tile_stage_propose<REPLAY>(a, tb, T, P, pld, pw, kProdWarps, lane);
         nbar_arrive(BAR_FULL0 + b, kWsThreads);
       }
       if (i >= 1) {
         const int b2 = (i - 1) & 1;
-        double* P = b2 ? P1 : P0;
-        const TileScratch& T = *reinterpret_cast<const TileScratch*>(P + t_off);
+        const double* P = Pbuf + b2 * p_stride;
+        const TileScratch& T = *reinterpret_cast<const TileScratch*>(Tbuf + ((i - 1) % 3) * t_stride);
         nbar_sync(BAR_DONE0 + b2, kWsThreads);          // consumers decided tile i-1
         tile_stage_writeback(a, T, P, pld, pw, kProdWarps, lane);
       }
-      nbar_sync(BAR_PROD, kProdThreads);   // buffer (i-1)&1 is free again before it is redrawn
+      // draws of tile i+1 are complete and buffers of tile i-1 are free for every producer
+      nbar_sync(BAR_PROD, kProdThreads);
     }
   }
 }
