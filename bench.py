@@ -151,7 +151,7 @@ def run_ours(args):
     np.random.seed(42)
     K, W = args.steps, args.warmup
     s = DreamMpi(tgt.ln_like, np.zeros(DIM), n_chains=N, varepsilon=np.arange(DIM) + 1.0, seed=42,
-                 n_cr_gen=50, burnin_gen=2000, device=local_rank,
+                 n_cr_gen=50, burnin_gen=args.burnin_gen, device=local_rank,
                  history=args.history, history_reserve=K + W + SETUP_GENS + 8, fused=args.fused)
     lib, h = s._libh, s._handle
     n_local = len(s.rank_chain_ids)
@@ -202,7 +202,8 @@ def run_ours(args):
     hist_b = 8 * d if args.history == "full" else 0
     # algorithmic bytes per chain-step: own row + 6 partner rows + write + lnL r/w,
     # + running moments r/w (mean, M2) during burn-in adaptation, + history append
-    step_bytes = 64 * d + 16 + 32 * d + hist_b
+    adapt_b = 8 * d if args.burnin_gen > SETUP_GENS + W + K else 0      # M2 read by the CR statistic
+    step_bytes = 64 * d + 16 + 24 * d + adapt_b + hist_b
     per_kind_bytes = {"fused_phase": step_bytes,
                       "propose": 8 * d * (1 + 6 + 1 + 1),          # own + partners + M2 read + proposal write
                       "likelihood": 8 * d + 8,                      # proposal read + lnL write
@@ -250,7 +251,8 @@ def run_ours(args):
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "configs[1]: DREAM on Gauss_100D(rho=0.5), %d chains per GPU" % N_PER_GPU,
                            "n_chains": N, "dim": DIM, "del_pairs": 3, "n_cr": 3, "n_cr_gen": 50,
-                           "burnin_gen": 2000, "history": args.history, "cr_adaptation": "on",
+                           "burnin_gen": args.burnin_gen, "history": args.history,
+                           "cr_adaptation": "on" if args.burnin_gen > SETUP_GENS + W + K else "off",
                            "init": "theta_0 + N(0, diag(Sigma)), %d untimed setup generations" % SETUP_GENS,
                            "rng": "philox4x32-10 seed 42", "parallelism": "chains sharded x%d" % world,
                            "l2": "working set per generation (state 80 MB + moments 160 MB + history "
@@ -272,6 +274,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--history", default="full", choices=["full", "none"])
     ap.add_argument("--fused", type=int, default=1, help="1 warp-specialised fused kernel (default), 2 two-halves fused kernel, 0 split path")
+    ap.add_argument("--burnin-gen", type=int, default=2000, help="DREAM burnin_gen (2000 = tests/test_100dgauss.py:109)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     args = ap.parse_args()
