@@ -87,8 +87,10 @@ SIGNATURES = {
     "bpm_generations_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                        C.c_int32]),
     "bpm_moments_from_history": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p]),
-    "bpm_outlier_reset": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p, C.POINTER(C.c_int32),
-                                    C.c_void_p]),
+    "bpm_omega_track": (C.c_int, [C.c_void_p, C.c_int32]),
+    "bpm_omega": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "bpm_outlier_reset": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p, C.c_void_p,
+                                    C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_void_p]),
     "bpm_rhat": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_int64, C.c_void_p, C.c_void_p]),
 }
 

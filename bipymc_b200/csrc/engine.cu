@@ -11,6 +11,8 @@
 #include "../../include/bipymc_b200.h"
 #include "kernels_generic.cuh"
 #include "kernels_fused.cuh"
+#include "diagnostics.cuh"
+#include <cub/device/device_radix_sort.cuh>
 
 namespace {
 
@@ -82,6 +84,18 @@ struct bpm_engine {
   double* hX = nullptr;
   double* hL = nullptr;
   int fused_ok = 1;  // allow the fused fast paths
+  // diagnostics (diagnostics.cuh): Omega tracking, IQR reset, R-hat scratch
+  double* omega_sum = nullptr;   // [N] sum of lnL per chain since tracking started
+  double* omega_buf = nullptr;   // [2][N] Omega means / sorted copy
+  double* diag_out = nullptr;    // [3] threshold, Q1, Q3
+  int32_t* diag_i = nullptr;     // [0] best chain, [1] number of resets
+  void* sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+  double* rh_mean = nullptr;     // [n_local][ld] scratch for history moments
+  double* rh_m2 = nullptr;
+  double* rh_out = nullptr;      // [dim]
+  bool omega_on = false;
+  int64_t omega_cnt = 0;
   // optional per-kernel timing (bpm_profile): CUDA events around every launch, by kind
   struct Rec { int kind; cudaEvent_t a, b; };
   bool prof_on = false;
@@ -106,6 +120,8 @@ struct bpm_engine {
     cudaFree(perm); cudaFree(flip); cudaFree(prop); cudaFree(lnl_prop); cudaFree(cr_delta);
     cudaFree(cr_pick); cudaFree(p_cr); cudaFree(cr_dm); cudaFree(cr_cnt); cudaFree(cr_part); cudaFree(cr_block);
     cudaFree(counters); cudaFree(nan_flag); cudaFree(tparams); cudaFree(hX); cudaFree(hL);
+    cudaFree(omega_sum); cudaFree(omega_buf); cudaFree(diag_out); cudaFree(diag_i); cudaFree(sort_tmp);
+    cudaFree(rh_mean); cudaFree(rh_m2); cudaFree(rh_out);
     for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ev_pool) cudaEventDestroy(e);
   }
@@ -265,6 +281,15 @@ struct bpm_engine {
     return 0;
   }
 
+  int track_omega(const bpm_state* st, cudaStream_t s) {
+    if (!omega_on) return 0;
+    const int nloc = cfg.chain_hi - cfg.chain_lo;
+    bpm::omega_accum_kernel<<<cdiv(nloc, 256), 256, 0, s>>>(st->lnl, omega_sum, cfg.chain_lo, cfg.chain_hi);
+    CU_TRY(cudaGetLastError());
+    omega_cnt += 1;
+    return 0;
+  }
+
   int end(cudaStream_t s) {
     if (cfg.algo != BPM_ALGO_DREAM) return 0;
     prof_begin(5, s);
@@ -331,6 +356,7 @@ struct bpm_engine {
     BPM_TRY(phase<REPLAY>(st, k_gen, 0, rp, tr, s));
     BPM_TRY(phase<REPLAY>(st, k_gen, 1, rp, tr, s));
     BPM_TRY(end(s));
+    BPM_TRY(track_omega(st, s));
     st->hist_len += 1;
     if (st->mom_len > 0) st->mom_len += 1;
     return 0;
@@ -616,6 +642,7 @@ int bpm_end_generation(bpm_handle h, bpm_state* st, bpm_stream stream) {
   if (!h->in_generation) return fail("bpm_end_generation without bpm_begin_generation");
   CU_TRY(cudaSetDevice(h->cfg.device));
   BPM_TRY(h->end((cudaStream_t)stream));
+  BPM_TRY(h->track_omega(st, (cudaStream_t)stream));
   st->hist_len += 1;
   if (st->mom_len > 0) st->mom_len += 1;
   h->in_generation = false;
@@ -695,11 +722,108 @@ int bpm_test_permutation(uint64_t seed, uint64_t g_abs, int32_t n, int32_t* out_
   return 0;
 }
 
-int bpm_outlier_reset(bpm_handle, bpm_state*, const double*, int32_t*, bpm_stream) {
-  return fail("bpm_outlier_reset: not implemented yet");
+int bpm_omega_track(bpm_handle h, int32_t on) {
+  if (!h) return fail("null handle");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  const int N = h->cfg.n_chains;
+  if (on) {
+    if (!h->omega_sum) CU_TRY(cudaMalloc(&h->omega_sum, sizeof(double) * N));
+    CU_TRY(cudaMemset(h->omega_sum, 0, sizeof(double) * N));
+    h->omega_cnt = 0;
+  }
+  h->omega_on = on != 0;
+  return 0;
 }
-int bpm_rhat(bpm_handle, const bpm_state*, int64_t, double*, bpm_stream) {
-  return fail("bpm_rhat: not implemented yet");
+
+int bpm_omega(bpm_handle h, double** sum_dev, int64_t* count) {
+  if (!h) return fail("null handle");
+  if (sum_dev) *sum_dev = h->omega_sum;
+  if (count) *count = h->omega_cnt;
+  return 0;
+}
+
+int bpm_outlier_reset(bpm_handle h, bpm_state* st, const double* omega, int32_t* flags_dev,
+                      int32_t* n_reset, double* stats_host, bpm_stream stream) {
+  if (!h || !st || !st->X || !st->lnl) return fail("null argument");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int N = h->cfg.n_chains;
+  const bool sharded = h->cfg.chain_lo != 0 || h->cfg.chain_hi != N;
+  if (!h->omega_buf) {
+    CU_TRY(cudaMalloc(&h->omega_buf, sizeof(double) * 2 * (size_t)N));
+    CU_TRY(cudaMalloc(&h->diag_out, sizeof(double) * 3));
+    CU_TRY(cudaMalloc(&h->diag_i, sizeof(int32_t) * 2));
+  }
+  double* om = h->omega_buf;          // Omega of every chain
+  double* sorted = h->omega_buf + N;
+  if (omega) {
+    CU_TRY(cudaMemcpyAsync(om, omega, sizeof(double) * N, cudaMemcpyDeviceToDevice, s));
+  } else {
+    if (sharded) return fail("bpm_outlier_reset: a sharded handle needs the all-gathered omega array");
+    if (!h->omega_sum || h->omega_cnt < 1) return fail("bpm_outlier_reset: no Omega tracked (bpm_omega_track)");
+    bpm::omega_mean_kernel<<<cdiv(N, 256), 256, 0, s>>>(h->omega_sum, 1.0 / (double)h->omega_cnt, N, om);
+  }
+  size_t need = 0;
+  CU_TRY(cub::DeviceRadixSort::SortKeys(nullptr, need, om, sorted, N, 0, 64, s));
+  if (need > h->sort_tmp_bytes) {
+    CU_TRY(cudaStreamSynchronize(s));
+    cudaFree(h->sort_tmp); h->sort_tmp = nullptr;
+    CU_TRY(cudaMalloc(&h->sort_tmp, need));
+    h->sort_tmp_bytes = need;
+  }
+  CU_TRY(cub::DeviceRadixSort::SortKeys(h->sort_tmp, need, om, sorted, N, 0, 64, s));
+  bpm::iqr_threshold_kernel<<<1, 32, 0, s>>>(sorted, N, h->diag_out);
+  bpm::argmax_kernel<<<1, 1024, 0, s>>>(om, N, h->diag_i);
+  CU_TRY(cudaMemsetAsync(h->diag_i + 1, 0, sizeof(int32_t), s));
+  const int nloc = h->cfg.chain_hi - h->cfg.chain_lo;
+  bpm::outlier_reset_kernel<<<cdiv((int64_t)nloc * 32, 256), 256, 0, s>>>(
+      st->X, st->lnl, omega ? nullptr : h->omega_sum, om, h->diag_out, h->diag_i, h->cfg.chain_lo,
+      h->cfg.chain_hi, h->cfg.dim, h->cfg.ld, flags_dev, h->diag_i + 1);
+  CU_TRY(cudaGetLastError());
+  if (n_reset || stats_host) {
+    CU_TRY(cudaStreamSynchronize(s));
+    if (n_reset) CU_TRY(cudaMemcpy(n_reset, h->diag_i + 1, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (stats_host) {
+      int32_t best = 0;
+      CU_TRY(cudaMemcpy(stats_host, h->diag_out, sizeof(double) * 3, cudaMemcpyDeviceToHost));
+      CU_TRY(cudaMemcpy(&best, h->diag_i, sizeof(int32_t), cudaMemcpyDeviceToHost));
+      stats_host[3] = (double)best;
+    }
+  }
+  return 0;
+}
+
+int bpm_rhat(bpm_handle h, const bpm_state* st, int64_t t0, double* rhat_host, bpm_stream stream) {
+  if (!h || !st || !rhat_host) return fail("null argument");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nloc = h->cfg.chain_hi - h->cfg.chain_lo, d = h->cfg.dim, ld = h->cfg.ld;
+  if (nloc < 2) return fail("bpm_rhat: at least two chains needed");
+  if (!h->rh_out) CU_TRY(cudaMalloc(&h->rh_out, sizeof(double) * d));
+  const double* mean = st->mean;
+  const double* m2 = st->m2;
+  double rows;
+  if (t0 < 0) {   // streaming: the running moments cover mom_len rows
+    if (!mean || !m2) return fail("bpm_rhat: running moments missing");
+    rows = (double)(st->mom_len > 0 ? st->mom_len : st->hist_len);
+  } else {
+    if (!st->history) return fail("bpm_rhat: history missing (pass t0 < 0 for the running moments)");
+    if (t0 >= st->hist_len) return fail("bpm_rhat: t0 beyond the history");
+    if (!h->rh_mean) {
+      CU_TRY(cudaMalloc(&h->rh_mean, sizeof(double) * (size_t)nloc * ld));
+      CU_TRY(cudaMalloc(&h->rh_m2, sizeof(double) * (size_t)nloc * ld));
+    }
+    bpm::history_moments_kernel<<<cdiv((int64_t)nloc * ld, 256), 256, 0, s>>>(
+        st->history, t0, st->hist_len, nloc, d, ld, h->rh_mean, h->rh_m2);
+    mean = h->rh_mean; m2 = h->rh_m2;
+    rows = (double)(st->hist_len - t0);
+  }
+  if (rows < 2.0) return fail("bpm_rhat: at least two rows needed");
+  bpm::rhat_kernel<<<d, 256, 0, s>>>(mean, m2, nloc, ld, rows, h->rh_out);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(s));
+  CU_TRY(cudaMemcpy(rhat_host, h->rh_out, sizeof(double) * d, cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 }  // extern "C"

@@ -261,6 +261,10 @@ class DeMcMpi(object):
         self._fused = kwargs.get("fused", True)
         self._chunk_bytes = int(kwargs.get("history_chunk_bytes", 1 << 30))
         self._reserve_rows = int(kwargs.get("history_reserve", 0))   # generations to pre-allocate
+        # IQR outlier-chain reset every `outlier_gen` generations (0 = off, the reference's
+        # behaviour); DREAM applies it only while k < burnin_gen (Vrugt et al. 2009)
+        self.outlier_gen = int(kwargs.get("outlier_gen", 0))
+        self.n_outlier_resets = 0
         self._setup_device()
         if not self.warm_start:
             self.init_chains(theta_0, varepsilon, **kwargs)
@@ -440,15 +444,79 @@ class DeMcMpi(object):
 
     def rhat(self):
         """Gelman-Rubin R-hat per dimension from the running moments of every chain
-        (rows since construction / the last reset_moments()); needs no stored history."""
+        (rows since construction / the last reset_moments()); needs no stored history.
+        Single rank: bpm_rhat on the device; sharded: the same formula on the all-gathered
+        per-chain moments."""
         torch = _torch()
         T = float(self._mom_len)
         if T < 2:
             raise RuntimeError("rhat() needs at least two rows in the running moments")
+        if self.comm.size == 1:
+            out = np.zeros(self.dim)
+            st = self._state(None)
+            _lib.check(self._libh.bpm_rhat(self._handle, C.byref(st), -1, out.ctypes.data, self._stream()))
+            return out
         mean, m2 = self._gathered_moments()
         W = (m2 / (T - 1.0)).mean(dim=0)
         B_over_T = mean.var(dim=0, unbiased=True)
         return torch.sqrt(((T - 1.0) / T * W + B_over_T) / W).cpu().numpy()
+
+    def rhat_history(self, t0=None):
+        """Gelman-Rubin R-hat per dimension over stored history rows [t0, T) of this rank's
+        chains (default: the second half of every chain, Vrugt et al. 2009)."""
+        if self._hist.policy != "full" or self._hist.stored != self._hist.length:
+            raise RuntimeError("rhat_history() needs the full stored history; use rhat()")
+        if t0 is None:
+            t0 = self._hist.length // 2
+        out = np.zeros(self.dim)
+        st = self._state(self._hist.tensor().data_ptr())
+        _lib.check(self._libh.bpm_rhat(self._handle, C.byref(st), int(t0), out.ctypes.data, self._stream()))
+        return out
+
+    def outlier_reset(self):
+        """IQR outlier-chain reset on Omega = mean log-density since the last check
+        (bpm_outlier_reset).  Returns the number of chains of this rank that were reset."""
+        torch = _torch()
+        cnt = C.c_int64()
+        p = C.c_void_p()
+        _lib.check(self._libh.bpm_omega(self._handle, C.byref(p), C.byref(cnt)))
+        if not p.value or cnt.value < 1:
+            raise RuntimeError("outlier_reset(): no generations tracked yet")
+        n_reset = C.c_int32()
+        stats = (C.c_double * 4)()
+        st = self._state(None)
+        if self.comm.size == 1:
+            _lib.check(self._libh.bpm_outlier_reset(self._handle, C.byref(st), None, None,
+                                                    C.byref(n_reset), stats, self._stream()))
+        else:
+            import torch.distributed as dist
+            lo, hi = int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
+            om = self._wrap_device(p.value, (self.n_chains,)) / float(cnt.value)
+            self._allgather_rows(om, lo, hi)
+            self._allgather_rows(self._lnl, lo, hi)
+            _lib.check(self._libh.bpm_outlier_reset(self._handle, C.byref(st), om.data_ptr(), None,
+                                                    C.byref(n_reset), stats, self._stream()))
+            self._allgather_population()
+        self.last_outlier_stats = dict(threshold=stats[0], q1=stats[1], q3=stats[2], best=int(stats[3]))
+        self.n_outlier_resets += int(n_reset.value)
+        _lib.check(self._libh.bpm_omega_track(self._handle, 1))      # next window starts here
+        return int(n_reset.value)
+
+    def _allgather_rows(self, t, lo, hi):
+        """In-place all-gather of a per-chain array whose rows [lo, hi) are local; shards may
+        differ by one chain (np.array_split), so gather shard by shard."""
+        import torch.distributed as dist
+        bounds = np.array_split(np.array(range(self.n_chains)), self.comm.size)
+        if len(set(len(b) for b in bounds)) == 1:
+            src = t[lo:hi].reshape(-1)
+            # NCCL gathers in place (the shard already sits at its slot); gloo needs a copy
+            dist.all_gather_into_tensor(t.view(-1), src if t.is_cuda else src.clone())
+            return
+        for r, b in enumerate(bounds):
+            dist.broadcast(t[int(b[0]):int(b[-1]) + 1], src=r)
+
+    def _outlier_active(self, k_gen):
+        return self.outlier_gen > 0
 
     def moment_estimates(self):
         """Posterior mean and standard deviation pooled over every chain and every row the
@@ -526,12 +594,16 @@ class DeMcMpi(object):
             G = min(G, len(replay))
         k_gen = 0
         k_off = int(kwargs.get("_k_gen0", 0))     # testing hook: start the schedule at k_off
+        track_outliers = self.outlier_gen > 0 and replay is None
+        _lib.check(self._libh.bpm_omega_track(self._handle, 1 if track_outliers else 0))
         mode = self._mode()
         while k_gen < G:
             base, avail = self._hist.reserve(G - k_gen)
             avail = min(avail, G - k_gen)
             if self.checkpoint > 0:
                 avail = min(avail, self.checkpoint - (k_gen % self.checkpoint))
+            if track_outliers:
+                avail = min(avail, self.outlier_gen - (k_gen % self.outlier_gen))
             st = self._state(base)
             if replay is not None:
                 self._replay_generation(st, replay[k_gen], k_gen + k_off, trace)
@@ -546,6 +618,8 @@ class DeMcMpi(object):
             self._hist.advance(done)
             self._mom_len += done
             k_gen += done
+            if track_outliers and k_gen % self.outlier_gen == 0 and self._outlier_active(k_gen + k_off):
+                self.outlier_reset()
             if self.checkpoint > 0 and k_gen % self.checkpoint == 0:        # demc.py:138-140
                 self.save_state(self.h5_file)
         torch.cuda.synchronize(self._device)
@@ -614,9 +688,9 @@ class DeMcMpi(object):
         return self._wrap_device(ptr, (n, self._ld))
 
     def _allgather_population(self):
-        import torch.distributed as dist
+        """comm.Allgather(current_chain_state) of demc.py:93,116 on the device replica."""
         lo, hi = int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
-        dist.all_gather_into_tensor(self._X.view(-1), self._X[lo:hi].reshape(-1))
+        self._allgather_rows(self._X, lo, hi)
 
     def _allreduce_cr(self):
         torch = _torch()

@@ -92,6 +92,9 @@ class DreamMpi(DeMcMpi):
     def p_cr_update(self):
         return self.p_cr
 
+    def _outlier_active(self, k_gen):
+        return self.outlier_gen > 0 and k_gen < self.burnin_gen
+
     @property
     def in_burnin(self):
         return True                                             # dream.py:142-144

@@ -196,11 +196,28 @@ int bpm_generations_host(bpm_handle h, double* X_host, double* lnl_host, int64_t
 /* Rebuild running moments from a stored history (load_state / warm start). */
 int bpm_moments_from_history(bpm_handle h, bpm_state* st, bpm_stream stream);
 
-/* Additions the north star asks for (not in the reference; Vrugt et al. 2009):
- * IQR outlier-chain reset on the mean log-density of the last half of each chain,
- * and Gelman-Rubin R-hat over history rows [t0, hist_len). */
-int bpm_outlier_reset(bpm_handle h, bpm_state* st, const double* omega, int32_t* n_reset,
-                      bpm_stream stream);
+/* Additions the north star asks for (not in the reference; Vrugt et al. 2009, the paper
+ * cited at readme.md:41-43).
+ *
+ * IQR outlier-chain reset.  Omega_c = mean log-density of chain c over a trailing window.
+ * bpm_omega_track(h, 1) zeroes and starts a per-chain running sum of the cached ln_like,
+ * advanced once per generation by the step entry points; bpm_omega returns the device
+ * array of sums (global chain index; only local rows are maintained) and the number of
+ * generations summed.  bpm_outlier_reset: chains with Omega_c < Q1 - 2 (Q3 - Q1)
+ * (numpy.percentile's linear rule over ALL n_chains) take the state, cached ln_like and
+ * Omega sum of the best chain (argmax Omega, lowest id on ties).  `omega` = device
+ * [n_chains] means for every chain (a sharded host all-gathers them, and st->lnl / st->X
+ * must then be current for all chains), or NULL to use the tracked sums of an unsharded
+ * handle.  Only local chains are written.  Optional outputs: flags_dev [n_chains] device
+ * (1 = reset, local rows only), *n_reset host count, stats_host[4] = {threshold, Q1, Q3,
+ * best chain}; asking for a host output synchronises the stream. */
+int bpm_omega_track(bpm_handle h, int32_t on);
+int bpm_omega(bpm_handle h, double** sum_dev, int64_t* count);
+int bpm_outlier_reset(bpm_handle h, bpm_state* st, const double* omega, int32_t* flags_dev,
+                      int32_t* n_reset, double* stats_host, bpm_stream stream);
+/* Gelman-Rubin R-hat per dimension over this handle's local chains: from history rows
+ * [t0, hist_len) when t0 >= 0, from the running moments (mean, m2 over mom_len rows) when
+ * t0 < 0.  rhat_host: dim doubles.  Synchronises the stream. */
 int bpm_rhat(bpm_handle h, const bpm_state* st, int64_t t0, double* rhat_host, bpm_stream stream);
 
 /* Per-kernel timing for the benchmark's roofline line: while on, every launch is

@@ -76,3 +76,20 @@ def test_replay_form_matches_scalar_oracle(name):
                 np.testing.assert_allclose(cr.delta_m, tr["delta_m"], rtol=1e-12)
                 assert np.array_equal(cr.n_cr_updates, tr["n_cr_updates"])
             hist.append(out["state"])
+
+
+def test_diagnostics_oracle_known_answers():
+    """oracle/diagnostics.py against hand-computed values (the reference holds no vectors
+    for the outlier reset / R-hat: parity for them is pinned to the published definitions)."""
+    from oracle import diagnostics as od
+    omega = np.array([-1.0, -2.0, -3.0, -4.0, -100.0])
+    # Q1 = -4, Q3 = -2 -> threshold = -4 - 2*2 = -8
+    mask, thr, best = od.iqr_outliers(omega)
+    assert thr == -8.0 and best == 0 and mask.tolist() == [False, False, False, False, True]
+    X = np.arange(10.0).reshape(5, 2)
+    X2, L2, m = od.outlier_reset(X, omega.copy(), omega)
+    assert X2[4].tolist() == [0.0, 1.0] and L2[4] == -1.0 and np.array_equal(X2[:4], X[:4])
+    # two chains, identical within-chain variance 1, means 0 and 2, T = 3:
+    h = np.array([[[-1.0], [1.0]], [[0.0], [2.0]], [[1.0], [3.0]]])
+    # W = 1, B/T = var([0, 2], ddof=1) = 2 -> R = sqrt((2/3 + 2) / 1)
+    np.testing.assert_allclose(od.rhat(h), [np.sqrt(2.0 / 3.0 + 2.0)], rtol=1e-15)

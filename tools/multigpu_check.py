@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Launched under torchrun with G >= 2 ranks (one per GPU, NCCL): a sharded DREAM / DE-MC run
+must reproduce the single-GPU run of the same seed.  With CR adaptation off the chains are
+bit-identical (every draw is a function of (seed, generation, chain), never of the rank);
+with adaptation on p_cr agrees to rounding of the all-reduced sums.  Rank 0 prints
+MULTIGPU_OK on success."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from bipymc_b200 import DreamMpi, DeMcMpi, targets
+    from bipymc_b200.demc import _SingleComm
+    world = dist.get_world_size()
+    cases = [
+        ("dream-gauss100", DreamMpi, targets.Gauss_100D(), np.zeros(100), 4096 + 2 * world, dict(burnin_gen=0), 1.0),
+        ("dream-gauss100-adapt", DreamMpi, targets.Gauss_100D(), np.zeros(100), 2048, dict(burnin_gen=1000, n_cr_gen=2), 1.0),
+        ("demc-banana", DeMcMpi, targets.Banana_2D(), [0.0, 0.0], 1000 * world, {}, 0.5),
+        ("dream-linefit-outlier", DreamMpi, targets.LineFit(), [-0.8, 4.5, 0.2], 512 * world,
+         dict(burnin_gen=1000, n_cr_gen=3, outlier_gen=5), 1e-2),
+    ]
+    G = 12
+    for name, cls, tgt, th0, N, kw, veps in cases:
+        np.random.seed(3)
+        s = cls(tgt.ln_like, th0, n_chains=N, seed=5, varepsilon=veps, device=local, **kw)
+        assert s.comm.size == world
+        s.run_mcmc(N * (G + 1))
+        full = s.super_chain_mpi(0)
+        acc = (s.n_accepted, s.n_rejected)
+        rh = s.rhat()
+        if rank == 0:
+            np.random.seed(3)
+            one = cls(tgt.ln_like, th0, n_chains=N, seed=5, varepsilon=veps, device=local,
+                      mpi_comm=_SingleComm(), **kw)
+            one.run_mcmc(N * (G + 1))
+            ref = one.super_chain
+            assert full.shape == ref.shape, (full.shape, ref.shape)
+            exact = "adapt" not in name and "outlier" not in name
+            if exact:
+                assert np.array_equal(full, ref), "%s: sharded run differs from the single-GPU run" % name
+                assert acc == (one.n_accepted, one.n_rejected + world - 1), (acc, one.n_accepted, one.n_rejected)
+            else:
+                # all-reduced CR sums round differently from the single-rank block order
+                frac = np.mean(np.all(full == ref, axis=1))
+                assert frac > 0.9, "%s: only %.3f of rows identical" % (name, frac)
+                np.testing.assert_allclose(s.p_cr, one.p_cr, rtol=1e-6)
+            np.testing.assert_allclose(rh, one.rhat(), rtol=1e-6 if not exact else 1e-9)
+            if "outlier" in name:
+                print(name, "resets", s.n_outlier_resets, one.n_outlier_resets)
+            print("case", name, "ok", flush=True)
+        dist.barrier()
+    if rank == 0:
+        print("MULTIGPU_OK", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
