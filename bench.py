@@ -273,7 +273,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--history", default="full", choices=["full", "none"])
-    ap.add_argument("--fused", type=int, default=1, help="1 warp-specialised fused kernel (default), 2 two-halves fused kernel, 0 split path")
+    ap.add_argument("--fused", type=int, default=1, help="1 fused v3 (default), 3 fused 12-producer variant, 2 two-halves fused kernel, 0 split path")
     ap.add_argument("--burnin-gen", type=int, default=2000, help="DREAM burnin_gen (2000 = tests/test_100dgauss.py:109)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")

@@ -194,9 +194,10 @@ struct GaussTables {
   double* gam;   // gamma_base[d'] for d' = 0..d (dream.py:61)
   double* cdf;   // normalised CR cdf (dream.py:51)
   double* crv;   // CR values (dream.py:113)
+  uint32_t* thr; // native mode: mask_i = (philox word <= thr[m])  <=>  u32d(word) <= CR[m]
 };
 __host__ __device__ inline size_t gauss_table_doubles(int d) {
-  return (size_t)d * kWld + ((d + 1) & ~1) + ((d + 2) & ~1) + 2 * BPM_MAX_CR;
+  return (size_t)d * kWld + ((d + 1) & ~1) + ((d + 2) & ~1) + 2 * BPM_MAX_CR + BPM_MAX_CR / 2;
 }
 // one proposal tile: P[64][pld] followed by the consumers' partial sums part[8][64]
 __host__ __device__ inline size_t gauss_ptile_doubles(int d) {
@@ -211,6 +212,7 @@ __device__ __forceinline__ GaussTables carve_tables(double* smem, int d) {
   t.gam = t.mus + ((d + 1) & ~1);
   t.cdf = t.gam + ((d + 2) & ~1);
   t.crv = t.cdf + BPM_MAX_CR;
+  t.thr = reinterpret_cast<uint32_t*>(t.crv + BPM_MAX_CR);
   return t;
 }
 
@@ -229,6 +231,9 @@ __device__ __forceinline__ void fill_tables(const PhaseArgs& a, const GaussArgs&
       acc = __dadd_rn(acc, a.p_cr[m]);
       t.cdf[m] = __ddiv_rn(acc, tot);
       t.crv[m] = __ddiv_rn((double)(m + 1), (double)a.n_cr);
+      // u32d(w) = (w + 0.5) 2^-32 <= cr  <=>  w <= floor(cr 2^32 - 0.5)   (all steps exact)
+      const double lim = floor(t.crv[m] * 4294967296.0 - 0.5);
+      t.thr[m] = lim >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)lim;
     }
   }
 }
@@ -678,6 +683,277 @@ fused_gauss_ws_kernel(const PhaseArgs a, const GaussArgs g) {
   }
 }
 
+
+// =====================================================================================
+// Variant 3 (default): the same producer / consumer pipeline re-balanced after profiling
+// variant 2 (profiles/r1_v2_*): its 8 consumer warps sat at the FULL barrier 76 % of the
+// time while each of the 12 producer warps walked its chains serially at ~0.2 IPC.  Here
+//   * 4 consumer warps (128 registers) each own TWO 14-column strips of the tile product;
+//   * 16 producer warps (88 registers) own exactly 4 chains of every 64-chain tile;
+//   * the producer stages are specialised at compile time (DREAM with 3 pairs, or the
+//     runtime-general form), need d % 4 == 0 so every row access is a 16-byte vector, test
+//     the crossover mask on the raw Philox words against an integer threshold, and take
+//     the jump statistic's 1/variance from a Newton reciprocal instead of an IEEE division.
+// Draw values, proposal arithmetic and the order of every floating-point sum are those of
+// the other variants, so the chains are bit-identical to them.
+constexpr int kV3ConsWarps = 4, kV3ProdWarps = 16;
+constexpr int kV3Threads = 32 * (kV3ConsWarps + kV3ProdWarps);   // 640
+constexpr int kV3ProdThreads = 32 * kV3ProdWarps;
+constexpr int kV3ConsThreads = 32 * kV3ConsWarps;
+
+__device__ __forceinline__ double2 ldg2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+// NPAIR: 3 = DREAM with del_pairs == 3 (the reference default), 0 = read algo / del_pairs at run time
+template <bool REPLAY, int NPAIR>
+__device__ __forceinline__ void tile_stage_propose_v3(const PhaseArgs& a, const GaussTables& tb,
+                                                      TileScratch& T, double* __restrict__ P, int pld,
+                                                      int gwarp, int gwarps, int lane) {
+  const int d = a.d;
+  const bool dream = NPAIR == 3 ? true : a.algo == BPM_ALGO_DREAM;
+  const int npair = NPAIR == 3 ? 3 : (dream ? a.del_pairs : 1);
+  const bool act = 4 * lane < d;                      // d % 4 == 0: a lane owns 4 dims or none
+  const bool adapt = dream && a.adapt;
+  const bool welford_var = adapt && !(REPLAY && a.hist_base != nullptr);
+  for (int row = gwarp; row < kTileRows; row += gwarps) {
+    const int c = T.cid[row];
+    double* prow = P + row * pld + 4 * lane;
+    if (c < 0) {
+      if (act) prow[0] = prow[1] = prow[2] = prow[3] = 0.0;
+      continue;
+    }
+    double cur[4] = {0, 0, 0, 0}, S[4] = {0, 0, 0, 0}, var[4] = {0, 0, 0, 0};
+    if (act) {
+      // every row gather of this chain is issued before anything consumes one
+      const double* xc = a.X + (size_t)c * a.ld + 4 * lane;
+      const double2 u0 = ldg2(xc), u1 = ldg2(xc + 2);
+      if (welford_var) {
+        const double* mp = a.m2 + (size_t)(c - a.chain_lo) * a.ld + 4 * lane;
+        const double2 w0 = ld_stream2(mp), w1 = ld_stream2(mp + 2);
+        var[0] = w0.x; var[1] = w0.y; var[2] = w1.x; var[3] = w1.y;
+      }
+      cur[0] = u0.x; cur[1] = u0.y; cur[2] = u1.x; cur[3] = u1.y;
+      if constexpr (NPAIR == 3) {
+        double2 va[3][2], vb[3][2];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          const double* pa = a.X + (size_t)T.pa[row][p] * a.ld + 4 * lane;
+          const double* pb = a.X + (size_t)T.pb[row][p] * a.ld + 4 * lane;
+          va[p][0] = ldg2(pa); va[p][1] = ldg2(pa + 2);
+          vb[p][0] = ldg2(pb); vb[p][1] = ldg2(pb + 2);
+        }
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          const double df0 = __dsub_rn(va[p][0].x, vb[p][0].x), df1 = __dsub_rn(va[p][0].y, vb[p][0].y);
+          const double df2 = __dsub_rn(va[p][1].x, vb[p][1].x), df3 = __dsub_rn(va[p][1].y, vb[p][1].y);
+          S[0] = p == 0 ? df0 : __dadd_rn(S[0], df0);
+          S[1] = p == 0 ? df1 : __dadd_rn(S[1], df1);
+          S[2] = p == 0 ? df2 : __dadd_rn(S[2], df2);
+          S[3] = p == 0 ? df3 : __dadd_rn(S[3], df3);
+        }
+      } else {
+        for (int p = 0; p < npair; ++p) {
+          const double* pa = a.X + (size_t)T.pa[row][p] * a.ld + 4 * lane;
+          const double* pb = a.X + (size_t)T.pb[row][p] * a.ld + 4 * lane;
+          const double2 s0 = ldg2(pa), s1 = ldg2(pa + 2), t0 = ldg2(pb), t1 = ldg2(pb + 2);
+          const double df0 = __dsub_rn(s0.x, t0.x), df1 = __dsub_rn(s0.y, t0.y);
+          const double df2 = __dsub_rn(s1.x, t1.x), df3 = __dsub_rn(s1.y, t1.y);
+          S[0] = p == 0 ? df0 : __dadd_rn(S[0], df0);
+          S[1] = p == 0 ? df1 : __dadd_rn(S[1], df1);
+          S[2] = p == 0 ? df2 : __dadd_rn(S[2], df2);
+          S[3] = p == 0 ? df3 : __dadd_rn(S[3], df3);
+        }
+      }
+    }
+    uint32_t mbits = 0xFu;
+    double gamma;
+    const double gu = T.gamma_u[row];
+    if (dream) {
+      mbits = 0u;
+      const int m = T.cr_idx[row];
+      if (act) {
+        if (REPLAY) {
+          const double cr = tb.crv[m];
+          double z[4];
+          z4<REPLAY>(a, c, lane, z);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (z[q] <= cr) mbits |= 1u << q;
+        } else {
+          const uint32_t th = tb.thr[m];
+          const Philox4 q = draw4(a.rng, (uint32_t)c, RNG_Z, (uint32_t)lane);
+          mbits = (q.x <= th ? 1u : 0u) | (q.y <= th ? 2u : 0u) | (q.z <= th ? 4u : 0u) | (q.w <= th ? 8u : 0u);
+        }
+      }
+      int d_prime = __reduce_add_sync(0xFFFFFFFFu, __popc(mbits));
+      if (d_prime == 0) {
+        const int fb = T.fallback[row] < 0 ? 0 : T.fallback[row];
+        if ((fb >> 2) == lane) mbits |= 1u << (fb & 3);
+        d_prime = 1;
+      }
+      gamma = tb.gam[d_prime];
+      if (a.gamma_jump) gamma = gu < a.gamma_p0 ? gamma : 1.0;
+    } else {
+      gamma = demc_gamma(a, gu);
+    }
+    double delta = 0.0;
+    if (act) {
+      double e[4], nn[4];
+      en4<REPLAY>(a, c, lane, e, nn);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        double pr;
+        if (dream) {
+          pr = dream_prop(cur[q], S[q], e[q], nn[q], gamma, (mbits >> q) & 1u ? 1.0 : 0.0);
+          if (adapt) {
+            double v;
+            if (welford_var) {
+              v = __dmul_rn(var[q], a.inv_mom);
+              if (!(v > 0.0)) v = 1e-12 * 1e-12;
+            } else {
+              v = cr_variance<REPLAY>(a, c, 4 * lane + q);
+            }
+            delta += cr_term(cur[q], pr, v);
+          }
+        } else {
+          pr = demc_prop(cur[q], S[q], nn[q], gamma);
+        }
+        prow[q] = pr;
+      }
+    }
+    if (dream) {
+      delta = group_sum_d<32>(delta);
+      if (lane == 0) {
+        a.cr_pick[c] = adapt ? T.cr_idx[row] : -1;
+        a.cr_delta[c] = delta;
+      }
+    }
+  }
+}
+
+// write-back for d % 4 == 0: all global loads of a chain row are issued before the Welford math
+__device__ __forceinline__ void tile_stage_writeback_v3(const PhaseArgs& a, const TileScratch& T,
+                                                        const double* __restrict__ P, int pld, int gwarp,
+                                                        int gwarps, int lane) {
+  if (4 * lane >= a.d) return;
+  const bool keep = a.mean != nullptr || a.hist_row != nullptr;
+  for (int row = gwarp; row < kTileRows; row += gwarps) {
+    const int c = T.cid[row];
+    if (c < 0) continue;
+    const int acc = T.acc[row];
+    if (!acc && !keep) continue;
+    double* xc = a.X + (size_t)c * a.ld + 4 * lane;
+    const size_t o = (size_t)(c - a.chain_lo) * a.ld + 4 * lane;
+    double2 m0, m1, v0, v1;
+    if (a.mean) {
+      m0 = ld_stream2(a.mean + o); m1 = ld_stream2(a.mean + o + 2);
+      v0 = ld_stream2(a.m2 + o); v1 = ld_stream2(a.m2 + o + 2);
+    }
+    double s[4];
+    if (acc) {
+      const double* prow = P + row * pld + 4 * lane;
+      s[0] = prow[0]; s[1] = prow[1]; s[2] = prow[2]; s[3] = prow[3];
+      *reinterpret_cast<double2*>(xc) = make_double2(s[0], s[1]);
+      *reinterpret_cast<double2*>(xc + 2) = make_double2(s[2], s[3]);
+    } else {
+      const double2 u0 = ldg2(xc), u1 = ldg2(xc + 2);
+      s[0] = u0.x; s[1] = u0.y; s[2] = u1.x; s[3] = u1.y;
+    }
+    if (a.mean) {
+      welford_update(s[0], a.inv_n1, m0.x, v0.x);
+      welford_update(s[1], a.inv_n1, m0.y, v0.y);
+      welford_update(s[2], a.inv_n1, m1.x, v1.x);
+      welford_update(s[3], a.inv_n1, m1.y, v1.y);
+      st_stream2(a.mean + o, m0.x, m0.y);
+      st_stream2(a.mean + o + 2, m1.x, m1.y);
+      st_stream2(a.m2 + o, v0.x, v0.y);
+      st_stream2(a.m2 + o + 2, v1.x, v1.y);
+    }
+    if (a.hist_row) {
+      st_stream2(a.hist_row + o, s[0], s[1]);
+      st_stream2(a.hist_row + o + 2, s[2], s[3]);
+    }
+  }
+}
+
+template <bool REPLAY, bool CENTER, int NPAIR>
+__global__ void __launch_bounds__(kV3Threads, 1)
+fused_gauss_v3_kernel(const PhaseArgs a, const GaussArgs g) {
+  extern __shared__ __align__(16) double smem[];
+  const int d = a.d, pld = d | 1;
+  const GaussTables tb = carve_tables(smem, d);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* Pbuf = smem + gauss_table_doubles(d);
+  const size_t p_stride = gauss_ptile_doubles(d);
+  const size_t part_off = ((size_t)kTileRows * pld + 1) & ~(size_t)1;
+  double* Tbuf = Pbuf + 2 * p_stride;
+  const size_t t_stride = gauss_scratch_doubles();
+  fill_tables(a, g, tb, threadIdx.x, kV3Threads);
+  __syncthreads();
+  const PhaseLists L = phase_lists(a);
+  const int n_tiles = (L.n_self + kTileRows - 1) / kTileRows;
+  const int n_my = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+
+  if (warp < kV3ConsWarps) {
+    // ------------------------------ consumers ------------------------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+    unsigned n_acc = 0, n_rej = 0;
+    for (int i = 0; i < n_my; ++i) {
+      const int b = i & 1;
+      double* P = Pbuf + b * p_stride;
+      double* part = P + part_off;
+      TileScratch& T = *reinterpret_cast<TileScratch*>(Tbuf + (i % 3) * t_stride);
+      nbar_sync(BAR_FULL0 + b, kV3Threads);            // producers filled buffer b
+      gauss_tile_rowsums<CENTER>(P, pld, tb.Ws, tb.mus, d, part, 2 * warp, lane);
+      gauss_tile_rowsums<CENTER>(P, pld, tb.Ws, tb.mus, d, part, 2 * warp + 1, lane);
+      nbar_sync(BAR_CONS, kV3ConsThreads);
+      if (threadIdx.x < kTileRows) tile_stage_decide(a, g, T, part, threadIdx.x, n_acc, n_rej);
+      nbar_arrive(BAR_DONE0 + b, kV3Threads);          // decisions of tile i are in T.acc
+    }
+    if (lane == 0) {
+      if (n_acc) atomicAdd(a.n_acc, (unsigned long long)n_acc);
+      if (n_rej) atomicAdd(a.n_rej, (unsigned long long)n_rej);
+    }
+  } else {
+    // ------------------------------ producers ------------------------------------------
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    const int pw = warp - kV3ConsWarps;
+    const int ptid = threadIdx.x - kV3ConsThreads;
+    if (n_my > 0)
+      tile_stage_draws<REPLAY>(a, L, tb, *reinterpret_cast<TileScratch*>(Tbuf), blockIdx.x, ptid,
+                               kV3ProdThreads);
+    nbar_sync(BAR_PROD, kV3ProdThreads);
+    for (int i = 0; i <= n_my; ++i) {
+      if (i + 1 < n_my)
+        tile_stage_draws<REPLAY>(a, L, tb, *reinterpret_cast<TileScratch*>(Tbuf + ((i + 1) % 3) * t_stride),
+                                 blockIdx.x + (i + 1) * gridDim.x, ptid, kV3ProdThreads);
+      if (i < n_my) {
+        const int b = i & 1;
+        double* P = Pbuf + b * p_stride;
+        TileScratch& T = *reinterpret_cast<TileScratch*>(Tbuf + (i % 3) * t_stride);
+        tile_stage_propose_v3<REPLAY, NPAIR>(a, tb, T, P, pld, pw, kV3ProdWarps, lane);
+        nbar_arrive(BAR_FULL0 + b, kV3Threads);
+      }
+      if (i >= 1) {
+        const int b2 = (i - 1) & 1;
+        const double* P = Pbuf + b2 * p_stride;
+        const TileScratch& T = *reinterpret_cast<const TileScratch*>(Tbuf + ((i - 1) % 3) * t_stride);
+        nbar_sync(BAR_DONE0 + b2, kV3Threads);          // consumers decided tile i-1
+        tile_stage_writeback_v3(a, T, P, pld, pw, kV3ProdWarps, lane);
+      }
+      nbar_sync(BAR_PROD, kV3ProdThreads);
+    }
+  }
+}
+
+template <bool REPLAY, bool CENTER, int NPAIR>
+inline int launch_fused_v3(const PhaseArgs& a, const GaussArgs& g, int grid, size_t sm, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(fused_gauss_v3_kernel<REPLAY, CENTER, NPAIR>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return 1;
+  fused_gauss_v3_kernel<REPLAY, CENTER, NPAIR><<<grid, kV3Threads, sm, s>>>(a, g);
+  return 0;
+}
+
 // ---- d <= 4 analytic targets: one thread per chain ------------------------------------
 template <bool REPLAY, int TARGET>
 __global__ void __launch_bounds__(128) fused_small_kernel(const PhaseArgs a, const TargetView tv) {
@@ -811,7 +1087,7 @@ inline int try_fused_phase(const TargetView& tv, const PhaseArgs& a, cudaStream_
         if (e != cudaSuccess) return 1;
         fused_gauss_kernel<REPLAY, true><<<grid, 2 * kHalfThreads, sm, s>>>(a, g);
       }
-    } else {
+    } else if (variant == 3 || (a.d % 4) != 0 || a.ld != a.d) {
       const int grid = n_tiles > 148 ? 148 : (n_tiles < 1 ? 1 : n_tiles);
       if (tv.mu_is_zero) {
         e = cudaFuncSetAttribute(fused_gauss_ws_kernel<REPLAY, false>,
@@ -824,6 +1100,17 @@ inline int try_fused_phase(const TargetView& tv, const PhaseArgs& a, cudaStream_
         if (e != cudaSuccess) return 1;
         fused_gauss_ws_kernel<REPLAY, true><<<grid, kWsThreads, sm, s>>>(a, g);
       }
+    } else {
+      const int grid = n_tiles > 148 ? 148 : (n_tiles < 1 ? 1 : n_tiles);
+      const bool d3 = a.algo == BPM_ALGO_DREAM && a.del_pairs == 3;
+      int rc;
+      if (tv.mu_is_zero)
+        rc = d3 ? launch_fused_v3<REPLAY, false, 3>(a, g, grid, sm, s)
+                : launch_fused_v3<REPLAY, false, 0>(a, g, grid, sm, s);
+      else
+        rc = d3 ? launch_fused_v3<REPLAY, true, 3>(a, g, grid, sm, s)
+                : launch_fused_v3<REPLAY, true, 0>(a, g, grid, sm, s);
+      if (rc) return 1;
     }
     if (cudaGetLastError() != cudaSuccess) return 1;
     *done = 1;

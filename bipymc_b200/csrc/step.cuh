@@ -207,11 +207,13 @@ __device__ __forceinline__ void en4(const PhaseArgs& a, int c, int b, double e[4
       const Philox4 q = draw4(a.rng, (uint32_t)c, RNG_EN, (uint32_t)b);
       if (a.u_eps > 0.0) {
         const double lo = -a.u_eps, w = __dsub_rn(a.u_eps, lo);  // numpy: low + (high-low)*u
-        const double k = 1.0 / 65536.0;
-        e[0] = __dadd_rn(lo, __dmul_rn(w, ((double)(q.x & 0xFFFFu) + 0.5) * k));
-        e[1] = __dadd_rn(lo, __dmul_rn(w, ((double)(q.x >> 16) + 0.5) * k));
-        e[2] = __dadd_rn(lo, __dmul_rn(w, ((double)(q.y & 0xFFFFu) + 0.5) * k));
-        e[3] = __dadd_rn(lo, __dmul_rn(w, ((double)(q.y >> 16) + 0.5) * k));
+        // u = (h + 0.5) / 65536 for a 16-bit h; (2h + 1) * (w * 2^-17) is the same product
+        // (power-of-two scaling commutes with rounding) in one conversion + one multiply
+        const double w17 = w * (1.0 / 131072.0);
+        e[0] = __dadd_rn(lo, __dmul_rn(w17, (double)(int)(2u * (q.x & 0xFFFFu) + 1u)));
+        e[1] = __dadd_rn(lo, __dmul_rn(w17, (double)(int)(2u * (q.x >> 16) + 1u)));
+        e[2] = __dadd_rn(lo, __dmul_rn(w17, (double)(int)(2u * (q.y & 0xFFFFu) + 1u)));
+        e[3] = __dadd_rn(lo, __dmul_rn(w17, (double)(int)(2u * (q.y >> 16) + 1u)));
       }
       if (a.eps > 0.0) {
         float f0, f1, f2, f3;
@@ -289,10 +291,27 @@ __device__ __forceinline__ double cr_variance(const PhaseArgs& a, int c, int i) 
   return var;
 }
 
+// Reciprocal to ~1 ulp without the IEEE division's slow path: hardware seed + two Newton
+// steps.  Only the CR jump statistic uses it (a sum over thousands of chains that is
+// compared with the reference to 1e-10), never the chain arithmetic itself.
+__device__ __forceinline__ double fast_rcp(double v) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v));
+  double e = fma(-v, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-v, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
 // dream.py:130 contribution of one dimension: (cur - prop)^2 / std^2.
 __device__ __forceinline__ double cr_term(double cur, double prop, double var) {
   const double df = __dsub_rn(cur, prop);
-  return __ddiv_rn(__dmul_rn(df, df), var);
+  if (df == 0.0) return 0.0;               // dimensions outside the crossover subspace
+  const double sq = __dmul_rn(df, df);
+  const double r = fast_rcp(var);
+  if (!(r > 0.0) || !(r < 1.7e308)) return __ddiv_rn(sq, var);   // var = inf / denormal / NaN
+  return __dmul_rn(sq, r);
 }
 
 // Explicitly rounded Welford update (identical bits in every kernel that uses it).

@@ -41,6 +41,18 @@ def _torch():
     return torch
 
 
+def shard_bounds(n_chains, size):
+    """[lo, hi) of every rank's block = np.array_split(range(N), size) (demc.py:39): the first
+    N % size ranks own one extra chain."""
+    q, r = divmod(int(n_chains), int(size))
+    out, lo = [], 0
+    for k in range(size):
+        hi = lo + q + (1 if k < r else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
 class _SingleComm(object):
     """Stand-in for MPI.COMM_WORLD when neither mpi4py nor torch.distributed is in use."""
     size, rank = 1, 0
@@ -298,7 +310,7 @@ class DeMcMpi(object):
     def _create_handle(self):
         d = self.dim
         self._ld = d if d <= 4 else ((d + 3) // 4) * 4
-        ids = np.array_split(np.array(range(self.n_chains)), self.comm.size)[self.comm.rank]
+        ids = np.array_split(np.arange(self.n_chains), self.comm.size)[self.comm.rank]
         self.rank_chain_ids = ids                                   # demc.py:39-40
         if self._seed is None:
             # keep np.random.seed(...) meaningful for the native stream as well
@@ -506,14 +518,13 @@ class DeMcMpi(object):
         """In-place all-gather of a per-chain array whose rows [lo, hi) are local; shards may
         differ by one chain (np.array_split), so gather shard by shard."""
         import torch.distributed as dist
-        bounds = np.array_split(np.array(range(self.n_chains)), self.comm.size)
-        if len(set(len(b) for b in bounds)) == 1:
+        if self.n_chains % self.comm.size == 0:
             src = t[lo:hi].reshape(-1)
             # NCCL gathers in place (the shard already sits at its slot); gloo needs a copy
             dist.all_gather_into_tensor(t.view(-1), src if t.is_cuda else src.clone())
             return
-        for r, b in enumerate(bounds):
-            dist.broadcast(t[int(b[0]):int(b[-1]) + 1], src=r)
+        for r, (b0, b1) in enumerate(shard_bounds(self.n_chains, self.comm.size)):
+            dist.broadcast(t[b0:b1], src=r)
 
     def _outlier_active(self, k_gen):
         return self.outlier_gen > 0
@@ -845,8 +856,8 @@ class DeMcMpi(object):
 
     def get_chain_rank(self, c_id):
         assert 0 <= c_id < self.n_chains
-        for r, ids in enumerate(np.array_split(np.array(range(self.n_chains)), self.comm.size)):
-            if c_id in ids:
+        for r, (b0, b1) in enumerate(shard_bounds(self.n_chains, self.comm.size)):
+            if b0 <= c_id < b1:
                 return r
         raise RuntimeError("ERROR: c_id not in global chain ids")
 

@@ -227,13 +227,15 @@ def test_full_size_properties_1e5_chains_100d():
     tgt = targets.Gauss_100D()
     N, d, G = 100000, 100, 6
     runs = []
-    for fused in (1, 0, 2):
+    for fused in (1, 0, 2, 3):
         np.random.seed(0)
         s = DreamMpi(tgt.ln_like, np.zeros(d), n_chains=N, seed=77, burnin_gen=1000, n_cr_gen=2,
                      fused=fused, varepsilon=1.0)
         s.run_mcmc(N * (G + 1))
         runs.append(s)
-    a, b, c2 = runs
+    a, b, c2, c3 = runs
+    assert torch.equal(a._hist.tensor(), c3._hist.tensor()), "v3 and the 12-producer variant must agree"
+    del c3
     ha, hb = a._hist.tensor(), b._hist.tensor()
     assert ha.shape == (G + 1, N, d)
     assert torch.equal(ha, hb), "fused and split paths must agree bit for bit"

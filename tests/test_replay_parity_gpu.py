@@ -109,7 +109,7 @@ def check_against_reference(name, s, sink, traces, osampler):
     assert np.array_equal(c.current_pos, hist[-1, 1, :]) and c.chain_len == ref.shape[0]
 
 
-@pytest.mark.parametrize("fused", [1, 0, 2], ids=["fused", "split", "fused-halves"])
+@pytest.mark.parametrize("fused", [1, 0, 2, 3], ids=["fused", "split", "fused-halves", "fused-ws12"])
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_replay_device_target(name, fused):
     osampler, traces = oracle_traces(name)
