@@ -684,18 +684,134 @@ fused_gauss_ws_kernel(const PhaseArgs a, const GaussArgs g) {
 }
 
 
+// ---- FP64 tensor-core (DMMA) tile product for variant 3 -------------------------------
+// B200 measures the same FP64 peak through mma.sync.m8n8k4.f64 as through DFMA
+// (profiles/r1_fp64_probe_b200.txt), but one DMMA replaces eight DFMA warp instructions
+// and its operand fragments are 1 double per lane, so the consumer needs ~10x less
+// shared-memory return bandwidth than the register-tiled DFMA form (which profiling
+// showed to be LSU-bound: 256 LSU cycles against 112 FP64 cycles per k step).
+//   A fragment (8 x 4, row): lane l holds A[l / 4][l % 4]       <- proposal tile P
+//   B fragment (4 x 8, col): lane l holds B[l % 4][l / 4]       <- W, stored in fragment order
+//   C fragment (8 x 8):      lane l holds C[l / 4][2 (l % 4) + {0, 1}]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__host__ __device__ inline int dmma_pld(int d) {          // row stride = 4 or 12 (mod 16) doubles:
+  int p = d;                                              // conflict-free A-fragment loads
+  while ((p & 15) != 4 && (p & 15) != 12) ++p;
+  return p;
+}
+__host__ __device__ inline int dmma_ntiles(int r) { return (r + 7) >> 3; }
+// Wf[(k4 * NT + nt) * 32 + lane] = W[4 k4 + lane % 4][8 nt + lane / 4]  (0 outside d x r)
+__device__ __forceinline__ void load_W_fragments(double* Wf, double* mus, const double* __restrict__ W,
+                                                 const double* __restrict__ mu, int d, int r, int tid,
+                                                 int nthreads) {
+  const int NT = dmma_ntiles(r);
+  const int total = (d >> 2) * NT * 32;
+  for (int idx = tid; idx < total; idx += nthreads) {
+    const int lane = idx & 31, t = idx >> 5;
+    const int k4 = t / NT, nt = t - k4 * NT;
+    const int k = 4 * k4 + (lane & 3), j = 8 * nt + (lane >> 2);
+    Wf[idx] = j < r ? W[(size_t)k * r + j] : 0.0;
+  }
+  for (int k = tid; k < d; k += nthreads) mus[k] = mu[k];
+}
+
+// maha[row] = |(P[row] - mu) . W|^2 for the 16 rows [16 cw, 16 cw + 16) of a 64-row tile.
+// Column tiles are processed in two groups of <= 7 so that 28 accumulators stay in registers.
+template <bool CENTER>
+__device__ __forceinline__ void gauss_tile_maha_dmma(const double* __restrict__ P, int pld,
+                                                     const double* __restrict__ Wf,
+                                                     const double* __restrict__ mus, int d, int NT,
+                                                     double* __restrict__ maha, int cw, int lane) {
+  const int r0 = 16 * cw + (lane >> 2), kq = lane & 3;
+  const double* pa0 = P + r0 * pld + kq;
+  const double* pa1 = pa0 + 8 * pld;
+  const int nk4 = d >> 2;
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll 1
+  for (int g = 0; g < 2; ++g) {
+    const int nt0 = 7 * g;
+    const int cnt = NT - nt0 < 7 ? NT - nt0 : 7;
+    if (cnt <= 0) break;
+    double acc0[7][2], acc1[7][2];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) acc0[j][0] = acc0[j][1] = acc1[j][0] = acc1[j][1] = 0.0;
+    const double* wf = Wf + nt0 * 32 + lane;
+#pragma unroll 2
+    for (int k4 = 0; k4 < nk4; ++k4) {
+      double a0 = pa0[4 * k4], a1 = pa1[4 * k4];
+      if (CENTER) {
+        const double m = mus[4 * k4 + kq];
+        a0 = __dsub_rn(a0, m);
+        a1 = __dsub_rn(a1, m);
+      }
+      const double* wk = wf + (size_t)k4 * NT * 32;
+#pragma unroll
+      for (int j = 0; j < 7; ++j)
+        if (j < cnt) {
+          const double b = wk[j * 32];
+          dmma884(acc0[j][0], acc0[j][1], a0, b);
+          dmma884(acc1[j][0], acc1[j][1], a1, b);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+      if (j < cnt) {
+        s0 = fma(acc0[j][0], acc0[j][0], s0);
+        s0 = fma(acc0[j][1], acc0[j][1], s0);
+        s1 = fma(acc1[j][0], acc1[j][0], s1);
+        s1 = fma(acc1[j][1], acc1[j][1], s1);
+      }
+  }
+  // the four lanes of a quad hold disjoint column sets of the same two rows
+  s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, 1);
+  s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, 1);
+  s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, 2);
+  s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, 2);
+  if (kq == 0) {
+    maha[r0] = s0;
+    maha[r0 + 8] = s1;
+  }
+}
+
+// Metropolis decision from a finished Mahalanobis distance (one thread per chain row; whole warps)
+__device__ __forceinline__ void tile_stage_decide_maha(const PhaseArgs& a, const GaussArgs& g, TileScratch& T,
+                                                       const double* __restrict__ maha, int row,
+                                                       unsigned& n_acc, unsigned& n_rej) {
+  const int c = T.cid[row];
+  int acc = 0;
+  if (c >= 0) {
+    const double lp = gauss_finish(g.c0, maha[row], g.log_of_pdf);
+    acc = metropolis(a.lnl[c], lp, T.accept_u[row]);
+    if (acc < 0) {
+      *a.nan_flag = 1;
+      acc = 0;
+    }
+    if (acc) a.lnl[c] = lp;
+    if (a.tr.accept) a.tr.accept[c] = acc;
+    if (a.tr.lnl_prop) a.tr.lnl_prop[c] = lp;
+  }
+  T.acc[row] = acc;
+  n_acc += __popc(__ballot_sync(0xFFFFFFFFu, c >= 0 && acc));
+  n_rej += __popc(__ballot_sync(0xFFFFFFFFu, c >= 0 && !acc));
+}
+
 // =====================================================================================
 // Variant 3 (default): the same producer / consumer pipeline re-balanced after profiling
 // variant 2 (profiles/r1_v2_*): its 8 consumer warps sat at the FULL barrier 76 % of the
 // time while each of the 12 producer warps walked its chains serially at ~0.2 IPC.  Here
-//   * 4 consumer warps (128 registers) each own TWO 14-column strips of the tile product;
+//   * 4 consumer warps each own 16 rows of the tile product and run it on the FP64 tensor
+//     pipe (mma.sync.m8n8k4.f64, W pre-arranged in fragment order in shared memory);
 //   * 16 producer warps (88 registers) own exactly 4 chains of every 64-chain tile;
 //   * the producer stages are specialised at compile time (DREAM with 3 pairs, or the
 //     runtime-general form), need d % 4 == 0 so every row access is a 16-byte vector, test
 //     the crossover mask on the raw Philox words against an integer threshold, and take
 //     the jump statistic's 1/variance from a Newton reciprocal instead of an IEEE division.
-// Draw values, proposal arithmetic and the order of every floating-point sum are those of
-// the other variants, so the chains are bit-identical to them.
+// Draw values and proposal arithmetic are those of the other variants (identical proposals);
+// the quadratic form is summed in the DMMA fragment order, so ln_like agrees with them to
+// rounding (~1e-15 relative), not bit for bit.
 constexpr int kV3ConsWarps = 4, kV3ProdWarps = 16;
 constexpr int kV3Threads = 32 * (kV3ConsWarps + kV3ProdWarps);   // 640
 constexpr int kV3ProdThreads = 32 * kV3ProdWarps;
@@ -716,9 +832,12 @@ __device__ __forceinline__ void tile_stage_propose_v3(const PhaseArgs& a, const 
   const bool welford_var = adapt && !(REPLAY && a.hist_base != nullptr);
   for (int row = gwarp; row < kTileRows; row += gwarps) {
     const int c = T.cid[row];
-    double* prow = P + row * pld + 4 * lane;
+    double* prow = P + row * pld + 4 * lane;          // pld even: 16-byte aligned
     if (c < 0) {
-      if (act) prow[0] = prow[1] = prow[2] = prow[3] = 0.0;
+      if (act) {
+        *reinterpret_cast<double2*>(prow) = make_double2(0.0, 0.0);
+        *reinterpret_cast<double2*>(prow + 2) = make_double2(0.0, 0.0);
+      }
       continue;
     }
     double cur[4] = {0, 0, 0, 0}, S[4] = {0, 0, 0, 0}, var[4] = {0, 0, 0, 0};
@@ -797,7 +916,7 @@ __device__ __forceinline__ void tile_stage_propose_v3(const PhaseArgs& a, const 
     }
     double delta = 0.0;
     if (act) {
-      double e[4], nn[4];
+      double e[4], nn[4], prv[4];
       en4<REPLAY>(a, c, lane, e, nn);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -817,8 +936,10 @@ __device__ __forceinline__ void tile_stage_propose_v3(const PhaseArgs& a, const 
         } else {
           pr = demc_prop(cur[q], S[q], nn[q], gamma);
         }
-        prow[q] = pr;
+        prv[q] = pr;
       }
+      *reinterpret_cast<double2*>(prow) = make_double2(prv[0], prv[1]);
+      *reinterpret_cast<double2*>(prow + 2) = make_double2(prv[2], prv[3]);
     }
     if (dream) {
       delta = group_sum_d<32>(delta);
@@ -851,7 +972,9 @@ __device__ __forceinline__ void tile_stage_writeback_v3(const PhaseArgs& a, cons
     double s[4];
     if (acc) {
       const double* prow = P + row * pld + 4 * lane;
-      s[0] = prow[0]; s[1] = prow[1]; s[2] = prow[2]; s[3] = prow[3];
+      const double2 p0 = *reinterpret_cast<const double2*>(prow);
+      const double2 p1 = *reinterpret_cast<const double2*>(prow + 2);
+      s[0] = p0.x; s[1] = p0.y; s[2] = p1.x; s[3] = p1.y;
       *reinterpret_cast<double2*>(xc) = make_double2(s[0], s[1]);
       *reinterpret_cast<double2*>(xc + 2) = make_double2(s[2], s[3]);
     } else {
@@ -875,19 +998,44 @@ __device__ __forceinline__ void tile_stage_writeback_v3(const PhaseArgs& a, cons
   }
 }
 
+__host__ __device__ inline size_t v3_ptile_doubles(int d) { return (size_t)kTileRows * dmma_pld(d) + kTileRows; }
+inline size_t fused_v3_smem(int d) {
+  return sizeof(double) * (gauss_table_doubles(d) + 2 * v3_ptile_doubles(d) + 3 * gauss_scratch_doubles());
+}
+__device__ __forceinline__ void fill_tables_v3(const PhaseArgs& a, const GaussArgs& g, const GaussTables& t,
+                                               int tid, int nthreads) {
+  load_W_fragments(t.Ws, t.mus, g.W, g.mu, a.d, g.r, tid, nthreads);
+  for (int dp = tid; dp <= a.d; dp += nthreads)
+    t.gam[dp] = dp == 0 ? 0.0
+                        : __ddiv_rn(a.gamma_num, __dsqrt_rn(__dmul_rn(__dmul_rn(2.0, (double)a.del_pairs),
+                                                                      (double)dp)));
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int m = 0; m < a.n_cr; ++m) tot = __dadd_rn(tot, a.p_cr[m]);
+    double acc = 0.0;
+    for (int m = 0; m < a.n_cr; ++m) {
+      acc = __dadd_rn(acc, a.p_cr[m]);
+      t.cdf[m] = __ddiv_rn(acc, tot);
+      t.crv[m] = __ddiv_rn((double)(m + 1), (double)a.n_cr);
+      const double lim = floor(t.crv[m] * 4294967296.0 - 0.5);
+      t.thr[m] = lim >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)lim;
+    }
+  }
+}
+
 template <bool REPLAY, bool CENTER, int NPAIR>
 __global__ void __launch_bounds__(kV3Threads, 1)
 fused_gauss_v3_kernel(const PhaseArgs a, const GaussArgs g) {
   extern __shared__ __align__(16) double smem[];
-  const int d = a.d, pld = d | 1;
-  const GaussTables tb = carve_tables(smem, d);
+  const int d = a.d, pld = dmma_pld(d), NT = dmma_ntiles(g.r);
+  const GaussTables tb = carve_tables(smem, d);      // tb.Ws holds W in DMMA fragment order
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* Pbuf = smem + gauss_table_doubles(d);
-  const size_t p_stride = gauss_ptile_doubles(d);
-  const size_t part_off = ((size_t)kTileRows * pld + 1) & ~(size_t)1;
+  const size_t p_stride = v3_ptile_doubles(d);
+  const size_t part_off = (size_t)kTileRows * pld;   // maha[64] after the tile
   double* Tbuf = Pbuf + 2 * p_stride;
   const size_t t_stride = gauss_scratch_doubles();
-  fill_tables(a, g, tb, threadIdx.x, kV3Threads);
+  fill_tables_v3(a, g, tb, threadIdx.x, kV3Threads);
   __syncthreads();
   const PhaseLists L = phase_lists(a);
   const int n_tiles = (L.n_self + kTileRows - 1) / kTileRows;
@@ -903,10 +1051,9 @@ fused_gauss_v3_kernel(const PhaseArgs a, const GaussArgs g) {
       double* part = P + part_off;
       TileScratch& T = *reinterpret_cast<TileScratch*>(Tbuf + (i % 3) * t_stride);
       nbar_sync(BAR_FULL0 + b, kV3Threads);            // producers filled buffer b
-      gauss_tile_rowsums<CENTER>(P, pld, tb.Ws, tb.mus, d, part, 2 * warp, lane);
-      gauss_tile_rowsums<CENTER>(P, pld, tb.Ws, tb.mus, d, part, 2 * warp + 1, lane);
+      gauss_tile_maha_dmma<CENTER>(P, pld, tb.Ws, tb.mus, d, NT, part, warp, lane);
       nbar_sync(BAR_CONS, kV3ConsThreads);
-      if (threadIdx.x < kTileRows) tile_stage_decide(a, g, T, part, threadIdx.x, n_acc, n_rej);
+      if (threadIdx.x < kTileRows) tile_stage_decide_maha(a, g, T, part, threadIdx.x, n_acc, n_rej);
       nbar_arrive(BAR_DONE0 + b, kV3Threads);          // decisions of tile i are in T.acc
     }
     if (lane == 0) {
@@ -1103,6 +1250,7 @@ inline int try_fused_phase(const TargetView& tv, const PhaseArgs& a, cudaStream_
     } else {
       const int grid = n_tiles > 148 ? 148 : (n_tiles < 1 ? 1 : n_tiles);
       const bool d3 = a.algo == BPM_ALGO_DREAM && a.del_pairs == 3;
+      const size_t sm = fused_v3_smem(a.d);
       int rc;
       if (tv.mu_is_zero)
         rc = d3 ? launch_fused_v3<REPLAY, false, 3>(a, g, grid, sm, s)

@@ -234,20 +234,22 @@ def test_full_size_properties_1e5_chains_100d():
         s.run_mcmc(N * (G + 1))
         runs.append(s)
     a, b, c2, c3 = runs
-    assert torch.equal(a._hist.tensor(), c3._hist.tensor()), "v3 and the 12-producer variant must agree"
-    del c3
     ha, hb = a._hist.tensor(), b._hist.tensor()
     assert ha.shape == (G + 1, N, d)
-    assert torch.equal(ha, hb), "fused and split paths must agree bit for bit"
-    assert torch.equal(ha, c2._hist.tensor()), "both fused variants must agree bit for bit"
-    assert torch.equal(a._lnl, b._lnl) and torch.equal(a._lnl, c2._lnl)
-    del c2
+    # every variant builds identical proposals and makes identical accept decisions; the
+    # default variant sums the quadratic form in DMMA fragment order, so its cached
+    # likelihoods agree with the scalar variants to rounding, theirs among themselves exactly
+    assert torch.equal(ha, hb), "fused and split paths must produce the same chains"
+    assert torch.equal(hb, c2._hist.tensor()) and torch.equal(hb, c3._hist.tensor())
+    assert torch.equal(b._lnl, c2._lnl) and torch.equal(b._lnl, c3._lnl)
+    assert torch.allclose(a._lnl, b._lnl, rtol=1e-13, atol=0.0)
+    del c2, c3
     np.testing.assert_allclose(a.p_cr, b.p_cr, rtol=1e-12)
     # history row G == live population; every chain moved at most once per generation
     assert torch.equal(ha[G], a._X)
     # cached likelihood == fresh evaluation of the current state
     fresh = a._eval_lnl_rows(a._X)
-    assert torch.equal(fresh, a._lnl)
+    assert torch.equal(fresh, b._lnl) and torch.allclose(fresh, a._lnl, rtol=1e-13, atol=0.0)
     # counters add up: every chain stepped once per generation
     assert a.n_accepted + a.n_rejected == N * G + 1
     changed = int((ha[1:] != ha[:-1]).any(dim=2).sum().item())
