@@ -152,7 +152,8 @@ def run_ours(args):
     K, W = args.steps, args.warmup
     s = DreamMpi(tgt.ln_like, np.zeros(DIM), n_chains=N, varepsilon=np.arange(DIM) + 1.0, seed=42,
                  n_cr_gen=50, burnin_gen=args.burnin_gen, device=local_rank,
-                 history=args.history, history_reserve=K + W + SETUP_GENS + 8, fused=args.fused)
+                 history=args.history, history_reserve=K + W + SETUP_GENS + 8, fused=args.fused,
+                 exchange=args.exchange)
     lib, h = s._libh, s._handle
     n_local = len(s.rank_chain_ids)
 
@@ -255,6 +256,9 @@ def run_ours(args):
                            "cr_adaptation": "on" if args.burnin_gen > SETUP_GENS + W + K else "off",
                            "init": "theta_0 + N(0, diag(Sigma)), %d untimed setup generations" % SETUP_GENS,
                            "rng": "philox4x32-10 seed 42", "parallelism": "chains sharded x%d" % world,
+                           "exchange": ("none (1 GPU)" if world == 1 else
+                                        "accepted rows stored into peer replicas in-kernel (NVLink P2P) + barrier"
+                                        if s._exchange == "p2p" else "NCCL all-gather of the shard per half-phase"),
                            "l2": "working set per generation (state 80 MB + moments 160 MB + history "
                                  "row 80 MB per GPU) exceeds the 126 MB L2; no explicit flush"},
                 "acceptance_fraction": acc_frac, "gpu_launches": launches,
@@ -275,6 +279,7 @@ def main():
     ap.add_argument("--history", default="full", choices=["full", "none"])
     ap.add_argument("--fused", type=int, default=1, help="1 fused v3 (default), 3 fused 12-producer variant, 2 two-halves fused kernel, 0 split path")
     ap.add_argument("--burnin-gen", type=int, default=2000, help="DREAM burnin_gen (2000 = tests/test_100dgauss.py:109)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "allgather"], help="multi-GPU state exchange")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     args = ap.parse_args()

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libbipymc_b200.so")
 
 BPM_ALGO_DEMC, BPM_ALGO_DREAM = 0, 1
 TARGET_EXTERNAL, TARGET_BANANA, TARGET_BIMODAL, TARGET_GAUSS, TARGET_LINEFIT = 0, 1, 2, 3, 4
-BPM_MAX_PAIRS, BPM_MAX_CR = 8, 16
+BPM_MAX_PAIRS, BPM_MAX_CR, BPM_MAX_PEERS = 8, 16, 15
 
 
 class Config(C.Structure):
@@ -86,6 +86,12 @@ SIGNATURES = {
     "bpm_test_permutation": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int32, C.POINTER(C.c_int32)]),
     "bpm_generations_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                        C.c_int32]),
+    "bpm_dev_alloc": (C.c_int, [C.c_int32, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "bpm_dev_free": (C.c_int, [C.c_int32, C.c_void_p]),
+    "bpm_ipc_export": (C.c_int, [C.c_int32, C.c_void_p, C.c_char_p]),
+    "bpm_ipc_open": (C.c_int, [C.c_int32, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "bpm_ipc_close": (C.c_int, [C.c_int32, C.c_void_p]),
+    "bpm_set_peers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32]),
     "bpm_moments_from_history": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p]),
     "bpm_omega_track": (C.c_int, [C.c_void_p, C.c_int32]),
     "bpm_omega": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),

@@ -84,6 +84,8 @@ struct bpm_engine {
   double* hX = nullptr;
   double* hL = nullptr;
   int fused_ok = 1;  // allow the fused fast paths
+  double* peers[BPM_MAX_PEERS] = {nullptr};   // other ranks' X replicas mapped here (bpm_set_peers)
+  int n_peers = 0;
   // diagnostics (diagnostics.cuh): Omega tracking, IQR reset, R-hat scratch
   double* omega_sum = nullptr;   // [N] sum of lnL per chain since tracking started
   double* omega_buf = nullptr;   // [2][N] Omega means / sorted copy
@@ -190,6 +192,8 @@ struct bpm_engine {
     a.inv_n1 = 1.0 / (double)(a.mom_len + 1);
     a.p_cr = p_cr; a.cr_delta = cr_delta; a.cr_pick = cr_pick;
     a.prop = prop; a.lnl_prop = lnl_prop;
+    for (int p = 0; p < n_peers; ++p) a.peers[p] = peers[p];
+    a.n_peers = n_peers;
     a.n_acc = counters; a.n_rej = counters + 1; a.nan_flag = nan_flag;
     a.rng = bpm::make_rng(cfg.seed, (uint64_t)st->hist_len);
     if (rp) a.rp = *rp;
@@ -671,6 +675,51 @@ int bpm_generations_host(bpm_handle h, double* X_host, double* lnl_host, int64_t
   CU_TRY(cudaMemcpyAsync(X_host, h->hX, nx, cudaMemcpyDeviceToHost, s));
   CU_TRY(cudaMemcpyAsync(lnl_host, h->hL, nl, cudaMemcpyDeviceToHost, s));
   CU_TRY(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int bpm_dev_alloc(int32_t device, uint64_t bytes, void** dev_ptr) {
+  if (!dev_ptr) return fail("null argument");
+  CU_TRY(cudaSetDevice(device));
+  CU_TRY(cudaMalloc(dev_ptr, (size_t)bytes));
+  return 0;
+}
+int bpm_dev_free(int32_t device, void* dev_ptr) {
+  CU_TRY(cudaSetDevice(device));
+  CU_TRY(cudaFree(dev_ptr));
+  return 0;
+}
+int bpm_ipc_export(int32_t device, const void* dev_ptr, unsigned char handle64[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (!dev_ptr || !handle64) return fail("null argument");
+  CU_TRY(cudaSetDevice(device));
+  cudaIpcMemHandle_t hd;
+  CU_TRY(cudaIpcGetMemHandle(&hd, const_cast<void*>(dev_ptr)));
+  memcpy(handle64, &hd, 64);
+  return 0;
+}
+int bpm_ipc_open(int32_t device, const unsigned char handle64[64], void** dev_ptr) {
+  if (!dev_ptr || !handle64) return fail("null argument");
+  CU_TRY(cudaSetDevice(device));
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle64, 64);
+  CU_TRY(cudaIpcOpenMemHandle(dev_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int bpm_ipc_close(int32_t device, void* dev_ptr) {
+  CU_TRY(cudaSetDevice(device));
+  CU_TRY(cudaIpcCloseMemHandle(dev_ptr));
+  return 0;
+}
+int bpm_set_peers(bpm_handle h, double* const* peer_X, int32_t n_peers) {
+  if (!h) return fail("null handle");
+  if (n_peers < 0 || n_peers > BPM_MAX_PEERS) return fail("n_peers must be in [0, 15]");
+  if (n_peers > 0 && !peer_X) return fail("null peer array");
+  for (int p = 0; p < n_peers; ++p) {
+    if (!peer_X[p]) return fail("null peer pointer");
+    h->peers[p] = peer_X[p];
+  }
+  h->n_peers = n_peers;
   return 0;
 }
 

@@ -496,10 +496,14 @@ __device__ __forceinline__ void tile_stage_writeback(const PhaseArgs& a, const T
       if (full) {
         *reinterpret_cast<double2*>(xc) = make_double2(s[0], s[1]);
         *reinterpret_cast<double2*>(xc + 2) = make_double2(s[2], s[3]);
+        store_peers4(a, (size_t)c * a.ld + 4 * blk, s[0], s[1], s[2], s[3]);
       } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (4 * blk + q < d) xc[q] = s[q];
+          if (4 * blk + q < d) {
+            xc[q] = s[q];
+            store_peers1(a, (size_t)c * a.ld + 4 * blk + q, s[q]);
+          }
       }
     } else if (a.mean || a.hist_row) {
       if (full) {
@@ -977,6 +981,7 @@ __device__ __forceinline__ void tile_stage_writeback_v3(const PhaseArgs& a, cons
       s[0] = p0.x; s[1] = p0.y; s[2] = p1.x; s[3] = p1.y;
       *reinterpret_cast<double2*>(xc) = make_double2(s[0], s[1]);
       *reinterpret_cast<double2*>(xc + 2) = make_double2(s[2], s[3]);
+      store_peers4(a, (size_t)c * a.ld + 4 * lane, s[0], s[1], s[2], s[3]);
     } else {
       const double2 u0 = ldg2(xc), u1 = ldg2(xc + 2);
       s[0] = u0.x; s[1] = u0.y; s[2] = u1.x; s[3] = u1.y;
@@ -1189,7 +1194,10 @@ __global__ void __launch_bounds__(128) fused_small_kernel(const PhaseArgs a, con
     for (int q = 0; q < 4; ++q)
       if (q < d) {
         const double s = acc ? pr[q] : cur[q];
-        if (acc) xc[q] = s;
+        if (acc) {
+          xc[q] = s;
+          store_peers1(a, (size_t)c * a.ld + q, s);
+        }
         if (a.mean) {
           double mu = a.mean[o + q], v = a.m2[o + q];
           welford_update(s, a.inv_n1, mu, v);

@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(kThreads) accept_kernel(const PhaseArgs a) {
             if (acc) {
               s = pr[i];
               xc[i] = s;
+              store_peers1(a, (size_t)c * a.ld + i, s);
             }
             if (a.mean) {  // Welford update with the appended row (chain.py:51-54)
               const size_t o = (size_t)(c - a.chain_lo) * a.ld + i;

@@ -45,6 +45,9 @@ struct PhaseArgs {
   // workspace
   double* prop;      // [nA][ld] proposals in phase order
   double* lnl_prop;  // [nA]
+  // peer replicas of X on the other GPUs (bpm_set_peers); accepted rows are stored there too
+  double* peers[BPM_MAX_PEERS];
+  int32_t n_peers;
   // counters
   unsigned long long* n_acc;
   unsigned long long* n_rej;
@@ -56,6 +59,19 @@ struct PhaseArgs {
   // optional trace
   bpm_trace_out tr;
 };
+
+// Accepted row -> every peer replica (4 doubles of chain c starting at element off; 16-byte aligned).
+__device__ __forceinline__ void store_peers4(const PhaseArgs& a, size_t elem_off, double s0, double s1,
+                                             double s2, double s3) {
+  for (int p = 0; p < a.n_peers; ++p) {
+    double* q = a.peers[p] + elem_off;
+    *reinterpret_cast<double2*>(q) = make_double2(s0, s1);
+    *reinterpret_cast<double2*>(q + 2) = make_double2(s2, s3);
+  }
+}
+__device__ __forceinline__ void store_peers1(const PhaseArgs& a, size_t elem_off, double s) {
+  for (int p = 0; p < a.n_peers; ++p) a.peers[p][elem_off] = s;
+}
 
 // Phase-list helpers.  self = chains updated in this phase, pool = the other half.
 struct PhaseLists {

@@ -275,6 +275,14 @@ class DeMcMpi(object):
         self._reserve_rows = int(kwargs.get("history_reserve", 0))   # generations to pre-allocate
         # IQR outlier-chain reset every `outlier_gen` generations (0 = off, the reference's
         # behaviour); DREAM applies it only while k < burnin_gen (Vrugt et al. 2009)
+        # multi-GPU exchange of updated chain states: "p2p" = accepted rows are stored into the
+        # peer replicas from inside the kernels (CUDA IPC peer memory over NVLink) and only a
+        # tiny barrier collective runs between half-phases; "allgather" = NCCL all-gather of
+        # every rank's shard after each half-phase (the reference's comm.Allgather, demc.py:93,116)
+        self._exchange = kwargs.get("exchange", "p2p")
+        if self._exchange not in ("p2p", "allgather"):
+            raise ValueError("exchange must be 'p2p' or 'allgather'")
+        self._peer_ptrs, self._own_X_ptr = [], None
         self.outlier_gen = int(kwargs.get("outlier_gen", 0))
         self.n_outlier_resets = 0
         self._setup_device()
@@ -344,11 +352,86 @@ class DeMcMpi(object):
 
     def __del__(self):
         try:
+            self._release_peer_memory()
             if getattr(self, "_handle", None) is not None:
                 self._libh.bpm_destroy(self._handle)
                 self._handle = None
         except Exception:
             pass
+
+    # ------------------------------------------------------------------ peer memory
+    def _release_peer_memory(self):
+        lib = getattr(self, "_libh", None)
+        if lib is None:
+            return
+        if getattr(self, "_handle", None) is not None and getattr(self, "_peer_ptrs", None):
+            lib.bpm_set_peers(self._handle, None, 0)
+        for q in getattr(self, "_peer_ptrs", []):
+            lib.bpm_ipc_close(self._device_index, C.c_void_p(q))
+        self._peer_ptrs = []
+        if getattr(self, "_own_X_ptr", None):
+            self._X = None
+            lib.bpm_dev_free(self._device_index, C.c_void_p(self._own_X_ptr))
+            self._own_X_ptr = None
+
+    def _alloc_population(self, N, ld):
+        """[N, ld] float64 population replica.  Sharded runs with exchange="p2p" take it from
+        bpm_dev_alloc (a plain cudaMalloc block, so its IPC handle can be opened by the peers)
+        and register every other rank's replica with the engine (bpm_set_peers)."""
+        torch = _torch()
+        if self.comm.size == 1 or self._exchange != "p2p":
+            return torch.zeros((N, ld), dtype=torch.float64, device=self._device)
+        import torch.distributed as dist
+        lib = self._libh
+        if self._peer_ptrs or self._own_X_ptr:
+            torch.cuda.synchronize(self._device)
+            dist.barrier()
+            self._release_peer_memory()
+        ptr = C.c_void_p()
+        _lib.check(lib.bpm_dev_alloc(self._device_index, N * ld * 8, C.byref(ptr)))
+        self._own_X_ptr = ptr.value
+        X = self._wrap_device(ptr.value, (N, ld))
+        X.zero_()
+        hbuf = C.create_string_buffer(64)
+        _lib.check(lib.bpm_ipc_export(self._device_index, ptr, hbuf))
+        handles = [None] * self.comm.size
+        dist.all_gather_object(handles, bytes(hbuf.raw))
+        ok = 1
+        for r, hb in enumerate(handles):
+            if r == self.comm.rank:
+                continue
+            q = C.c_void_p()
+            if lib.bpm_ipc_open(self._device_index, C.create_string_buffer(hb, 64), C.byref(q)) != 0:
+                ok = 0
+                break
+            self._peer_ptrs.append(q.value)
+        flag = torch.tensor([ok], dtype=torch.int32, device=self._device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            # no peer access between some pair of GPUs: every rank falls back to the NCCL gather
+            for q in self._peer_ptrs:
+                lib.bpm_ipc_close(self._device_index, C.c_void_p(q))
+            self._peer_ptrs = []
+            self._exchange = "allgather"
+            return X
+        arr = (C.c_void_p * len(self._peer_ptrs))(*self._peer_ptrs)
+        _lib.check(lib.bpm_set_peers(self._handle, arr, len(self._peer_ptrs)))
+        self._bar = torch.zeros((1,), dtype=torch.float32, device=self._device)
+        return X
+
+    def _phase_exchange(self, last):
+        """Make this half-phase's updates visible on every rank before the next one reads them.
+        p2p: the rows are already in the peer replicas, only a barrier is needed (the CR
+        all-reduce that follows the second half-phase of a DREAM generation is that barrier)."""
+        if self.comm.size == 1:
+            return
+        if self._exchange == "p2p":
+            if last and self._algo == _lib.BPM_ALGO_DREAM:
+                return
+            import torch.distributed as dist
+            dist.all_reduce(self._bar)
+        else:
+            self._allgather_population()
 
     # ------------------------------------------------------------------ chains
     def init_chains(self, theta_0, varepsilon=1e-6, **kwargs):
@@ -380,8 +463,12 @@ class DeMcMpi(object):
         N, d, ld = self.n_chains, self.dim, self._ld
         lo, hi = int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
         nl = hi - lo
-        self._X = torch.zeros((N, ld), dtype=torch.float64, device=self._device)
+        self._X = self._alloc_population(N, ld)
         self._X[:, :d] = torch.from_numpy(np.ascontiguousarray(x0)).to(self._device)
+        if self.comm.size > 1:
+            import torch.distributed as dist
+            torch.cuda.synchronize(self._device)
+            dist.barrier()          # nobody steps before every replica holds the initial states
         self._lnl = torch.zeros((N,), dtype=torch.float64, device=self._device)
         self._mean = self._X[lo:hi].clone()
         self._m2 = torch.zeros((nl, ld), dtype=torch.float64, device=self._device)
@@ -665,8 +752,7 @@ class DeMcMpi(object):
             if self._mode() == "device":
                 # built-in likelihood: the whole half-phase stays inside the library
                 _lib.check(lib.bpm_phase(h, C.byref(st), phase, s))
-                if self.comm.size > 1:
-                    self._allgather_population()
+                self._phase_exchange(last=(phase == 1))
                 continue
             prop_p, n_p = C.c_void_p(), C.c_int32()
             _lib.check(lib.bpm_propose(h, C.byref(st), phase, C.byref(prop_p), C.byref(n_p), s))
@@ -678,8 +764,7 @@ class DeMcMpi(object):
                 # likelihood values are ignored by bpm_accept (ownership check in-kernel)
                 pass
             _lib.check(lib.bpm_accept(h, C.byref(st), phase, lnl_prop.data_ptr(), None, s))
-            if self.comm.size > 1:
-                self._allgather_population()
+            self._phase_exchange(last=(phase == 1))
         _lib.check(lib.bpm_end_generation(h, C.byref(st), s))
         if self.comm.size > 1 and self._algo == _lib.BPM_ALGO_DREAM:
             self._allreduce_cr()

@@ -30,6 +30,7 @@ extern "C" {
 
 #define BPM_MAX_PAIRS 8
 #define BPM_MAX_CR 16
+#define BPM_MAX_PEERS 15
 
 /* Built-in batched likelihoods (the reference's test targets). */
 #define BPM_TARGET_EXTERNAL 0 /* ln_like supplied through bpm_propose / bpm_accept or a callback */
@@ -186,6 +187,24 @@ int bpm_end_generation(bpm_handle h, bpm_state* st, bpm_stream stream);
  * bpm_begin_generation and bpm_end_generation: what a multi-rank host calls before
  * its all-gather of the population (demc.py:93,116). */
 int bpm_phase(bpm_handle h, bpm_state* st, int32_t phase, bpm_stream stream);
+
+/* Multi-GPU exchange over peer memory.  The reference all-gathers the whole population
+ * before each half-phase (comm.Allgather, demc.py:93,116).  Here every rank keeps a replica
+ * of X; with peers set, the accept stage of every kernel stores an ACCEPTED chain's new row
+ * into each peer replica as well (NVLink peer stores from inside the kernel), so only the
+ * rows that changed cross the fabric and no separate gather runs.  The host still has to
+ * put a cross-rank barrier between half-phases (any tiny collective on the same stream).
+ *   bpm_dev_alloc / bpm_dev_free : plain cudaMalloc'ed memory (IPC-exportable) for X
+ *   bpm_ipc_export : 64-byte cudaIpcMemHandle of such an allocation (send it to the peers)
+ *   bpm_ipc_open / bpm_ipc_close : map a peer's allocation into this process
+ *   bpm_set_peers : device pointers (mapped here) of the OTHER ranks' X replicas, same
+ *                   [n_chains][ld] layout; n_peers = 0 switches the peer stores off.     */
+int bpm_dev_alloc(int32_t device, uint64_t bytes, void** dev_ptr);
+int bpm_dev_free(int32_t device, void* dev_ptr);
+int bpm_ipc_export(int32_t device, const void* dev_ptr, unsigned char handle64[64]);
+int bpm_ipc_open(int32_t device, const unsigned char handle64[64], void** dev_ptr);
+int bpm_ipc_close(int32_t device, void* dev_ptr);
+int bpm_set_peers(bpm_handle h, double* const* peer_X, int32_t n_peers);
 
 /* Host-buffer entry (the end-to-end path): X_host / lnl_host are HOST arrays (pinned
  * for full speed); copies them to the device, runs n_gen native generations without

@@ -32,10 +32,13 @@ def main():
          dict(burnin_gen=1000, n_cr_gen=3, outlier_gen=5), 1e-2),
     ]
     G = 12
-    for name, cls, tgt, th0, N, kw, veps in cases:
+    runs = [(c, ex) for c in cases for ex in ("p2p", "allgather")]
+    for (name, cls, tgt, th0, N, kw, veps), exchange in runs:
         np.random.seed(3)
-        s = cls(tgt.ln_like, th0, n_chains=N, seed=5, varepsilon=veps, device=local, **kw)
+        s = cls(tgt.ln_like, th0, n_chains=N, seed=5, varepsilon=veps, device=local, exchange=exchange, **kw)
         assert s.comm.size == world
+        if exchange == "p2p" and s._exchange != "p2p" and rank == 0:
+            print("NOTE: no peer access on this box, p2p fell back to", s._exchange, flush=True)
         s.run_mcmc(N * (G + 1))
         full = s.super_chain_mpi(0)
         acc = (s.n_accepted, s.n_rejected)
@@ -59,8 +62,9 @@ def main():
             np.testing.assert_allclose(rh, one.rhat(), rtol=1e-6 if not exact else 1e-9)
             if "outlier" in name:
                 print(name, "resets", s.n_outlier_resets, one.n_outlier_resets)
-            print("case", name, "ok", flush=True)
+            print("case", name, exchange, "->", s._exchange, "ok", flush=True)
         dist.barrier()
+        del s
     if rank == 0:
         print("MULTIGPU_OK", flush=True)
     dist.destroy_process_group()
