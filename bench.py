@@ -33,6 +33,17 @@ METRIC = "DREAM chain-steps/s, 100-D Gaussian"
 UNIT = "chain-steps/s"
 
 
+def ncu_traffic(history, adapt):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the
+    committed ncu --set full capture of this same workload (profiles/r1_traffic.json); None for
+    configurations that were not captured."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(p):
+        return None
+    j = json.load(open(p))
+    return j.get("history=%s,adapt=%s" % (history, "on" if adapt else "off"))
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -102,11 +113,12 @@ def run_reference(args):
     from oracle.mp_port import time_port
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
-    n_chains = 40 * procs
+    n_chains = 200 * procs
     # a step = one generation of the sample population; warm-up generations are untimed
     dt, steps = time_port(cpu_port_spec(n_chains), procs, gens=args.steps, gens_warm=max(args.warmup, 1))
     v = steps / dt
-    sample = "DREAM 100-D Gaussian, %d chains (40 per process), %d timed generations" % (n_chains, args.steps)
+    sample = "DREAM 100-D Gaussian, %d chains (200 per process), %d timed generations, %.1f s" % (
+        n_chains, args.steps, dt)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -123,7 +135,7 @@ def cpu_baseline_leg():
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
     n_chains = 40 * procs
-    gens = 25
+    gens = 400            # ~10-20 s of host work: the port's np.std over the growing history is O(T)
     dt, steps = time_port(cpu_port_spec(n_chains), procs, gens=gens, gens_warm=2)
     return {"value": steps / dt, "unit": UNIT, "cores": procs, "kind": "port",
             "sample": "oracle port of DreamMpi (shared-memory ranks), 100-D Gaussian, %d chains, "
@@ -216,7 +228,11 @@ def run_ours(args):
         avg_ms = ms_k[dom] / n_k[dom]
         ach = per_kind_bytes[kinds[dom]] * chains_per_launch / (avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": kinds[dom], "achieved": ach, "peak": hbm, "unit": "GB/s",
-                "frac": ach / hbm, "traffic": None, "avg_launch_ms": avg_ms,
+                "frac": ach / hbm,
+                "traffic": ncu_traffic(args.history, adapt_b > 0) if (kinds[dom] == "fused_phase" and world == 1
+                                                                      and args.fused == 1) else None,
+                "algorithmic_bytes_per_launch": per_kind_bytes[kinds[dom]] * chains_per_launch,
+                "avg_launch_ms": avg_ms,
                 "bytes_per_chain_step": per_kind_bytes[kinds[dom]], "peak_source": peak_src,
                 "share_of_step": ms_k[dom] / max(sum(ms_k), 1e-12)}
         if kinds[dom] == "likelihood":

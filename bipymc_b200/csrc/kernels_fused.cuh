@@ -851,7 +851,7 @@ __device__ __forceinline__ void tile_stage_propose_v3(const PhaseArgs& a, const 
       const double2 u0 = ldg2(xc), u1 = ldg2(xc + 2);
       if (welford_var) {
         const double* mp = a.m2 + (size_t)(c - a.chain_lo) * a.ld + 4 * lane;
-        const double2 w0 = ld_stream2(mp), w1 = ld_stream2(mp + 2);
+        const double2 w0 = ldg2(mp), w1 = ldg2(mp + 2);      // kept in L2: the write-back re-reads it
         var[0] = w0.x; var[1] = w0.y; var[2] = w1.x; var[3] = w1.y;
       }
       cur[0] = u0.x; cur[1] = u0.y; cur[2] = u1.x; cur[3] = u1.y;
@@ -1003,9 +1003,164 @@ __device__ __forceinline__ void tile_stage_writeback_v3(const PhaseArgs& a, cons
   }
 }
 
+
+// ---- mbarrier helpers (CTA scope): variant 3 hands tiles over with these so that no producer
+// warp ever waits for another producer warp -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_addr(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2, 0x1000;\n"
+                 "selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_addr(b)), "r"(parity) : "memory");
+  }
+}
+
+// Per-warp scalar draws: producer warp pw owns tile rows pw, pw + 16, pw + 32, pw + 48 from the
+// draws to the write-back, so the scratch of a row is written and read by one warp only (plus
+// the consumers, ordered by the FULL mbarrier).  gid0 = population-list index of tile row 0,
+// gid_end = end of this CTA's row range.
+template <bool REPLAY>
+__device__ __forceinline__ void warp_stage_draws(const PhaseArgs& a, const PhaseLists& L,
+                                                 const GaussTables& tb, TileScratch& T, int gid0,
+                                                 int gid_end, int pw, int lane) {
+  const bool dream = a.algo == BPM_ALGO_DREAM;
+  const int npair = dream ? a.del_pairs : 1;
+  const int nslots = 2 + npair;
+  const int rows_per_warp = kTileRows / kV3ProdWarps;
+  for (int idx = lane; idx < rows_per_warp * nslots; idx += 32) {
+    const int j = idx / nslots, slot = idx - j * nslots;
+    const int row = pw + kV3ProdWarps * j;
+    const int gid = gid0 + row;
+    bool valid = gid < gid_end;
+    const int c = valid ? L.self[gid] : 0;
+    valid = valid && c >= a.chain_lo && c < a.chain_hi;
+    if (slot == 0) T.cid[row] = valid ? c : -1;
+    if (!valid) continue;
+    const int row_bytes = a.ld * 8;
+    if (slot == 0) {
+      l2_prefetch_row(a.X + (size_t)c * a.ld, row_bytes);
+      if (a.mean) l2_prefetch_row(a.mean + (size_t)(c - a.chain_lo) * a.ld, row_bytes);
+    } else if (slot == 1) {
+      if (a.m2) l2_prefetch_row(a.m2 + (size_t)(c - a.chain_lo) * a.ld, row_bytes);
+    }
+    if (REPLAY) {
+      if (slot == 0) {
+        T.cr_idx[row] = dream ? a.rp.cr_idx[c] : 0;
+        T.accept_u[row] = a.rp.accept_u[c];
+      } else if (slot == 1) {
+        T.gamma_u[row] = a.rp.gamma_u[c];
+        T.fallback[row] = dream ? a.rp.fallback_dim[c] : -1;
+      } else {
+        const int p = slot - 2;
+        T.pa[row][p] = L.pool[a.rp.pairs[((size_t)c * npair + p) * 2 + 0]];
+        T.pb[row][p] = L.pool[a.rp.pairs[((size_t)c * npair + p) * 2 + 1]];
+        l2_prefetch_row(a.X + (size_t)T.pa[row][p] * a.ld, row_bytes);
+        l2_prefetch_row(a.X + (size_t)T.pb[row][p] * a.ld, row_bytes);
+      }
+    } else {
+      const Philox4 q = draw4(a.rng, (uint32_t)c, RNG_SCALAR, (uint32_t)slot);
+      if (slot == 0) {
+        int m = 0;
+        if (dream) {
+          const double u = slot0_cr_u(q);
+          for (int jj = 0; jj < a.n_cr; ++jj)
+            if (tb.cdf[jj] <= u) m = jj + 1;
+          m = m < a.n_cr ? m : a.n_cr - 1;
+        }
+        T.cr_idx[row] = m;
+        T.accept_u[row] = slot0_accept_u(q);
+      } else if (slot == 1) {
+        T.gamma_u[row] = slot1_gamma_u(q);
+        T.fallback[row] = slot1_fallback(q, a.d);
+      } else {
+        int r1, r2;
+        slot_pair(q, L.n_pool, r1, r2);
+        const int ga = L.pool[r1], gb = L.pool[r2];
+        T.pa[row][slot - 2] = ga;
+        T.pb[row][slot - 2] = gb;
+        l2_prefetch_row(a.X + (size_t)ga * a.ld, row_bytes);
+        l2_prefetch_row(a.X + (size_t)gb * a.ld, row_bytes);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// One chain row of the write-back, split so two rows can be in flight per warp.
+struct WbRow {
+  double2 m0, m1, v0, v1;
+  int c, acc;
+};
+__device__ __forceinline__ void wb_issue(const PhaseArgs& a, const TileScratch& T, int row, int lane, bool keep,
+                                         WbRow& w) {
+  w.c = T.cid[row];
+  w.acc = w.c >= 0 ? T.acc[row] : 0;
+  if (w.c < 0 || (!w.acc && !keep)) { w.c = -1; return; }
+  const size_t o = (size_t)(w.c - a.chain_lo) * a.ld + 4 * lane;
+  if (a.mean) {
+    w.m0 = ld_stream2(a.mean + o); w.m1 = ld_stream2(a.mean + o + 2);
+    w.v0 = ld_stream2(a.m2 + o); w.v1 = ld_stream2(a.m2 + o + 2);
+  }
+}
+__device__ __forceinline__ void wb_finish(const PhaseArgs& a, const double* __restrict__ P, int pld, int row,
+                                          int lane, WbRow& w) {
+  if (w.c < 0) return;
+  const size_t o = (size_t)(w.c - a.chain_lo) * a.ld + 4 * lane;
+  double s[4];
+  if (w.acc) {
+    double* xc = a.X + (size_t)w.c * a.ld + 4 * lane;
+    const double* prow = P + row * pld + 4 * lane;
+    const double2 p0 = *reinterpret_cast<const double2*>(prow);
+    const double2 p1 = *reinterpret_cast<const double2*>(prow + 2);
+    s[0] = p0.x; s[1] = p0.y; s[2] = p1.x; s[3] = p1.y;
+    *reinterpret_cast<double2*>(xc) = p0;
+    *reinterpret_cast<double2*>(xc + 2) = p1;
+    store_peers4(a, (size_t)w.c * a.ld + 4 * lane, s[0], s[1], s[2], s[3]);
+  } else {
+    // rejected: the chain's own row was read by the proposal stage moments ago (an L2 hit)
+    const double* xc = a.X + (size_t)w.c * a.ld + 4 * lane;
+    const double2 u0 = ldg2(xc), u1 = ldg2(xc + 2);
+    s[0] = u0.x; s[1] = u0.y; s[2] = u1.x; s[3] = u1.y;
+  }
+  if (a.mean) {
+    welford_update(s[0], a.inv_n1, w.m0.x, w.v0.x);
+    welford_update(s[1], a.inv_n1, w.m0.y, w.v0.y);
+    welford_update(s[2], a.inv_n1, w.m1.x, w.v1.x);
+    welford_update(s[3], a.inv_n1, w.m1.y, w.v1.y);
+    st_stream2(a.mean + o, w.m0.x, w.m0.y);
+    st_stream2(a.mean + o + 2, w.m1.x, w.m1.y);
+    st_stream2(a.m2 + o, w.v0.x, w.v0.y);
+    st_stream2(a.m2 + o + 2, w.v1.x, w.v1.y);
+  }
+  if (a.hist_row) {
+    st_stream2(a.hist_row + o, s[0], s[1]);
+    st_stream2(a.hist_row + o + 2, s[2], s[3]);
+  }
+}
+// write-back of the warp's rows of one tile (d % 4 == 0), two rows' loads in flight at a time
+__device__ __forceinline__ void warp_stage_writeback(const PhaseArgs& a, const TileScratch& T,
+                                                     const double* __restrict__ P, int pld, int pw, int lane) {
+  if (4 * lane >= a.d) return;
+  const bool keep = a.mean != nullptr || a.hist_row != nullptr;
+#pragma unroll 1
+  for (int row = pw; row < kTileRows; row += 2 * kV3ProdWarps) {
+    WbRow w0, w1;
+    wb_issue(a, T, row, lane, keep, w0);
+    wb_issue(a, T, row + kV3ProdWarps, lane, keep, w1);
+    wb_finish(a, P, pld, row, lane, w0);
+    wb_finish(a, P, pld, row + kV3ProdWarps, lane, w1);
+  }
+}
+
 __host__ __device__ inline size_t v3_ptile_doubles(int d) { return (size_t)kTileRows * dmma_pld(d) + kTileRows; }
 inline size_t fused_v3_smem(int d) {
-  return sizeof(double) * (gauss_table_doubles(d) + 2 * v3_ptile_doubles(d) + 3 * gauss_scratch_doubles());
+  return sizeof(double) * (gauss_table_doubles(d) + 2 * v3_ptile_doubles(d) + 3 * gauss_scratch_doubles() + 4);
 }
 __device__ __forceinline__ void fill_tables_v3(const PhaseArgs& a, const GaussArgs& g, const GaussTables& t,
                                                int tid, int nthreads) {
@@ -1040,11 +1195,20 @@ fused_gauss_v3_kernel(const PhaseArgs a, const GaussArgs g) {
   const size_t part_off = (size_t)kTileRows * pld;   // maha[64] after the tile
   double* Tbuf = Pbuf + 2 * p_stride;
   const size_t t_stride = gauss_scratch_doubles();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Tbuf + 3 * t_stride);   // full[2], done[2]
   fill_tables_v3(a, g, tb, threadIdx.x, kV3Threads);
+  if (threadIdx.x == 0) {
+    mbar_init(bars + 0, kV3ProdWarps); mbar_init(bars + 1, kV3ProdWarps);   // FULL: one arrival per producer warp
+    mbar_init(bars + 2, kTileRows); mbar_init(bars + 3, kTileRows);         // DONE: one per deciding thread
+  }
   __syncthreads();
   const PhaseLists L = phase_lists(a);
-  const int n_tiles = (L.n_self + kTileRows - 1) / kTileRows;
-  const int n_my = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  // every CTA owns an equal contiguous range of the phase list (no 5-vs-6-tile imbalance):
+  // full 64-row tiles plus one partial tile
+  const int per_cta = (L.n_self + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int g_lo = min((int)blockIdx.x * per_cta, L.n_self);
+  const int g_hi = min(g_lo + per_cta, L.n_self);
+  const int n_my = (g_hi - g_lo + kTileRows - 1) / kTileRows;
 
   if (warp < kV3ConsWarps) {
     // ------------------------------ consumers ------------------------------------------
@@ -1055,11 +1219,13 @@ fused_gauss_v3_kernel(const PhaseArgs a, const GaussArgs g) {
       double* P = Pbuf + b * p_stride;
       double* part = P + part_off;
       TileScratch& T = *reinterpret_cast<TileScratch*>(Tbuf + (i % 3) * t_stride);
-      nbar_sync(BAR_FULL0 + b, kV3Threads);            // producers filled buffer b
+      mbar_wait(bars + b, (i >> 1) & 1);                // every producer warp filled its rows of buffer b
       gauss_tile_maha_dmma<CENTER>(P, pld, tb.Ws, tb.mus, d, NT, part, warp, lane);
       nbar_sync(BAR_CONS, kV3ConsThreads);
-      if (threadIdx.x < kTileRows) tile_stage_decide_maha(a, g, T, part, threadIdx.x, n_acc, n_rej);
-      nbar_arrive(BAR_DONE0 + b, kV3Threads);          // decisions of tile i are in T.acc
+      if (threadIdx.x < kTileRows) {
+        tile_stage_decide_maha(a, g, T, part, threadIdx.x, n_acc, n_rej);
+        mbar_arrive(bars + 2 + b);                      // T.acc / lnl of this row are final
+      }
     }
     if (lane == 0) {
       if (n_acc) atomicAdd(a.n_acc, (unsigned long long)n_acc);
@@ -1067,32 +1233,31 @@ fused_gauss_v3_kernel(const PhaseArgs a, const GaussArgs g) {
     }
   } else {
     // ------------------------------ producers ------------------------------------------
+    // each warp is an independent pipeline over ITS rows: draws + L2 prefetch of tile i+1 |
+    // proposal of tile i | write-back of tile i-1; it synchronises only with the consumers
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     const int pw = warp - kV3ConsWarps;
-    const int ptid = threadIdx.x - kV3ConsThreads;
     if (n_my > 0)
-      tile_stage_draws<REPLAY>(a, L, tb, *reinterpret_cast<TileScratch*>(Tbuf), blockIdx.x, ptid,
-                               kV3ProdThreads);
-    nbar_sync(BAR_PROD, kV3ProdThreads);
+      warp_stage_draws<REPLAY>(a, L, tb, *reinterpret_cast<TileScratch*>(Tbuf), g_lo, g_hi, pw, lane);
     for (int i = 0; i <= n_my; ++i) {
       if (i + 1 < n_my)
-        tile_stage_draws<REPLAY>(a, L, tb, *reinterpret_cast<TileScratch*>(Tbuf + ((i + 1) % 3) * t_stride),
-                                 blockIdx.x + (i + 1) * gridDim.x, ptid, kV3ProdThreads);
+        warp_stage_draws<REPLAY>(a, L, tb, *reinterpret_cast<TileScratch*>(Tbuf + ((i + 1) % 3) * t_stride),
+                                 g_lo + (i + 1) * kTileRows, g_hi, pw, lane);
       if (i < n_my) {
         const int b = i & 1;
         double* P = Pbuf + b * p_stride;
         TileScratch& T = *reinterpret_cast<TileScratch*>(Tbuf + (i % 3) * t_stride);
         tile_stage_propose_v3<REPLAY, NPAIR>(a, tb, T, P, pld, pw, kV3ProdWarps, lane);
-        nbar_arrive(BAR_FULL0 + b, kV3Threads);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + b);
       }
       if (i >= 1) {
         const int b2 = (i - 1) & 1;
         const double* P = Pbuf + b2 * p_stride;
         const TileScratch& T = *reinterpret_cast<const TileScratch*>(Tbuf + ((i - 1) % 3) * t_stride);
-        nbar_sync(BAR_DONE0 + b2, kV3Threads);          // consumers decided tile i-1
-        tile_stage_writeback_v3(a, T, P, pld, pw, kV3ProdWarps, lane);
+        mbar_wait(bars + 2 + b2, ((i - 1) >> 1) & 1);   // consumers decided tile i-1
+        warp_stage_writeback(a, T, P, pld, pw, lane);
       }
-      nbar_sync(BAR_PROD, kV3ProdThreads);
     }
   }
 }
