@@ -356,10 +356,11 @@ __global__ void moments_from_history_kernel(const double* __restrict__ hist, int
   if (i >= d) return;
   double mu = 0.0, s2 = 0.0;
   for (int64_t t = 0; t < T; ++t) {
+    // the running update of the generation kernels, row by row: a resumed chain gets the
+    // moments an uninterrupted one would hold, bit for bit (a column that never moved keeps
+    // M2 == 0 exactly, which a two-pass formula does not guarantee)
     const double s = hist[((size_t)t * (hi - lo) + (c - lo)) * ld + i];
-    const double dl = s - mu;
-    mu = mu + dl / (double)(t + 1);
-    s2 += dl * (s - mu);
+    welford_update(s, 1.0 / (double)(t + 1), mu, s2);
   }
   mean[(size_t)(c - lo) * ld + i] = mu;
   m2[(size_t)(c - lo) * ld + i] = s2;

@@ -41,6 +41,18 @@ def _torch():
     return torch
 
 
+def _try_h5py():
+    try:
+        import h5py
+        return h5py if hasattr(h5py, "File") else None
+    except ImportError:
+        return None
+
+
+def _npz_name(h5_file):
+    return h5_file if h5_file.endswith(".npz") else h5_file + ".npz"
+
+
 def shard_bounds(n_chains, size):
     """[lo, hi) of every rank's block = np.array_split(range(N), size) (demc.py:39): the first
     N % size ranks own one extra chain."""
@@ -512,10 +524,13 @@ class DeMcMpi(object):
 
     def _rebuild_moments(self):
         """Running mean / M2 of every local chain from the stored history."""
+        torch = _torch()
         h = self._hist.tensor()
-        self._mean = h.mean(dim=0)
-        self._m2 = ((h - self._mean[None]) ** 2).sum(dim=0)
+        self._mean = torch.zeros_like(h[0])
+        self._m2 = torch.zeros_like(h[0])
         self._mom_len = self._hist.length
+        st = self._state(h.data_ptr())
+        _lib.check(self._libh.bpm_moments_from_history(self._handle, C.byref(st), self._stream()))
 
     # -- streaming diagnostics (no history needed) ------------------------------------
     def reset_moments(self):
@@ -948,31 +963,70 @@ class DeMcMpi(object):
 
     # ------------------------------------------------------------------ checkpoint
     def save_state(self, h5_file=""):
-        """demc.py:198-215: one gzip dataset /chains/chain_id_<id> of shape (T, dim)."""
-        import h5py  # lazy: optional dependency
+        """demc.py:198-215: one gzip dataset /chains/chain_id_<id> of shape (T, dim) per chain.
+        Extension: the sampler state the reference loses on resume -- Philox seed, CR
+        adaptation state -- is stored next to the chains (HDF5 attributes of /chains).
+        Without h5py (it is an optional dependency) or for a name ending in ".npz" the same
+        content goes to a numpy archive."""
         if not h5_file:
             h5_file = self.h5_file
         sc = self._super_chain(0)
+        extra = self._checkpoint_extra()
         if self.comm.rank == 0:
-            with h5py.File(h5_file, "w") as h5f:
-                for c_id in range(self.n_chains):
-                    h5f.create_dataset("/chains/chain_id_" + str(c_id), data=sc[c_id::self.n_chains, :],
-                                       compression="gzip")
+            h5py = None if h5_file.endswith(".npz") else _try_h5py()
+            if h5py is not None:
+                with h5py.File(h5_file, "w") as h5f:
+                    for c_id in range(self.n_chains):
+                        h5f.create_dataset("/chains/chain_id_" + str(c_id), data=sc[c_id::self.n_chains, :],
+                                           compression="gzip")
+                    for k, v in extra.items():
+                        h5f["/chains"].attrs[k] = v
+            else:
+                T = sc.shape[0] // self.n_chains
+                np.savez_compressed(_npz_name(h5_file), history=sc.reshape(T, self.n_chains, self.dim), **extra)
         self.comm.Barrier()
+
+    def _checkpoint_extra(self):
+        return dict(b200_seed=np.uint64(self._seed))
+
+    def _restore_extra(self, extra):
+        if "b200_seed" in extra:
+            self._seed = int(extra["b200_seed"])
 
     def load_state(self, h5_file=""):
         """demc.py:217-233."""
-        import h5py
         if not h5_file:
             h5_file = self.h5_file
-        with h5py.File(h5_file, "r") as h5f:
-            chains = [h5f["/chains/chain_id_" + str(int(c))][:] for c in range(self.n_chains)]
-        k_gen = len(chains[0])
-        for ch in chains:
-            if len(ch) != k_gen:
+        h5py = None if h5_file.endswith(".npz") else _try_h5py()
+        if h5py is not None:
+            with h5py.File(h5_file, "r") as h5f:
+                chains = [h5f["/chains/chain_id_" + str(int(c))][:] for c in range(self.n_chains)]
+                extra = dict((k, np.asarray(v)) for k, v in h5f["/chains"].attrs.items())
+            k_gen = len(chains[0])
+            for ch in chains:
+                if len(ch) != k_gen:
+                    raise RuntimeError
+            hist = np.stack(chains, axis=1)
+        else:
+            with np.load(_npz_name(h5_file)) as z:
+                hist = z["history"]
+                extra = dict((k, z[k]) for k in z.files if k != "history")
+            if hist.shape[1] != self.n_chains:
                 raise RuntimeError
-        self.load_history(np.stack(chains, axis=1))
+        seed_before = self._seed
+        self._restore_extra(extra)
+        if self._seed != seed_before:
+            # the Philox key is part of the engine configuration: rebuild the handle
+            self._release_peer_memory()
+            self._libh.bpm_destroy(self._handle)
+            self._handle = None
+            self._create_handle()
+        self.load_history(hist)
+        self._restore_extra_late(extra)
         self.comm.Barrier()
+
+    def _restore_extra_late(self, extra):
+        pass
 
     def load_history(self, hist):
         """hist: (T, N, dim) array of every chain's history (what load_state reads)."""

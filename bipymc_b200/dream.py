@@ -40,7 +40,9 @@ class DreamMpi(DeMcMpi):
         super(DreamMpi, self).__init__(ln_like_fn, theta_0=theta_0, varepsilon=varepsilon,
                                        n_chains=n_chains, mpi_comm=mpi_comm, ln_kwargs=ln_kwargs,
                                        **kwargs)
-        self._init_cr()
+        self.CR = (np.array(range(self.n_cr)) + 1) / self.n_cr
+        if not getattr(self, "_cr_restored", False):            # a warm start restored it already
+            self._init_cr()
 
     def _dream_cfg(self):
         return dict(del_pairs=int(self.del_pairs), n_cr=int(self.n_cr), burnin_gen=int(self.burnin_gen),
@@ -91,6 +93,17 @@ class DreamMpi(DeMcMpi):
     @property
     def p_cr_update(self):
         return self.p_cr
+
+    def _checkpoint_extra(self):
+        e = super(DreamMpi, self)._checkpoint_extra()
+        p_cr, dm, cnt = self._get_cr()
+        e.update(b200_p_cr=p_cr, b200_delta_m=dm, b200_n_cr_updates=cnt)
+        return e
+
+    def _restore_extra_late(self, extra):
+        if "b200_p_cr" in extra:
+            self._set_cr(extra["b200_p_cr"], extra["b200_delta_m"], extra["b200_n_cr_updates"])
+            self._cr_restored = True
 
     def _outlier_active(self, k_gen):
         return self.outlier_gen > 0 and k_gen < self.burnin_gen

@@ -132,6 +132,14 @@ class BimodeGauss_2D(object):
 
     def ln_like(self, y):
         assert len(y) == 2
+        if not self.log_of_pdf:
+            # direct log-density (log-sum-exp): finite far from both modes, where the
+            # reference's np.log(pdf) underflows to -inf
+            pos = np.asarray(y, dtype=float)
+            a = self.rv_2d_g1.logpdf(pos) + np.log(self.w_g1)
+            b = self.rv_2d_g2.logpdf(pos) + np.log(self.w_g2)
+            m = max(a, b)
+            return m + np.log(np.exp(a - m) + np.exp(b - m))
         with np.errstate(divide="ignore"):
             return np.log(self.pdf(y[0], y[1]))
 

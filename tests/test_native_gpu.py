@@ -263,3 +263,80 @@ def test_full_size_properties_1e5_chains_100d():
     # rejected chain is bit-identical to its previous row (no partial writes)
     same = (ha[1:] == ha[:-1]).all(dim=2)
     assert int(same.sum().item()) == N * G - a.n_accepted
+
+
+# ---------------------------------------------------------------- the other BASELINE configs
+def test_config5_shape_1000d_gauss_matches_oracle_replay():
+    """configs[4] at a size the oracle finishes: DREAM on the 1000-D correlated Gaussian with
+    the direct log-density (the reference's log(pdf) underflows there, SURVEY.md section 0);
+    generic split path (d > 112), native Philox draws replayed by the oracle."""
+    from bipymc_b200 import DreamMpi, targets
+    np.random.seed(11)
+    dim, n = 1000, 12
+    tgt = targets.Gauss_100D(dim=dim)
+    assert tgt.log_of_pdf is False
+    s = DreamMpi(tgt.ln_like, np.zeros(dim), n_chains=n, n_cr_gen=2, burnin_gen=1000, seed=5, varepsilon=0.5)
+    _native_vs_oracle(s, otargets.GaussND(dim=dim, use_logpdf=True).ln_like, gens=4, k0=4)
+
+
+def test_config3_bimodal_1e6_chains_outlier_reset_and_cr_adaptation():
+    """configs[2] at full size: DREAM on the bimodal Gaussian with 10^6 chains, CR adaptation
+    and the IQR outlier reset ON.  Size-independent properties: counters add up, cached
+    likelihoods equal a fresh evaluation, p_cr is a distribution that moved off uniform, the
+    population mean reaches the reference's gate (tests/test_dblgauss.py:67-69) and the two modes carry their
+    weights (0.25 / 0.75)."""
+    import torch
+    from bipymc_b200 import DreamMpi, targets
+    tgt = targets.BimodeGauss_2D(log_of_pdf=False)      # log-sum-exp: finite in the far tails
+    N = 1000000
+    np.random.seed(1)
+    s = DreamMpi(tgt.ln_like, [0.0, 0.0], n_chains=N, seed=17, varepsilon=1.0, history="none",
+                 burnin_gen=150, n_cr_gen=20, outlier_gen=50)
+    G1 = 150
+    s.run_mcmc(N * (G1 + 1))
+    assert s.n_accepted + s.n_rejected == N * G1 + 1
+    p = s.p_cr
+    assert abs(p.sum() - 1.0) < 1e-12 and np.all(p > 0) and np.abs(p - 1.0 / 3).max() > 1e-3
+    assert np.all(s.n_cr_updates > 0)
+    assert s.last_outlier_stats["threshold"] < s.last_outlier_stats["q1"]
+    s.reset_moments()
+    G2 = 200
+    s.run_mcmc(N * (G2 + 1), _k_gen0=G1)
+    fresh = s._eval_lnl_rows(s._X)
+    assert torch.equal(fresh, s._lnl)
+    mean, std = s.moment_estimates()
+    assert abs(mean[0] - 1.5) < 0.1 and abs(mean[1] - 1.5) < 0.1, mean
+    # each chain saw only 200 post-burn-in rows of a bimodal target: the per-chain means
+    # differ (chains sit in one mode), so R-hat is a mixing statement, not < 1.01 here;
+    # the population statistic that must hold is the mode weight (0.25 / 0.75)
+    frac_hi = float((s._X[:, 0] + s._X[:, 1] > 2.0).double().mean().item())
+    assert abs(frac_hi - 0.75) < 0.03, frac_hi
+    assert 0.05 < s.acceptance_fraction < 0.7
+
+
+def test_checkpoint_roundtrip_resumes_the_same_chains(tmp_path):
+    """save_state / load_state / warm_start (demc.py:198-233, demc.py:46-51): chains restored
+    bit for bit, and -- the extension over the reference -- the Philox seed and CR adaptation
+    state travel with them, so a resumed run continues exactly like an uninterrupted one."""
+    from bipymc_b200 import DreamMpi, targets
+    tgt = targets.Banana_2D()
+    f = str(tmp_path / "ckpt.h5")
+    kw = dict(n_chains=24, n_cr_gen=3, burnin_gen=1000, varepsilon=0.3)
+    np.random.seed(4)
+    a = DreamMpi(tgt.ln_like, [0.0, 0.0], seed=31, **kw)
+    a.run_mcmc(24 * 11)
+    a.save_state(f)
+    a.run_mcmc(24 * 6)
+    np.random.seed(99)
+    b = DreamMpi(tgt.ln_like, [0.0, 0.0], warm_start=True, h5_file=f, **kw)      # no seed given
+    assert b._seed == 31
+    assert b.am_chains[3].chain_len == 11
+    np.testing.assert_array_equal(b.am_chains[3].chain, a.am_chains[3].chain[:11])
+    b.run_mcmc(24 * 6)
+    np.testing.assert_array_equal(b.super_chain, a.super_chain)
+    np.testing.assert_allclose(b.p_cr, a.p_cr, rtol=1e-13)
+    assert np.array_equal(b.n_cr_updates, a.n_cr_updates)
+    # ragged / foreign files are rejected like the reference does (bare RuntimeError, demc.py:232)
+    c = DreamMpi(tgt.ln_like, [0.0, 0.0], seed=1, n_chains=25)
+    with pytest.raises(RuntimeError):
+        c.load_state(f)
