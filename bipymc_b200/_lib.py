@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbipymc_b200.so")
+# BIPYMC_B200_LIB: alternative build of the same library (A/B experiments of kernel variants)
+LIB_PATH = os.environ.get("BIPYMC_B200_LIB") or os.path.join(_HERE, "lib", "libbipymc_b200.so")
 
 BPM_ALGO_DEMC, BPM_ALGO_DREAM = 0, 1
 TARGET_EXTERNAL, TARGET_BANANA, TARGET_BIMODAL, TARGET_GAUSS, TARGET_LINEFIT = 0, 1, 2, 3, 4

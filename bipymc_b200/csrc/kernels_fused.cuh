@@ -821,13 +821,22 @@ constexpr int kV3Threads = 32 * (kV3ConsWarps + kV3ProdWarps);   // 640
 constexpr int kV3ProdThreads = 32 * kV3ProdWarps;
 constexpr int kV3ConsThreads = 32 * kV3ConsWarps;
 
+#ifdef BPM_GATHER_CG
+__device__ __forceinline__ double2 ldg2(const double* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
+#else
 __device__ __forceinline__ double2 ldg2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+#endif
 
 // NPAIR: 3 = DREAM with del_pairs == 3 (the reference default), 0 = read algo / del_pairs at run time
-template <bool REPLAY, int NPAIR>
+struct NoMid {
+  __device__ __forceinline__ void operator()(int) const {}
+};
+// `mid(row)` runs once per tile row between the issue of that row's gathers and their first
+// use: independent work (the write-back of the previous tile's row) placed in the memory shadow.
+template <bool REPLAY, int NPAIR, typename Mid = NoMid>
 __device__ __forceinline__ void tile_stage_propose_v3(const PhaseArgs& a, const GaussTables& tb,
                                                       TileScratch& T, double* __restrict__ P, int pld,
-                                                      int gwarp, int gwarps, int lane) {
+                                                      int gwarp, int gwarps, int lane, Mid mid = Mid()) {
   const int d = a.d;
   const bool dream = NPAIR == 3 ? true : a.algo == BPM_ALGO_DREAM;
   const int npair = NPAIR == 3 ? 3 : (dream ? a.del_pairs : 1);
@@ -842,21 +851,20 @@ __device__ __forceinline__ void tile_stage_propose_v3(const PhaseArgs& a, const 
         *reinterpret_cast<double2*>(prow) = make_double2(0.0, 0.0);
         *reinterpret_cast<double2*>(prow + 2) = make_double2(0.0, 0.0);
       }
+      mid(row);
       continue;
     }
     double cur[4] = {0, 0, 0, 0}, S[4] = {0, 0, 0, 0}, var[4] = {0, 0, 0, 0};
+    double2 u0, u1, w0, w1, va[3][2], vb[3][2];
     if (act) {
       // every row gather of this chain is issued before anything consumes one
       const double* xc = a.X + (size_t)c * a.ld + 4 * lane;
-      const double2 u0 = ldg2(xc), u1 = ldg2(xc + 2);
+      u0 = ldg2(xc); u1 = ldg2(xc + 2);
       if (welford_var) {
         const double* mp = a.m2 + (size_t)(c - a.chain_lo) * a.ld + 4 * lane;
-        const double2 w0 = ldg2(mp), w1 = ldg2(mp + 2);      // kept in L2: the write-back re-reads it
-        var[0] = w0.x; var[1] = w0.y; var[2] = w1.x; var[3] = w1.y;
+        w0 = ldg2(mp); w1 = ldg2(mp + 2);                    // kept in L2: the write-back re-reads it
       }
-      cur[0] = u0.x; cur[1] = u0.y; cur[2] = u1.x; cur[3] = u1.y;
       if constexpr (NPAIR == 3) {
-        double2 va[3][2], vb[3][2];
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
           const double* pa = a.X + (size_t)T.pa[row][p] * a.ld + 4 * lane;
@@ -864,6 +872,13 @@ __device__ __forceinline__ void tile_stage_propose_v3(const PhaseArgs& a, const 
           va[p][0] = ldg2(pa); va[p][1] = ldg2(pa + 2);
           vb[p][0] = ldg2(pb); vb[p][1] = ldg2(pb + 2);
         }
+      }
+    }
+    mid(row);
+    if (act) {
+      if (welford_var) { var[0] = w0.x; var[1] = w0.y; var[2] = w1.x; var[3] = w1.y; }
+      cur[0] = u0.x; cur[1] = u0.y; cur[2] = u1.x; cur[3] = u1.y;
+      if constexpr (NPAIR == 3) {
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
           const double df0 = __dsub_rn(va[p][0].x, vb[p][0].x), df1 = __dsub_rn(va[p][0].y, vb[p][0].y);
@@ -1021,6 +1036,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
   }
 }
 
+// Measured (profiles/r1_ab_prefetch.txt): with 16 independent producer warps the L2 bulk
+// prefetch one tile ahead no longer pays -- the kernel is 9 % faster without it.
+#ifndef BPM_PF_MODE
+#define BPM_PF_MODE 0     // 0 none, 1 population + moments rows, 2 moments rows only, 3 population rows only
+#endif
+__device__ __forceinline__ void v3_prefetch_x(const double* p, int bytes) {
+  if (BPM_PF_MODE == 1 || BPM_PF_MODE == 3) l2_prefetch_row(p, bytes);
+}
+__device__ __forceinline__ void v3_prefetch_mom(const double* p, int bytes) {
+  if (BPM_PF_MODE == 1 || BPM_PF_MODE == 2) l2_prefetch_row(p, bytes);
+}
+
 // Per-warp scalar draws: producer warp pw owns tile rows pw, pw + 16, pw + 32, pw + 48 from the
 // draws to the write-back, so the scratch of a row is written and read by one warp only (plus
 // the consumers, ordered by the FULL mbarrier).  gid0 = population-list index of tile row 0,
@@ -1044,10 +1071,10 @@ __device__ __forceinline__ void warp_stage_draws(const PhaseArgs& a, const Phase
     if (!valid) continue;
     const int row_bytes = a.ld * 8;
     if (slot == 0) {
-      l2_prefetch_row(a.X + (size_t)c * a.ld, row_bytes);
-      if (a.mean) l2_prefetch_row(a.mean + (size_t)(c - a.chain_lo) * a.ld, row_bytes);
+      v3_prefetch_x(a.X + (size_t)c * a.ld, row_bytes);
+      if (a.mean) v3_prefetch_mom(a.mean + (size_t)(c - a.chain_lo) * a.ld, row_bytes);
     } else if (slot == 1) {
-      if (a.m2) l2_prefetch_row(a.m2 + (size_t)(c - a.chain_lo) * a.ld, row_bytes);
+      if (a.m2) v3_prefetch_mom(a.m2 + (size_t)(c - a.chain_lo) * a.ld, row_bytes);
     }
     if (REPLAY) {
       if (slot == 0) {
@@ -1060,8 +1087,8 @@ __device__ __forceinline__ void warp_stage_draws(const PhaseArgs& a, const Phase
         const int p = slot - 2;
         T.pa[row][p] = L.pool[a.rp.pairs[((size_t)c * npair + p) * 2 + 0]];
         T.pb[row][p] = L.pool[a.rp.pairs[((size_t)c * npair + p) * 2 + 1]];
-        l2_prefetch_row(a.X + (size_t)T.pa[row][p] * a.ld, row_bytes);
-        l2_prefetch_row(a.X + (size_t)T.pb[row][p] * a.ld, row_bytes);
+        v3_prefetch_x(a.X + (size_t)T.pa[row][p] * a.ld, row_bytes);
+        v3_prefetch_x(a.X + (size_t)T.pb[row][p] * a.ld, row_bytes);
       }
     } else {
       const Philox4 q = draw4(a.rng, (uint32_t)c, RNG_SCALAR, (uint32_t)slot);
@@ -1084,8 +1111,8 @@ __device__ __forceinline__ void warp_stage_draws(const PhaseArgs& a, const Phase
         const int ga = L.pool[r1], gb = L.pool[r2];
         T.pa[row][slot - 2] = ga;
         T.pb[row][slot - 2] = gb;
-        l2_prefetch_row(a.X + (size_t)ga * a.ld, row_bytes);
-        l2_prefetch_row(a.X + (size_t)gb * a.ld, row_bytes);
+        v3_prefetch_x(a.X + (size_t)ga * a.ld, row_bytes);
+        v3_prefetch_x(a.X + (size_t)gb * a.ld, row_bytes);
       }
     }
   }
@@ -1212,7 +1239,9 @@ fused_gauss_v3_kernel(const PhaseArgs a, const GaussArgs g) {
 
   if (warp < kV3ConsWarps) {
     // ------------------------------ consumers ------------------------------------------
+#ifndef BPM_V3_EQUAL_REGS
     asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+#endif
     unsigned n_acc = 0, n_rej = 0;
     for (int i = 0; i < n_my; ++i) {
       const int b = i & 1;
@@ -1235,7 +1264,9 @@ fused_gauss_v3_kernel(const PhaseArgs a, const GaussArgs g) {
     // ------------------------------ producers ------------------------------------------
     // each warp is an independent pipeline over ITS rows: draws + L2 prefetch of tile i+1 |
     // proposal of tile i | write-back of tile i-1; it synchronises only with the consumers
+#ifndef BPM_V3_EQUAL_REGS
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+#endif
     const int pw = warp - kV3ConsWarps;
     if (n_my > 0)
       warp_stage_draws<REPLAY>(a, L, tb, *reinterpret_cast<TileScratch*>(Tbuf), g_lo, g_hi, pw, lane);
