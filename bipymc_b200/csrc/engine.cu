@@ -53,6 +53,10 @@ struct bpm_engine {
   // workspace (device)
   int32_t* perm = nullptr;
   int32_t* flip = nullptr;
+  int32_t* loc_list = nullptr;   // sharded: local chains of both halves, compacted (kernels_generic.cuh)
+  int32_t* loc_cnt = nullptr;    // [2]
+  int32_t* cmp_blk = nullptr;    // [2][nblk][2] block counts / offsets
+  bool sharded() const { return cfg.chain_lo != 0 || cfg.chain_hi != cfg.n_chains; }
   double* prop = nullptr;
   double* lnl_prop = nullptr;
   double* cr_delta = nullptr;
@@ -119,6 +123,7 @@ struct bpm_engine {
   }
 
   ~bpm_engine() {
+    cudaFree(loc_list); cudaFree(loc_cnt); cudaFree(cmp_blk);
     cudaFree(perm); cudaFree(flip); cudaFree(prop); cudaFree(lnl_prop); cudaFree(cr_delta);
     cudaFree(cr_pick); cudaFree(p_cr); cudaFree(cr_dm); cudaFree(cr_cnt); cudaFree(cr_part); cudaFree(cr_block);
     cudaFree(counters); cudaFree(nan_flag); cudaFree(tparams); cudaFree(hX); cudaFree(hL);
@@ -134,6 +139,12 @@ struct bpm_engine {
     CU_TRY(cudaSetDevice(cfg.device));
     CU_TRY(cudaMalloc(&perm, sizeof(int32_t) * N));
     CU_TRY(cudaMalloc(&flip, sizeof(int32_t)));
+    if (sharded()) {
+      const int nblk = cdiv(N, bpm::kCompactBlock);
+      CU_TRY(cudaMalloc(&loc_list, sizeof(int32_t) * N));
+      CU_TRY(cudaMalloc(&loc_cnt, sizeof(int32_t) * 2));
+      CU_TRY(cudaMalloc(&cmp_blk, sizeof(int32_t) * 4 * nblk));
+    }
     CU_TRY(cudaMalloc(&prop, sizeof(double) * (size_t)nA * cfg.ld));
     CU_TRY(cudaMalloc(&lnl_prop, sizeof(double) * nA));
     CU_TRY(cudaMalloc(&cr_delta, sizeof(double) * N));
@@ -168,6 +179,7 @@ struct bpm_engine {
     a.hist_row = st->history ? st->history + (size_t)st->hist_len * (cfg.chain_hi - cfg.chain_lo) * cfg.ld
                              : nullptr;
     a.perm = perm; a.flip = flip; a.phase = phase;
+    a.loc_list = loc_list; a.loc_cnt = loc_cnt;     // both nullptr on an unsharded handle
     a.N = cfg.n_chains; a.nA = nA; a.d = cfg.dim; a.ld = cfg.ld;
     a.chain_lo = cfg.chain_lo; a.chain_hi = cfg.chain_hi;
     a.algo = cfg.algo;
@@ -210,6 +222,14 @@ struct bpm_engine {
     } else {
       bpm::RngCtx rng = bpm::make_rng(cfg.seed, (uint64_t)st->hist_len);
       bpm::split_native_kernel<<<cdiv(N, 256), 256, 0, s>>>(perm, flip, N, cfg.shuffle, cfg.flip, rng);
+    }
+    if (sharded()) {
+      const int nblk = cdiv(N, bpm::kCompactBlock);
+      bpm::compact_count_kernel<<<nblk, bpm::kCompactThreads, 0, s>>>(perm, N, nA, cfg.chain_lo, cfg.chain_hi,
+                                                                     cmp_blk);
+      bpm::compact_scan_kernel<<<1, 1024, 0, s>>>(cmp_blk, nblk, cmp_blk + 2 * nblk, loc_cnt);
+      bpm::compact_write_kernel<<<nblk, bpm::kCompactThreads, 0, s>>>(perm, N, nA, cfg.chain_lo, cfg.chain_hi,
+                                                                     cmp_blk + 2 * nblk, loc_list);
     }
     prof_end(s);
     CU_TRY(cudaGetLastError());
@@ -611,6 +631,11 @@ int bpm_propose(bpm_handle h, bpm_state* st, int32_t phase, double** prop, int32
     CU_TRY(cudaMemcpy(&f, h->flip, sizeof(f), cudaMemcpyDeviceToHost));
     const bool first = ((phase ^ (f != 0)) == 0);
     *n_phase = first ? h->nA : h->cfg.n_chains - h->nA;
+    if (h->sharded()) {   // only this rank's chains of the half were proposed, densely packed
+      int32_t cnt[2];
+      CU_TRY(cudaMemcpy(cnt, h->loc_cnt, sizeof(cnt), cudaMemcpyDeviceToHost));
+      *n_phase = cnt[first ? 0 : 1];
+    }
   }
   return 0;
 }

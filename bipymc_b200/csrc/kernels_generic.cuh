@@ -35,6 +35,106 @@ __global__ void split_native_kernel(int32_t* __restrict__ perm, int32_t* __restr
 
 __global__ void set_flag_kernel(int32_t* flag, int32_t v) { *flag = v; }
 
+// ---- sharded ranks: ordered compaction of the chains this rank owns -----------------
+// A rank steps only its own chains (demc.py:103-107 loops over the local ids and tests
+// `c_id in a_ids`).  Walking the global half-lists and skipping foreign chains would leave
+// every 64-chain tile 1/G full on G GPUs, so each generation the local members of the two
+// halves are packed (in list order, deterministically) into loc_list with three small
+// kernels: per-block counts, a one-block scan of the block counts, per-block write.
+constexpr int kCompactThreads = 256, kCompactPer = 8, kCompactBlock = kCompactThreads * kCompactPer;
+// exclusive prefix sums of (xa, xb) over the threads of a block (NT <= 1024), warp shuffles + one smem hop
+template <int NT>
+__device__ __forceinline__ void block_excl_scan2(int xa, int xb, int& ea, int& eb, int& tota, int& totb) {
+  __shared__ int wa[NT / 32], wb[NT / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int ia = xa, ib = xb;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int ya = __shfl_up_sync(0xFFFFFFFFu, ia, o), yb = __shfl_up_sync(0xFFFFFFFFu, ib, o);
+    if (lane >= o) { ia += ya; ib += yb; }
+  }
+  if (lane == 31) { wa[w] = ia; wb[w] = ib; }
+  __syncthreads();
+  if (w == 0) {
+    int va = lane < NT / 32 ? wa[lane] : 0, vb = lane < NT / 32 ? wb[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int ya = __shfl_up_sync(0xFFFFFFFFu, va, o), yb = __shfl_up_sync(0xFFFFFFFFu, vb, o);
+      if (lane >= o) { va += ya; vb += yb; }
+    }
+    if (lane < NT / 32) { wa[lane] = va; wb[lane] = vb; }     // inclusive over warps
+  }
+  __syncthreads();
+  ea = ia - xa + (w > 0 ? wa[w - 1] : 0);
+  eb = ib - xb + (w > 0 ? wb[w - 1] : 0);
+  tota = wa[NT / 32 - 1];
+  totb = wb[NT / 32 - 1];
+}
+__device__ __forceinline__ void compact_flags(const int32_t* __restrict__ perm, int N, int nA, int lo, int hi,
+                                              int j0, int& cA, int& cB, unsigned& mA, unsigned& mB) {
+  cA = cB = 0; mA = mB = 0u;
+#pragma unroll
+  for (int k = 0; k < kCompactPer; ++k) {
+    const int j = j0 + k;
+    if (j < N) {
+      const int c = perm[j];
+      if (c >= lo && c < hi) {
+        if (j < nA) { ++cA; mA |= 1u << k; } else { ++cB; mB |= 1u << k; }
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(kCompactThreads) compact_count_kernel(const int32_t* __restrict__ perm, int N,
+                                                                        int nA, int lo, int hi,
+                                                                        int32_t* __restrict__ blk_cnt) {
+  __shared__ int sa[kCompactThreads / 32], sb[kCompactThreads / 32];
+  int cA, cB; unsigned mA, mB;
+  compact_flags(perm, N, nA, lo, hi, blockIdx.x * kCompactBlock + threadIdx.x * kCompactPer, cA, cB, mA, mB);
+  cA = __reduce_add_sync(0xFFFFFFFFu, cA);
+  cB = __reduce_add_sync(0xFFFFFFFFu, cB);
+  if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = cA; sb[threadIdx.x >> 5] = cB; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int ta = 0, tb = 0;
+    for (int w = 0; w < kCompactThreads / 32; ++w) { ta += sa[w]; tb += sb[w]; }
+    blk_cnt[2 * blockIdx.x] = ta;
+    blk_cnt[2 * blockIdx.x + 1] = tb;
+  }
+}
+// exclusive scan of the block counts (one block; thread t owns a contiguous run of blocks)
+__global__ void __launch_bounds__(1024) compact_scan_kernel(const int32_t* __restrict__ blk_cnt, int nblk,
+                                                            int32_t* __restrict__ blk_off,
+                                                            int32_t* __restrict__ tot) {
+  const int per = (nblk + 1023) / 1024;
+  const int b0 = threadIdx.x * per, b1 = min(nblk, b0 + per);
+  int ta = 0, tb = 0;
+  for (int b = b0; b < b1; ++b) { ta += blk_cnt[2 * b]; tb += blk_cnt[2 * b + 1]; }
+  int ra, rb, alla, allb;
+  block_excl_scan2<1024>(ta, tb, ra, rb, alla, allb);
+  if (threadIdx.x == 0) { tot[0] = alla; tot[1] = allb; }
+  for (int b = b0; b < b1; ++b) {
+    blk_off[2 * b] = ra; blk_off[2 * b + 1] = rb;
+    ra += blk_cnt[2 * b]; rb += blk_cnt[2 * b + 1];
+  }
+}
+__global__ void __launch_bounds__(kCompactThreads) compact_write_kernel(const int32_t* __restrict__ perm, int N,
+                                                                        int nA, int lo, int hi,
+                                                                        const int32_t* __restrict__ blk_off,
+                                                                        int32_t* __restrict__ loc_list) {
+  const int j0 = blockIdx.x * kCompactBlock + threadIdx.x * kCompactPer;
+  int cA, cB; unsigned mA, mB;
+  compact_flags(perm, N, nA, lo, hi, j0, cA, cB, mA, mB);
+  int ea, eb, ta, tb;
+  block_excl_scan2<kCompactThreads>(cA, cB, ea, eb, ta, tb);
+  int oa = blk_off[2 * blockIdx.x] + ea;
+  int ob = nA + blk_off[2 * blockIdx.x + 1] + eb;
+#pragma unroll
+  for (int k = 0; k < kCompactPer; ++k) {
+    if (mA & (1u << k)) loc_list[oa++] = perm[j0 + k];
+    if (mB & (1u << k)) loc_list[ob++] = perm[j0 + k];
+  }
+}
+
 // ---- proposal ---------------------------------------------------------------------
 template <bool REPLAY, int LPC>
 __global__ void __launch_bounds__(kThreads) propose_kernel(const PhaseArgs a) {

@@ -22,6 +22,10 @@ struct PhaseArgs {
   // phase lists: perm[0:nA) is half "a", perm[nA:N) half "b" before the flip swap
   const int32_t* perm;
   const int32_t* flip;  // device flag (demc.py:81,98-100)
+  // sharded handles: this rank's chains of each half, compacted in list order into
+  // loc_list[0 : loc_cnt[0]) and loc_list[nA : nA + loc_cnt[1]); nullptr when the rank owns all chains
+  const int32_t* loc_list;
+  const int32_t* loc_cnt;
   int32_t phase;        // 0: update a from frozen b; 1: update b from updated a
   int32_t N, nA, d, ld;
   int32_t chain_lo, chain_hi;
@@ -86,6 +90,10 @@ __device__ __forceinline__ PhaseLists phase_lists(const PhaseArgs& a) {
     L.self = a.perm; L.n_self = a.nA; L.pool = a.perm + a.nA; L.n_pool = a.N - a.nA;
   } else {
     L.self = a.perm + a.nA; L.n_self = a.N - a.nA; L.pool = a.perm; L.n_pool = a.nA;
+  }
+  if (a.loc_cnt) {   // only the local chains of the half, densely packed
+    L.self = a.loc_list + (first ? 0 : a.nA);
+    L.n_self = a.loc_cnt[first ? 0 : 1];
   }
   return L;
 }
