@@ -238,7 +238,9 @@ def run_ours(args):
         if kinds[dom] == "likelihood":
             fl = 2.0 * d * d * chains_per_launch / (avg_ms * 1e-3) / 1e12
             roof.update({"fp64_tflops": fl})
-    launches = sum(n_k) + n_k[5]          # cr_reduce records cover 2 kernels (reduce + apply)
+    # kernels launched in the timed region: one per record, plus the three list-compaction
+    # kernels that ride in the "split" record of a sharded generation
+    launches = sum(n_k) + (3 * n_k[0] if world > 1 else 0)
 
     # ---- end to end through the C-ABI with HOST buffers (rank-local population) --------
     e2e = None

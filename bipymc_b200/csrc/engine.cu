@@ -66,6 +66,7 @@ struct bpm_engine {
   double* cr_cnt = nullptr;
   double* cr_part = nullptr;
   double* cr_block = nullptr;
+  unsigned int* cr_ticket = nullptr;
   unsigned long long* counters = nullptr;  // [0] accepted, [1] rejected
   int32_t* nan_flag = nullptr;
   // target
@@ -123,7 +124,7 @@ struct bpm_engine {
   }
 
   ~bpm_engine() {
-    cudaFree(loc_list); cudaFree(loc_cnt); cudaFree(cmp_blk);
+    cudaFree(loc_list); cudaFree(loc_cnt); cudaFree(cmp_blk); cudaFree(cr_ticket);
     cudaFree(perm); cudaFree(flip); cudaFree(prop); cudaFree(lnl_prop); cudaFree(cr_delta);
     cudaFree(cr_pick); cudaFree(p_cr); cudaFree(cr_dm); cudaFree(cr_cnt); cudaFree(cr_part); cudaFree(cr_block);
     cudaFree(counters); cudaFree(nan_flag); cudaFree(tparams); cudaFree(hX); cudaFree(hL);
@@ -154,6 +155,8 @@ struct bpm_engine {
     CU_TRY(cudaMalloc(&cr_cnt, sizeof(double) * BPM_MAX_CR));
     CU_TRY(cudaMalloc(&cr_part, sizeof(double) * 2 * BPM_MAX_CR));
     CU_TRY(cudaMalloc(&cr_block, sizeof(double) * 2 * BPM_MAX_CR * bpm::kCrBlocks));
+    CU_TRY(cudaMalloc(&cr_ticket, sizeof(unsigned int)));
+    CU_TRY(cudaMemset(cr_ticket, 0, sizeof(unsigned int)));
     CU_TRY(cudaMalloc(&counters, sizeof(unsigned long long) * 2));
     CU_TRY(cudaMalloc(&nan_flag, sizeof(int32_t)));
     CU_TRY(cudaMemset(flip, 0, sizeof(int32_t)));
@@ -320,15 +323,10 @@ struct bpm_engine {
     const int nloc = cfg.chain_hi - cfg.chain_lo;
     int nb = cdiv(nloc, 2048);
     if (nb > bpm::kCrBlocks) nb = bpm::kCrBlocks;
-    bpm::cr_reduce_kernel<<<nb, 256, 0, s>>>(cr_delta, cr_pick, cfg.chain_lo, cfg.chain_hi, cfg.n_cr,
-                                             cr_block);
-    bpm::cr_finish_kernel<<<1, 32, 0, s>>>(cr_block, nb, cfg.n_cr, cr_part);
+    // multi-rank hosts all-reduce cr_part first, then call bpm_apply_cr
+    bpm::cr_update_kernel<<<nb, 256, 0, s>>>(cr_delta, cr_pick, cfg.chain_lo, cfg.chain_hi, cfg.n_cr, cr_block,
+                                             cr_ticket, cr_part, sharded() ? 0 : 1, cr_dm, cr_cnt, p_cr);
     CU_TRY(cudaGetLastError());
-    const bool sharded = cfg.chain_lo != 0 || cfg.chain_hi != cfg.n_chains;
-    if (!sharded) {  // multi-rank hosts all-reduce cr_part first, then call bpm_apply_cr
-      bpm::cr_apply_kernel<<<1, 32, 0, s>>>(cr_part, cfg.n_cr, cr_dm, cr_cnt, p_cr);
-      CU_TRY(cudaGetLastError());
-    }
     prof_end(s);
     return 0;
   }

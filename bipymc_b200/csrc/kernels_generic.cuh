@@ -387,12 +387,37 @@ __global__ void __launch_bounds__(256) lnl_gauss_tiled_kernel(const double* __re
 // Stage 1: block b sums the chains of its contiguous segment (fixed order inside the
 // block); stage 2: one warp adds the block partials in block order.
 constexpr int kCrBlocks = 148;
-__global__ void __launch_bounds__(256) cr_reduce_kernel(const double* __restrict__ cr_delta,
-                                                        const int32_t* __restrict__ cr_pick, int lo,
-                                                        int hi, int n_cr,
-                                                        double* __restrict__ block_part) {
-  // block_part[b][0:n_cr) = sum of jump statistics per CR value, [n_cr:2n_cr) = counts
+// Second half of the reduction, run by whichever block finishes last (ticket counter): adds
+// the block partials in block order -- so the sums do not depend on scheduling -- and, on an
+// unsharded handle, applies the p_cr update (dream.py:132-140).  One launch per generation
+// instead of three.
+__device__ __forceinline__ void cr_apply(const double* __restrict__ part, int n_cr, double* __restrict__ dm,
+                                         double* __restrict__ cnt, double* __restrict__ p_cr) {
+  double got = 0.0;
+  for (int m = 0; m < n_cr; ++m) {
+    dm[m] += part[m];
+    cnt[m] += part[n_cr + m];
+    got += part[n_cr + m];
+  }
+  if (got == 0.0) return;  // no chain ran _update_cr_ratios this generation
+  int nz = 0;
+  for (int m = 0; m < n_cr; ++m) nz += cnt[m] > 0.0;
+  if (nz == n_cr)
+    for (int m = 0; m < n_cr; ++m) p_cr[m] = dm[m] / cnt[m];
+  double tot = 0.0;
+  for (int m = 0; m < n_cr; ++m) tot += p_cr[m];
+  for (int m = 0; m < n_cr; ++m) p_cr[m] /= tot;
+}
+
+__global__ void __launch_bounds__(256) cr_update_kernel(const double* __restrict__ cr_delta,
+                                                        const int32_t* __restrict__ cr_pick, int lo, int hi,
+                                                        int n_cr, double* __restrict__ block_part,
+                                                        unsigned int* __restrict__ ticket,
+                                                        double* __restrict__ part, int apply,
+                                                        double* __restrict__ dm, double* __restrict__ cnt,
+                                                        double* __restrict__ p_cr) {
   __shared__ double sm[8];
+  __shared__ bool last;
   const int n = hi - lo;
   const int per = (n + gridDim.x - 1) / gridDim.x;
   const int c0 = lo + blockIdx.x * per;
@@ -415,34 +440,42 @@ __global__ void __launch_bounds__(256) cr_reduce_kernel(const double* __restrict
       __syncthreads();
     }
   }
-}
-
-__global__ void cr_finish_kernel(const double* __restrict__ block_part, int nb, int n_cr,
-                                 double* __restrict__ part) {
-  const int i = threadIdx.x;
-  if (i >= 2 * n_cr) return;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // all block partials land in shared memory with independent loads, then each of the 2 n_cr
+  // outputs is added up in block order
+  __shared__ double stage[kCrBlocks * 2 * BPM_MAX_CR / 4];    // gridDim.x <= 148 blocks x 2 n_cr <= 8 values (n_cr <= 4) or fewer blocks
+  const int nv = 2 * n_cr;
+  const int fit = (int)(sizeof(stage) / sizeof(double)) / nv;      // blocks that fit in the stage
   double w = 0.0;
-  for (int b = 0; b < nb; ++b) w += block_part[(size_t)b * 2 * BPM_MAX_CR + i];
-  part[i] = w;
+  for (unsigned b0 = 0; b0 < gridDim.x; b0 += fit) {
+    const int nb_here = min((int)(gridDim.x - b0), fit);
+    for (int idx = threadIdx.x; idx < nb_here * nv; idx += blockDim.x) {
+      const int b = idx / nv, i = idx - b * nv;
+      stage[idx] = __ldcg(&block_part[(size_t)(b0 + b) * 2 * BPM_MAX_CR + i]);
+    }
+    __syncthreads();
+    if (threadIdx.x < nv)
+      for (int b = 0; b < nb_here; ++b) w += stage[b * nv + threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x < nv) part[threadIdx.x] = w;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *ticket = 0u;                        // ready for the next generation
+    if (apply) cr_apply(part, n_cr, dm, cnt, p_cr);
+  }
 }
 
 __global__ void cr_apply_kernel(const double* __restrict__ part, int n_cr, double* __restrict__ dm,
                                 double* __restrict__ cnt, double* __restrict__ p_cr) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double got = 0.0;
-  for (int m = 0; m < n_cr; ++m) {
-    dm[m] += part[m];
-    cnt[m] += part[n_cr + m];
-    got += part[n_cr + m];
-  }
-  if (got == 0.0) return;  // no chain ran _update_cr_ratios this generation
-  int nz = 0;
-  for (int m = 0; m < n_cr; ++m) nz += cnt[m] > 0.0;
-  if (nz == n_cr)
-    for (int m = 0; m < n_cr; ++m) p_cr[m] = dm[m] / cnt[m];
-  double tot = 0.0;
-  for (int m = 0; m < n_cr; ++m) tot += p_cr[m];
-  for (int m = 0; m < n_cr; ++m) p_cr[m] /= tot;
+  cr_apply(part, n_cr, dm, cnt, p_cr);
 }
 
 // ---- moments rebuilt from a stored history (load_state / warm start) -------------
