@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""Secondary measurements for the BASELINE configs that are NOT the headline bench line
+(bench.py measures configs[1]).  Prints one JSON line per configuration:
+  c3  DREAM, bimodal 2-D Gaussian, 10^6 chains, CR adaptation + outlier reset on, no history
+  c4  DREAM, line fit (3 parameters, 50 data points), 10^5 chains
+  demc100  DE-MC on the 100-D Gaussian, 10^5 chains (32 d + 16 bytes per chain-step)
+Device-resident timing with CUDA events, same rules as bench.py."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def run(name, make, N, d, bytes_per_step, gens=100, warm=20):
+    from bipymc_b200 import _lib
+    np.random.seed(1)
+    s = make()
+    k = 0
+    s.run_mcmc(N * (warm + 1))
+    k += warm
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    s.run_mcmc(N * (gens + 1), _k_gen0=k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    v = N * gens / (ms * 1e-3)
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    print(json.dumps({"config": name, "n_chains": N, "dim": d, "chain_steps_per_s": v, "ms_per_generation": ms / gens,
+                      "algorithmic_bytes_per_chain_step": bytes_per_step,
+                      "algorithmic_GBps": v * bytes_per_step / 1e9, "frac_of_hbm_peak": v * bytes_per_step / 1e9 / peak,
+                      "acceptance_fraction": s.acceptance_fraction}))
+
+
+def main():
+    from bipymc_b200 import DreamMpi, DeMcMpi, targets
+    which = sys.argv[1:] or ["c3", "c4", "demc100"]
+    if "c3" in which:
+        N = 1000000
+        t = targets.BimodeGauss_2D(log_of_pdf=False)
+        # own row + 6 partners + write (8 d each) + lnL r/w, + moments r/w (32 d) during adaptation
+        run("c3 bimodal DREAM 1e6 chains", lambda: DreamMpi(t.ln_like, [0.0, 0.0], n_chains=N, seed=3, varepsilon=1.0,
+                                                              history="none", burnin_gen=10 ** 6, n_cr_gen=10,
+                                                              outlier_gen=50), N, 2, 64 * 2 + 16 + 32 * 2 + 8 * 2)
+    if "c4" in which:
+        N = 100000
+        t = targets.LineFit()
+        run("c4 linefit DREAM 1e5 chains", lambda: DreamMpi(t.ln_like, [-0.8, 4.5, 0.2], n_chains=N, seed=3,
+                                                              varepsilon=1e-2, history="none", burnin_gen=10 ** 6,
+                                                              n_cr_gen=10), N, 3, 64 * 3 + 16 + 32 * 3 + 8 * 3)
+    if "demc100" in which:
+        N = 100000
+        t = targets.Gauss_100D()
+        run("DE-MC Gauss_100D 1e5 chains", lambda: DeMcMpi(t.ln_like, np.zeros(100), n_chains=N, seed=3,
+                                                             varepsilon=np.arange(100) + 1.0, history="none"),
+            N, 100, 32 * 100 + 16 + 32 * 100)
+
+
+if __name__ == "__main__":
+    main()
