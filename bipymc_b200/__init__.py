@@ -9,6 +9,7 @@ sampler does, and fails loudly otherwise (no CPU fallback).
 from .chain import McmcChain  # noqa: F401
 from .demc import DeMcMpi  # noqa: F401
 from .dream import DreamMpi  # noqa: F401
+from .samplers import DeMc  # noqa: F401
 from . import targets  # noqa: F401
 
-__all__ = ["McmcChain", "DeMcMpi", "DreamMpi", "targets"]
+__all__ = ["McmcChain", "DeMcMpi", "DreamMpi", "DeMc", "targets"]

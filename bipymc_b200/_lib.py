@@ -12,8 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # BIPYMC_B200_LIB: alternative build of the same library (A/B experiments of kernel variants)
 LIB_PATH = os.environ.get("BIPYMC_B200_LIB") or os.path.join(_HERE, "lib", "libbipymc_b200.so")
 
-BPM_ALGO_DEMC, BPM_ALGO_DREAM = 0, 1
-TARGET_EXTERNAL, TARGET_BANANA, TARGET_BIMODAL, TARGET_GAUSS, TARGET_LINEFIT = 0, 1, 2, 3, 4
+BPM_ALGO_DEMC, BPM_ALGO_DREAM, BPM_ALGO_DEMC_SERIAL = 0, 1, 2
+TARGET_EXTERNAL, TARGET_BANANA, TARGET_BIMODAL, TARGET_GAUSS, TARGET_LINEFIT, TARGET_EXPFIT = 0, 1, 2, 3, 4, 5
 BPM_MAX_PAIRS, BPM_MAX_CR, BPM_MAX_PEERS = 8, 16, 15
 
 

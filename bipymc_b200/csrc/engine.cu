@@ -56,6 +56,7 @@ struct bpm_engine {
   int32_t* loc_list = nullptr;   // sharded: local chains of both halves, compacted (kernels_generic.cuh)
   int32_t* loc_cnt = nullptr;    // [2]
   int32_t* cmp_blk = nullptr;    // [2][nblk][2] block counts / offsets
+  bool serial() const { return cfg.algo == BPM_ALGO_DEMC_SERIAL; }
   bool sharded() const { return cfg.chain_lo != 0 || cfg.chain_hi != cfg.n_chains; }
   double* prop = nullptr;
   double* lnl_prop = nullptr;
@@ -136,7 +137,7 @@ struct bpm_engine {
 
   int init() {
     const int N = cfg.n_chains;
-    nA = (N + 1) / 2;
+    nA = serial() ? N : (N + 1) / 2;   // serial DE-MC: one "half" holding every chain
     CU_TRY(cudaSetDevice(cfg.device));
     CU_TRY(cudaMalloc(&perm, sizeof(int32_t) * N));
     CU_TRY(cudaMalloc(&flip, sizeof(int32_t)));
@@ -185,7 +186,8 @@ struct bpm_engine {
     a.loc_list = loc_list; a.loc_cnt = loc_cnt;     // both nullptr on an unsharded handle
     a.N = cfg.n_chains; a.nA = nA; a.d = cfg.dim; a.ld = cfg.ld;
     a.chain_lo = cfg.chain_lo; a.chain_hi = cfg.chain_hi;
-    a.algo = cfg.algo;
+    a.algo = serial() ? BPM_ALGO_DEMC : cfg.algo;     // same proposal arithmetic (demc.py:180-182 == samplers.py:284-286)
+    a.serial = serial() ? 1 : 0;
     a.del_pairs = cfg.algo == BPM_ALGO_DREAM ? cfg.del_pairs : 1;
     a.n_cr = cfg.n_cr;
     if (cfg.algo == BPM_ALGO_DREAM) {
@@ -195,6 +197,7 @@ struct bpm_engine {
       a.gamma_jump = (k_gen % 10) == 0;  // demc.py:174
       a.gamma_p0 = 0.1;
     }
+    if (serial()) a.gamma_jump = 0;                   // samplers.py:284 uses gamma as is
     a.gamma_fixed = cfg.gamma > 0.0 ? cfg.gamma : 2.38 / sqrt(2.0 * cfg.dim);   // demc.py:162
     a.gamma_num = cfg.gamma_scale * 2.38;                                        // dream.py:61
     a.eps = cfg.epsilon > 0.0 ? sqrt(cfg.epsilon * cfg.epsilon) : 0.0;           // util.py:11-14
@@ -219,7 +222,9 @@ struct bpm_engine {
   int begin(const bpm_state* st, const bpm_replay* rp, cudaStream_t s) {
     const int N = cfg.n_chains;
     prof_begin(0, s);
-    if (rp) {
+    if (serial()) {
+      bpm::identity_split_kernel<<<cdiv(N, 256), 256, 0, s>>>(perm, flip, N);
+    } else if (rp) {
       CU_TRY(cudaMemcpyAsync(perm, rp->shuffle_idx, sizeof(int32_t) * N, cudaMemcpyDeviceToDevice, s));
       bpm::set_flag_kernel<<<1, 1, 0, s>>>(flip, rp->flip ? 1 : 0);
     } else {
@@ -295,6 +300,11 @@ struct bpm_engine {
         bpm::lnl_linefit_kernel<<<cdiv(n, 128), 128, sizeof(double) * 3 * linefit_M, s>>>(
             P, n, ld, tparams, linefit_M, out);
         break;
+      case BPM_TARGET_EXPFIT:
+        if (cfg.dim != 5) return fail("expfit target needs dim == 5");
+        bpm::lnl_expfit_kernel<<<cdiv(n, 128), 128, sizeof(double) * 2 * linefit_M, s>>>(
+            P, n, ld, tparams, linefit_M, out);
+        break;
       default:
         if (!user_fn) return fail("no likelihood: set a built-in target or a batched callback, or "
                                   "drive the split bpm_propose / bpm_accept API");
@@ -335,7 +345,7 @@ struct bpm_engine {
   int phase(const bpm_state* st, int64_t k_gen, int ph, const bpm_replay* rp, const bpm_trace_out* tr,
             cudaStream_t s) {
     bpm::PhaseArgs a = make_args(st, k_gen, ph, rp, tr);
-    if (fused_ok && !a.tr.prop) {
+    if (fused_ok && !a.tr.prop && !serial()) {
       int done = 0;
       prof_begin(4, s);
       BPM_TRY(bpm::try_fused_phase<REPLAY>(*this_target(), a, s, fused_ok, &done));
@@ -376,7 +386,7 @@ struct bpm_engine {
                  cudaStream_t s) {
     BPM_TRY(begin(st, rp, s));
     BPM_TRY(phase<REPLAY>(st, k_gen, 0, rp, tr, s));
-    BPM_TRY(phase<REPLAY>(st, k_gen, 1, rp, tr, s));
+    if (!serial()) BPM_TRY(phase<REPLAY>(st, k_gen, 1, rp, tr, s));
     BPM_TRY(end(s));
     BPM_TRY(track_omega(st, s));
     st->hist_len += 1;
@@ -396,7 +406,8 @@ int bpm_create(const bpm_config* cfg, bpm_handle* out) {
   if (cfg->n_chains < 4) return fail("n_chains >= 4 required (samplers.py:249)");
   if (cfg->dim < 1 || cfg->ld < cfg->dim) return fail("bad dim / ld");
   if (cfg->dim > 4 * bpm::kMaxBlocksPerLane * 32) return fail("dim > 1024 not supported yet");
-  if (cfg->algo != BPM_ALGO_DEMC && cfg->algo != BPM_ALGO_DREAM) return fail("bad algo");
+  if (cfg->algo != BPM_ALGO_DEMC && cfg->algo != BPM_ALGO_DREAM && cfg->algo != BPM_ALGO_DEMC_SERIAL)
+    return fail("bad algo");
   if (cfg->algo == BPM_ALGO_DREAM && (cfg->del_pairs < 1 || cfg->del_pairs > BPM_MAX_PAIRS))
     return fail("del_pairs must be in [1, 8]");
   if (cfg->n_cr < 1 || cfg->n_cr > BPM_MAX_CR) return fail("n_cr must be in [1, 16]");
@@ -481,6 +492,17 @@ int bpm_set_target(bpm_handle h, int32_t target, const double* params, int64_t n
       cudaFree(h->tparams); h->tparams = nullptr;
       CU_TRY(cudaMalloc(&h->tparams, sizeof(double) * 3 * M));
       CU_TRY(cudaMemcpy(h->tparams, params + 1, sizeof(double) * 3 * M, cudaMemcpyHostToDevice));
+      break;
+    }
+    case BPM_TARGET_EXPFIT: {
+      // [M, t[M], y[M]]
+      if (n < 1) return fail("expfit: header missing");
+      const int M = (int)params[0];
+      if (M < 1 || n != 1 + 2 * (int64_t)M || M > 3000) return fail("expfit: parameter count mismatch");
+      h->linefit_M = M;
+      cudaFree(h->tparams); h->tparams = nullptr;
+      CU_TRY(cudaMalloc(&h->tparams, sizeof(double) * 2 * M));
+      CU_TRY(cudaMemcpy(h->tparams, params + 1, sizeof(double) * 2 * M, cudaMemcpyHostToDevice));
       break;
     }
     default: return fail("unknown target id");

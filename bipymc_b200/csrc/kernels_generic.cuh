@@ -34,6 +34,11 @@ __global__ void split_native_kernel(int32_t* __restrict__ perm, int32_t* __restr
 }
 
 __global__ void set_flag_kernel(int32_t* flag, int32_t v) { *flag = v; }
+__global__ void identity_split_kernel(int32_t* __restrict__ perm, int32_t* __restrict__ flip, int N) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0) *flip = 0;
+  if (j < N) perm[j] = j;
+}
 
 // ---- sharded ranks: ordered compaction of the chains this rank owns -----------------
 // A rank steps only its own chains (demc.py:103-107 loops over the local ids and tests
@@ -190,8 +195,8 @@ __global__ void __launch_bounds__(kThreads) propose_kernel(const PhaseArgs a) {
   for (int p = 0; p < BPM_MAX_PAIRS; ++p) {
     pa[p] = a.X; pb[p] = a.X;
     if (valid && p < npair) {
-      pa[p] = a.X + (size_t)L.pool[D.r1[p]] * a.ld;
-      pb[p] = a.X + (size_t)L.pool[D.r2[p]] * a.ld;
+      pa[p] = a.X + (size_t)pool_chain(L, D.r1[p], c) * a.ld;
+      pb[p] = a.X + (size_t)pool_chain(L, D.r2[p], c) * a.ld;
     }
   }
   const double* xc = a.X + (size_t)c * a.ld;
@@ -319,6 +324,18 @@ __global__ void lnl_linefit_kernel(const double* __restrict__ P, int n, int ld,
   if (j < n)
     out[j] = linefit_lnl(sdata, sdata + M, sdata + 2 * M, M, P[(size_t)j * ld], P[(size_t)j * ld + 1],
                          P[(size_t)j * ld + 2]);
+}
+
+__global__ void lnl_expfit_kernel(const double* __restrict__ P, int n, int ld,
+                                  const double* __restrict__ data, int M, double* __restrict__ out) {
+  extern __shared__ double sdata[];
+  for (int i = threadIdx.x; i < 2 * M; i += blockDim.x) sdata[i] = data[i];
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) {
+    const double* th = P + (size_t)j * ld;
+    out[j] = expfit_lnl(sdata, sdata + M, M, th[0], th[1], th[2], th[3], th[4]);
+  }
 }
 
 // Generic tiled quadratic form for any d: out[j] = finish(|(P[j] - mu) . W|^2).
@@ -505,7 +522,7 @@ __global__ void dump_draws_kernel(const PhaseArgs a, bpm_replay out) {
   if (j >= a.N) return;
   const int c = a.perm[j];
   const bool first_half = j < a.nA;
-  const int n_pool = first_half ? a.N - a.nA : a.nA;  // pool sizes do not depend on the flip
+  const int n_pool = a.serial ? a.N - 1 : (first_half ? a.N - a.nA : a.nA);  // independent of the flip
   const_cast<int32_t*>(out.shuffle_idx)[j] = c;
   ChainDraws D;
   chain_scalar_draws<false>(a, c, n_pool, D);

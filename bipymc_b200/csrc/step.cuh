@@ -31,6 +31,7 @@ struct PhaseArgs {
   int32_t chain_lo, chain_hi;
   // schedule
   int32_t algo, del_pairs, n_cr;
+  int32_t serial;      // BPM_ALGO_DEMC_SERIAL: self = every chain, pool = every OTHER chain
   int32_t gamma_jump;  // k % 5 == 0 (DREAM, dream.py:77) / k % 10 == 0 (DE-MC, demc.py:174)
   double gamma_p0;     // 0.2 / 0.1: probability of KEEPING gamma_base on a jump generation
   double gamma_fixed;  // DE-MC gamma_base (demc.py:162)
@@ -82,10 +83,21 @@ struct PhaseLists {
   const int32_t* self;
   const int32_t* pool;
   int32_t n_self, n_pool;
+  int32_t skip_self;   // pool position r of chain c means chain r + (r >= c): np.delete(range(N), c)[r]
 };
+// global chain id of pool position r for the chain c being stepped
+__device__ __forceinline__ int pool_chain(const PhaseLists& L, int r, int c) {
+  return L.skip_self ? r + (r >= c ? 1 : 0) : L.pool[r];
+}
 __device__ __forceinline__ PhaseLists phase_lists(const PhaseArgs& a) {
   const int32_t first = (a.phase ^ (*a.flip != 0)) == 0;  // true: self is perm[0:nA)
   PhaseLists L;
+  L.skip_self = 0;
+  if (a.serial) {   // samplers.py:275-277: valid_pool_ids = np.delete(range(n_chains), i)
+    L.self = a.perm; L.n_self = a.N; L.pool = a.perm; L.n_pool = a.N - 1; L.skip_self = 1;
+    if (a.loc_cnt) { L.self = a.loc_list; L.n_self = a.loc_cnt[0]; }
+    return L;
+  }
   if (first) {
     L.self = a.perm; L.n_self = a.nA; L.pool = a.perm + a.nA; L.n_pool = a.N - a.nA;
   } else {

@@ -76,4 +76,25 @@ __device__ __forceinline__ double linefit_lnl(const double* x, const double* y, 
   return 0.0 + -0.5 * s;
 }
 
+// Exponential-relaxation fit, examples/ex_exp_fit.py:38-121.
+//   theta = (tau, c_inf, c_0, leak, sigma);  flat box prior (ex_exp_fit.py:103-121);
+//   model(t) = c_inf + c_0 * (-1) * exp(-t / tau) - leak * t          (ex_exp_fit.py:38-43)
+//   lnprob   = 0.0 + -0.5 * sum_i [ (model_i - y_i)^2 / sigma - log(1 / sigma) ]   (ex_exp_fit.py:73-101)
+__device__ __forceinline__ double expfit_lnl(const double* t, const double* y, int M, double tau, double c_inf,
+                                             double c_0, double leak, double sigma) {
+  if (!(-5.0 < c_inf && c_inf < 5.0 && 1.0 < tau && tau < 50.0 && -1.0 < c_0 && c_0 < 1.0 && -5.0 < leak &&
+        leak < 5.0 && 0.0 < sigma && sigma < 1.0))
+    return -INFINITY;
+  const double c0v = __dmul_rn(c_0, -1.0);
+  const double lg = log(__ddiv_rn(1.0, sigma));
+  double s = 0.0;
+  for (int i = 0; i < M; ++i) {
+    const double ex = exp(__ddiv_rn(-t[i], tau));
+    const double m = __dsub_rn(__dadd_rn(c_inf, __dmul_rn(c0v, ex)), __dmul_rn(leak, t[i]));
+    const double r = __dsub_rn(m, y[i]);
+    s += __dsub_rn(__ddiv_rn(__dmul_rn(r, r), sigma), lg);
+  }
+  return 0.0 + -0.5 * s;
+}
+
 }  // namespace bpm

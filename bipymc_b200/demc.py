@@ -255,6 +255,7 @@ class _ChainList(object):
 class DeMcMpi(object):
     """Parallel DE-MC (emcee-style a/b pools) on B200; mirrors bipymc/demc.py:10."""
     _algo = _lib.BPM_ALGO_DEMC
+    _n_phases = 2
 
     def __init__(self, ln_like_fn, theta_0=None, varepsilon=1e-6, n_chains=8,
                  mpi_comm=None, ln_kwargs={}, **kwargs):
@@ -763,11 +764,12 @@ class DeMcMpi(object):
         s = self._stream()
         lib, h = self._libh, self._handle
         _lib.check(lib.bpm_begin_generation(h, C.byref(st), k_gen, rp, s))
-        for phase in (0, 1):
+        for phase in range(self._n_phases):
+            last = phase == self._n_phases - 1
             if self._mode() == "device":
                 # built-in likelihood: the whole half-phase stays inside the library
                 _lib.check(lib.bpm_phase(h, C.byref(st), phase, s))
-                self._phase_exchange(last=(phase == 1))
+                self._phase_exchange(last=last)
                 continue
             prop_p, n_p = C.c_void_p(), C.c_int32()
             _lib.check(lib.bpm_propose(h, C.byref(st), phase, C.byref(prop_p), C.byref(n_p), s))
@@ -779,7 +781,7 @@ class DeMcMpi(object):
                 # likelihood values are ignored by bpm_accept (ownership check in-kernel)
                 pass
             _lib.check(lib.bpm_accept(h, C.byref(st), phase, lnl_prop.data_ptr(), None, s))
-            self._phase_exchange(last=(phase == 1))
+            self._phase_exchange(last=last)
         _lib.check(lib.bpm_end_generation(h, C.byref(st), s))
         if self.comm.size > 1 and self._algo == _lib.BPM_ALGO_DREAM:
             self._allreduce_cr()

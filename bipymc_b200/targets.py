@@ -7,6 +7,7 @@ Mirrors the reference's test-target classes (same constructor arguments, same ``
   BimodeGauss_2D  bipymc/utils/dblgauss_rv.py:10-43
   Gauss_100D      bipymc/utils/d100_gauss.py:10-39
   LineFit         examples/ex_para_fit.py:26-55 (lnprob of the second example)
+  ExpFit          examples/ex_exp_fit.py:38-121 (5-parameter relaxation fit)
 
 ``ln_like`` stays a scalar host function, so the objects remain valid ``ln_like_fn``
 arguments everywhere; when a sampler of this package receives ``obj.ln_like`` it
@@ -227,6 +228,35 @@ class LineFit(object):
     def device_target(self):
         p = np.concatenate([[float(len(self.x))], self.x, self.y, self.yerr])
         return DeviceTarget(_lib.TARGET_LINEFIT, p, 3)
+
+
+def expfit_data(seed=42, n=60, tau=12.0, c_inf=1.5, c_0=0.6, leak=1e-3, sigma=2e-3):
+    """Synthetic relaxation data for the model of examples/ex_exp_fit.py:38-43 (the example
+    reads a measured .mat series; a seeded synthetic series of the same shape stands in)."""
+    rs = np.random.RandomState(seed)
+    t = np.linspace(0.5, 60.0, n)
+    y = c_inf + c_0 * -1.0 * np.exp(-t / tau) - leak * t + np.sqrt(sigma) * 0.3 * rs.randn(n)
+    return t, y
+
+
+class ExpFit(object):
+    """theta = (tau, c_inf, c_0, leak, sigma): lnprob of examples/ex_exp_fit.py:73-121."""
+    def __init__(self, t=None, y=None):
+        if t is None:
+            t, y = expfit_data()
+        self.t, self.y = np.asarray(t, dtype=float), np.asarray(y, dtype=float)
+
+    def ln_like(self, theta):
+        tau, c_inf, c_0, leak, sigma = theta
+        if not (-5.0 < c_inf < 5.0 and 1.0 < tau < 50.0 and -1.0 < c_0 < 1.0 and -5.0 < leak < 5.0 and
+                0.0 < sigma < 1.0):
+            return -np.inf
+        m = c_inf + c_0 * -1.0 * np.exp(-self.t / tau) - leak * self.t
+        return 0.0 + -0.5 * np.sum((m - self.y) ** 2. / sigma - np.log(1.0 / sigma))
+
+    def device_target(self):
+        p = np.concatenate([[float(len(self.t))], self.t, self.y])
+        return DeviceTarget(_lib.TARGET_EXPFIT, p, 5)
 
 
 def resolve_device_target(ln_like_fn, ln_kwargs):

@@ -27,6 +27,9 @@ extern "C" {
 
 #define BPM_ALGO_DEMC 0   /* DeMcMpi._update_chain_pool   bipymc/demc.py:153-196 */
 #define BPM_ALGO_DREAM 1  /* DreamMpi._update_chain_pool  bipymc/dream.py:32-107 */
+#define BPM_ALGO_DEMC_SERIAL 2 /* DeMc._mcmc_run, delayed accept: every chain proposes from the frozen
+                                  population, partners drawn from ALL other chains, no a/b split, no
+                                  gamma jumps (bipymc/samplers.py:261-308); one phase per generation */
 
 #define BPM_MAX_PAIRS 8
 #define BPM_MAX_CR 16
@@ -38,6 +41,7 @@ extern "C" {
 #define BPM_TARGET_BIMODAL 2  /* bipymc/utils/dblgauss_rv.py:26-32 params: 2 x bpm_mvn2 + weights  */
 #define BPM_TARGET_GAUSS 3    /* bipymc/utils/d100_gauss.py:14-35  params: mu[d], W[d][r], c0      */
 #define BPM_TARGET_LINEFIT 4  /* examples/ex_para_fit.py:39-55     params: x[M], y[M], yerr[M]     */
+#define BPM_TARGET_EXPFIT 5   /* examples/ex_exp_fit.py:38-121     params: t[M], y[M]; dim = 5     */
 
 typedef struct bpm_engine* bpm_handle;
 typedef void* bpm_stream; /* cudaStream_t */

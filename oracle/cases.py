@@ -39,6 +39,15 @@ CASES = {
 }
 
 
+# Serial DeMc (bipymc/samplers.py:237-324, delayed accept): run_mcmc(n, theta_0, **run_kwargs)
+SERIAL_CASES = {
+    "serial_banana": dict(target="banana", theta_0=[0.0, 0.0], n_chains=12, n=12 * 41, seed=51,
+                          run_kwargs=dict(varepsilon=1e-2)),
+    "serial_gauss7": dict(target="gauss7", theta_0=list(np.zeros(7)), n_chains=9, n=9 * 21, seed=52,
+                          run_kwargs=dict(varepsilon=1e-3, gamma=0.7, inflate=3.0)),
+}
+
+
 def linefit_lnprob_ref():
     """(fn, ln_kwargs) with the signature the reference freezes (samplers.py:43):
     lnprob(theta, x, y, yerr) of examples/ex_para_fit.py:39-55."""

@@ -30,7 +30,9 @@ from bipymc.demc import DeMcMpi  # noqa: E402  (the reference)
 from bipymc.dream import DreamMpi  # noqa: E402
 from bipymc.utils import banana_rv, dblgauss_rv, d100_gauss  # noqa: E402
 
-from oracle.cases import CASES, linefit_lnprob_ref  # noqa: E402
+from bipymc.samplers import DeMc  # noqa: E402
+
+from oracle.cases import CASES, SERIAL_CASES, linefit_lnprob_ref  # noqa: E402
 
 
 def target_fn(name):
@@ -64,9 +66,31 @@ def run_case(case):
     return out
 
 
+def run_serial_case(case):
+    """Unmodified reference DeMc (samplers.py:237-324), default delayed accept."""
+    fn, ln_kwargs = target_fn(case["target"])
+    np.random.seed(case["seed"])
+    s = DeMc(fn, n_chains=case["n_chains"], ln_kwargs=ln_kwargs)
+    s.run_mcmc(case["n"], np.asarray(case["theta_0"], dtype=float), **case["run_kwargs"])
+    hist = np.ascontiguousarray(np.array([c.chain for c in s.am_chains]).transpose(1, 0, 2))
+    mean, std, sl = s.param_est(n_burn=0)
+    return dict(history=hist, n_accepted=np.int64(s.n_accepted), n_rejected=np.int64(s.n_rejected),
+                acceptance_fraction=np.float64(s.acceptance_fraction), mean=mean, std=std,
+                super_chain_head=sl[:3 * case["n_chains"]])
+
+
 def main():
     gdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gdir, exist_ok=True)
+    for name, case in SERIAL_CASES.items():
+        out = run_serial_case(case)
+        path = os.path.join(gdir, "ref_%s.npz" % name)
+        np.savez_compressed(path, **out)
+        print("%-22s T=%d N=%d d=%d acc=%d rej=%d -> %s" % (
+            name, out["history"].shape[0], out["history"].shape[1], out["history"].shape[2],
+            out["n_accepted"], out["n_rejected"], os.path.relpath(path, ROOT)))
+    if "--serial-only" in sys.argv:
+        return
     for name, case in CASES.items():
         out = run_case(case)
         path = os.path.join(gdir, "ref_%s.npz" % name)

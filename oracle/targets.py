@@ -116,3 +116,42 @@ class LineFit(object):
         model = m * self.x + b
         inv_sigma2 = 1.0 / (self.yerr ** 2 + model ** 2 * np.exp(2 * lnf))
         return 0.0 + -0.5 * (np.sum((self.y - model) ** 2 * inv_sigma2 - np.log(inv_sigma2)))
+
+
+def expfit_data(seed=42, n=60, tau=12.0, c_inf=1.5, c_0=0.6, leak=1e-3, sigma=2e-3):
+    """Synthetic series for the model of examples/ex_exp_fit.py:38-43 (same generator as the
+    product's bipymc_b200.targets.expfit_data; restated here so oracle/ stays self-contained)."""
+    rs = np.random.RandomState(seed)
+    t = np.linspace(0.5, 60.0, n)
+    y = c_inf + c_0 * -1.0 * np.exp(-t / tau) - leak * t + np.sqrt(sigma) * 0.3 * rs.randn(n)
+    return t, y
+
+
+class ExpFit(object):
+    """lnprob(theta, t, y_data) of examples/ex_exp_fit.py:73-121, function by function."""
+    def __init__(self, t=None, y=None):
+        if t is None:
+            t, y = expfit_data()
+        self.t, self.y = np.asarray(t), np.asarray(y)
+
+    @staticmethod
+    def exp_c1_model_full(tau, c_inf, c_0, leak, t):          # ex_exp_fit.py:38-43
+        v2 = -1.0
+        return c_inf + c_0 * v2 * np.exp(-t / tau) - leak * t
+
+    @staticmethod
+    def ln_params_prior(tau, c_inf, c_0, leak, sigma):        # ex_exp_fit.py:103-121
+        if (-5 < c_inf < 5.0) and (1.0 < tau < 50) and (-1.0 < c_0 < 1.) and (-5. < leak < 5.0) \
+                and (0 < sigma < 1.0):
+            return 0.0
+        return -np.inf
+
+    def ln_like(self, theta):                                  # ex_exp_fit.py:73-101
+        lp = self.ln_params_prior(*theta)
+        if not np.isfinite(lp):
+            return -np.inf
+        tau, c_inf, c_0, leak, sigma = theta
+        y_sigma = theta[-1]
+        ln_model = np.sum((self.exp_c1_model_full(tau, c_inf, c_0, leak, self.t) - self.y) ** 2. / y_sigma
+                          - np.log(1.0 / y_sigma))
+        return lp + -0.5 * ln_model

@@ -117,6 +117,12 @@ def test_host_targets_match_oracle_targets():
     for th in ([-0.8, 4.5, 0.2], [-1.0, 4.0, -0.5], [0.6, 4.0, 0.0]):
         assert lf.ln_like(th) == olf.ln_like(th)
     np.testing.assert_allclose(targets.Gauss_100D().ln_like(np.zeros(100)), -241.4137423, atol=1e-6)
+    ef, oef = targets.ExpFit(), otargets.ExpFit()
+    assert np.array_equal(ef.t, oef.t) and np.array_equal(ef.y, oef.y)
+    for th in ([12.0, 1.5, 0.6, 1e-3, 2e-3], [20.0, 1.0, -0.3, 0.5, 0.5], [0.5, 1.0, 0.1, 0.0, 0.1],
+               [10.0, 1.0, 0.1, 0.0, 1.5]):
+        assert ef.ln_like(th) == oef.ln_like(th)
+    assert ef.ln_like([0.5, 1.0, 0.1, 0.0, 0.1]) == -np.inf       # tau outside its prior box
 
 
 def test_var_ball_matches_numpy_stream():

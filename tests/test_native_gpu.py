@@ -105,6 +105,21 @@ def test_native_linefit_matches_oracle_replay():
     _native_vs_oracle(s, otargets.LineFit().ln_like, gens=10)
 
 
+def test_native_expfit_matches_oracle_replay():
+    """5-parameter relaxation fit of examples/ex_exp_fit.py (d = 5: generic split path with the
+    built-in device likelihood)."""
+    from bipymc_b200 import DreamMpi, DeMcMpi, targets
+    th0 = [12.0, 1.5, 0.6, 1e-3, 2e-3]
+    veps = np.asarray([1e-2, 1e-2, 1e-3, 1e-8, 1e-9]) * 1e-2          # ex_exp_fit.py:135
+    np.random.seed(5)
+    s = DreamMpi(targets.ExpFit().ln_like, th0, n_chains=14, n_cr_gen=2, burnin_gen=1000, seed=8,
+                 varepsilon=veps)
+    _native_vs_oracle(s, otargets.ExpFit().ln_like, gens=10, k0=0)
+    np.random.seed(6)
+    s = DeMcMpi(targets.ExpFit().ln_like, th0, n_chains=9, seed=9, varepsilon=veps)
+    _native_vs_oracle(s, otargets.ExpFit().ln_like, gens=6, k0=8)
+
+
 def test_seed_reproducible_and_seed_sensitive():
     from bipymc_b200 import DreamMpi, targets
     outs = []

@@ -93,3 +93,25 @@ def test_diagnostics_oracle_known_answers():
     h = np.array([[[-1.0], [1.0]], [[0.0], [2.0]], [[1.0], [3.0]]])
     # W = 1, B/T = var([0, 2], ddof=1) = 2 -> R = sqrt((2/3 + 2) / 1)
     np.testing.assert_allclose(od.rhat(h), [np.sqrt(2.0 / 3.0 + 2.0)], rtol=1e-15)
+
+
+@pytest.mark.parametrize("name", ["serial_banana", "serial_gauss7"])
+def test_serial_demc_oracle_matches_reference_bit_for_bit(name):
+    """oracle/demc_serial.py vs the unmodified reference's DeMc (samplers.py:237-324)."""
+    from oracle.cases import SERIAL_CASES, oracle_target
+    from oracle.demc_serial import OracleDeMc
+    case = SERIAL_CASES[name]
+    g = np.load(os.path.join(GOLD, "ref_%s.npz" % name))
+    fn, kw = oracle_target(case["target"])
+    np.random.seed(case["seed"])
+    s = OracleDeMc(fn, n_chains=case["n_chains"], ln_kwargs=kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        traces = s.run_mcmc(case["n"], case["theta_0"], record=True, **case["run_kwargs"])
+    assert np.array_equal(np.array(s.history), g["history"])
+    assert s.n_accepted == int(g["n_accepted"]) and s.n_rejected == int(g["n_rejected"])
+    assert s.acceptance_fraction == float(g["acceptance_fraction"])
+    mean, std, sl = s.param_est(0)
+    assert np.array_equal(mean, g["mean"]) and np.array_equal(std, g["std"])
+    assert np.array_equal(sl[:3 * case["n_chains"]], g["super_chain_head"])
+    assert len(traces) == g["history"].shape[0] - 1
