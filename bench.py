@@ -263,6 +263,44 @@ def run_ours(args):
                "steps": ke, "ms_per_step": 1e3 * dt / ke,
                "note": "bpm_generations_host: pinned host population -> H2D -> one generation -> D2H, every step"}
 
+    if world > 1 and not args.no_e2e:
+        # sharded end-to-end step: every rank copies ITS shard (states + cached likelihoods) in from
+        # pinned host memory, the replicas are completed by an all-gather, one generation runs
+        # through the same C-ABI calls run_mcmc makes, and the shard is copied back out
+        lo, hi = int(s.rank_chain_ids[0]), int(s.rank_chain_ids[-1]) + 1
+        Xh = torch.empty((hi - lo, s._ld), dtype=torch.float64).pin_memory()
+        Lh = torch.empty((hi - lo,), dtype=torch.float64).pin_memory()
+        Xh.copy_(s._X[lo:hi]); Lh.copy_(s._lnl[lo:hi])
+        g0 = s._hist.length
+        ke = max(3, min(K, 20))
+
+        def e2e_step(i):
+            s._X[lo:hi].copy_(Xh, non_blocking=True)
+            s._lnl[lo:hi].copy_(Lh, non_blocking=True)
+            s._allgather_population()
+            st = s._state(None)
+            st.hist_len = g0 + i
+            st.mom_len = s._mom_len + i
+            s._split_generation(st, k_done + i)
+            Xh.copy_(s._X[lo:hi], non_blocking=True)
+            Lh.copy_(s._lnl[lo:hi], non_blocking=True)
+            torch.cuda.synchronize(dev)
+        for i in range(2):
+            e2e_step(i)
+        sync_all()
+        t0 = time.perf_counter()
+        for i in range(ke):
+            e2e_step(2 + i)
+        sync_all()
+        dt_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
+        dt = float(dt_t.item())
+        nb = (N * s._ld * 8 + N * 8)
+        e2e = {"value": N * ke / dt, "unit": UNIT, "h2d_bytes_per_step": nb, "d2h_bytes_per_step": nb,
+               "steps": ke, "ms_per_step": 1e3 * dt / ke,
+               "note": "per rank: pinned host shard -> H2D, NCCL all-gather of the replicas, one sharded "
+                       "generation, shard -> D2H; bytes are summed over ranks"}
+
     cpu = cpu_baseline_leg() if (rank == 0 and world == 1 and not args.no_cpu) else None
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
