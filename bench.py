@@ -64,7 +64,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -162,6 +162,13 @@ def run_ours(args):
     tgt = targets.Gauss_100D(rho=0.5, dim=DIM)
     np.random.seed(42)
     K, W = args.steps, args.warmup
+    # full history = 80 MB per generation per GPU: keep it while it fits comfortably in HBM
+    hist_rows = K + W + SETUP_GENS + 8
+    if args.history == "full" and hist_rows * N_PER_GPU * DIM * 8 > 0.5 * torch.cuda.get_device_properties(dev).total_memory:
+        args.history = "none"
+        history_note = "none (the %d requested generations of history would not fit in HBM)" % hist_rows
+    else:
+        history_note = args.history
     s = DreamMpi(tgt.ln_like, np.zeros(DIM), n_chains=N, varepsilon=np.arange(DIM) + 1.0, seed=42,
                  n_cr_gen=50, burnin_gen=args.burnin_gen, device=local_rank,
                  history=args.history, history_reserve=K + W + SETUP_GENS + 8, fused=args.fused,
@@ -308,7 +315,7 @@ def run_ours(args):
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "configs[1]: DREAM on Gauss_100D(rho=0.5), %d chains per GPU" % N_PER_GPU,
                            "n_chains": N, "dim": DIM, "del_pairs": 3, "n_cr": 3, "n_cr_gen": 50,
-                           "burnin_gen": args.burnin_gen, "history": args.history,
+                           "burnin_gen": args.burnin_gen, "history": history_note,
                            "cr_adaptation": "on" if args.burnin_gen > SETUP_GENS + W + K else "off",
                            "init": "theta_0 + N(0, diag(Sigma)), %d untimed setup generations" % SETUP_GENS,
                            "rng": "philox4x32-10 seed 42", "parallelism": "chains sharded x%d" % world,
