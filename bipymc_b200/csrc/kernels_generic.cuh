@@ -433,30 +433,65 @@ __global__ void __launch_bounds__(256) cr_update_kernel(const double* __restrict
                                                         double* __restrict__ part, int apply,
                                                         double* __restrict__ dm, double* __restrict__ cnt,
                                                         double* __restrict__ p_cr) {
-  __shared__ double sm[8];
+  __shared__ double sm[8][2 * 4];
   __shared__ bool last;
   const int n = hi - lo;
   const int per = (n + gridDim.x - 1) / gridDim.x;
   const int c0 = lo + blockIdx.x * per;
   const int c1 = min(hi, c0 + per);
-  for (int m = 0; m < n_cr; ++m) {
-    double s = 0.0, k = 0.0;
-    for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x)
-      if (cr_pick[c] == m) { s += cr_delta[c]; k += 1.0; }
-    for (int pass = 0; pass < 2; ++pass) {
-      double v = pass == 0 ? s : k;
+  if (n_cr <= 4) {
+    // one pass over the block's chains, the (at most four) CR classes in registers
+    double s[4] = {0.0, 0.0, 0.0, 0.0}, k[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
+      const int m = cr_pick[c];
+      if (m >= 0) {
+        const double v = cr_delta[c];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-      if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        double w = 0.0;
-        for (int i = 0; i < 8; ++i) w += sm[i];
-        block_part[(size_t)blockIdx.x * 2 * BPM_MAX_CR + pass * n_cr + m] = w;
+        for (int q = 0; q < 4; ++q)
+          if (m == q) { s[q] += v; k[q] += 1.0; }
       }
-      __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s[q] += __shfl_xor_sync(0xFFFFFFFFu, s[q], o);
+        k[q] += __shfl_xor_sync(0xFFFFFFFFu, k[q], o);
+      }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { sm[threadIdx.x >> 5][q] = s[q]; sm[threadIdx.x >> 5][4 + q] = k[q]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      const int q = threadIdx.x & 3, pass = threadIdx.x >> 2;
+      double w = 0.0;
+      for (int i = 0; i < 8; ++i) w += sm[i][threadIdx.x];
+      if (q < n_cr) block_part[(size_t)blockIdx.x * 2 * BPM_MAX_CR + pass * n_cr + q] = w;
+    }
+  } else {
+    for (int m = 0; m < n_cr; ++m) {
+      double s = 0.0, k = 0.0;
+      for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x)
+        if (cr_pick[c] == m) { s += cr_delta[c]; k += 1.0; }
+      for (int pass = 0; pass < 2; ++pass) {
+        double v = pass == 0 ? s : k;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5][0] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          double w = 0.0;
+          for (int i = 0; i < 8; ++i) w += sm[i][0];
+          block_part[(size_t)blockIdx.x * 2 * BPM_MAX_CR + pass * n_cr + m] = w;
+        }
+        __syncthreads();
+      }
     }
   }
+  __threadfence();        // every writer publishes its block partials before the ticket is taken
+  __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     last = atomicAdd(ticket, 1u) == gridDim.x - 1;
