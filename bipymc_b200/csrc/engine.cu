@@ -12,6 +12,7 @@
 #include "kernels_generic.cuh"
 #include "kernels_fused.cuh"
 #include "diagnostics.cuh"
+#include "gauss_dmma.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
 namespace {
@@ -290,7 +291,11 @@ struct bpm_engine {
                                      gauss_mu_zero, out, s))
             return fail("gauss rows kernel launch failed");
         }
-        else
+        else if (bpm::gauss_dmma_supported(cfg.dim, gauss_r, ld)) {   // large d: FP64 tensor-pipe GEMM
+          if (bpm::launch_gauss_dmma(P, n, ld, cfg.dim, gauss_r, mu, W, gauss_c0, gauss_logpdf_flag,
+                                     gauss_mu_zero, out, s))
+            return fail("gauss dmma kernel launch failed");
+        } else
           bpm::lnl_gauss_tiled_kernel<<<cdiv(n, 64), 256, 0, s>>>(P, n, ld, cfg.dim, gauss_r, mu, W,
                                                                   gauss_c0, gauss_logpdf_flag, out);
         break;

@@ -355,3 +355,24 @@ def test_checkpoint_roundtrip_resumes_the_same_chains(tmp_path):
     c = DreamMpi(tgt.ln_like, [0.0, 0.0], seed=1, n_chains=25)
     with pytest.raises(RuntimeError):
         c.load_state(f)
+
+
+@pytest.mark.parametrize("dim,n,shift", [(128, 300, False), (200, 1000, True), (1000, 777, False), (1000, 64, True),
+                                         (114, 50, True)])
+def test_large_d_quadratic_form_matches_numpy(dim, n, shift):
+    """bpm_eval_lnl for d > 112 (FP64 tensor-pipe GEMM kernel, gauss_dmma.cuh): values agree with
+    the host's scipy-style evaluation to 1e-12 relative, including a non-zero mean, ragged n and
+    column / k tails that are not multiples of the tile."""
+    import torch
+    from bipymc_b200 import DreamMpi, targets
+    rs = np.random.RandomState(dim + n)
+    mean = rs.randn(dim) if shift else None
+    t = targets.Gauss_100D(dim=dim, mean=mean, log_of_pdf=False)
+    np.random.seed(0)
+    s = DreamMpi(t.ln_like, np.zeros(dim), n_chains=8, seed=1, varepsilon=1.0)
+    X = rs.randn(n, dim) * np.sqrt(np.arange(dim) + 1.0)
+    rows = torch.zeros((n, s._ld), dtype=torch.float64, device=s._device)
+    rows[:, :dim] = torch.from_numpy(X).to(s._device)
+    got = s._eval_lnl_rows(rows).cpu().numpy()
+    want = np.array([t.ln_like(x) for x in X])
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-10)

@@ -40,7 +40,7 @@ def run(name, make, N, d, bytes_per_step, gens=100, warm=20):
 
 def main():
     from bipymc_b200 import DreamMpi, DeMcMpi, targets
-    which = sys.argv[1:] or ["c3", "c4", "demc100"]
+    which = sys.argv[1:] or ["c3", "c4", "demc100", "c5shape"]
     if "c3" in which:
         N = 1000000
         t = targets.BimodeGauss_2D(log_of_pdf=False)
@@ -62,5 +62,21 @@ def main():
             N, 100, 32 * 100 + 16 + 32 * 100)
 
 
+def c5shape():
+    """configs[4] shape on one GPU: DREAM on the 1000-D correlated Gaussian (direct log-density),
+    2 x 10^4 chains -- the generic split path (propose / tiled FP64 quadratic form / accept)."""
+    from bipymc_b200 import DreamMpi, targets
+    N, d = 20000, 1000
+    t = targets.Gauss_100D(dim=d)
+    run("c5-shape DREAM Gauss_1000D 2e4 chains", lambda: DreamMpi(t.ln_like, np.zeros(d), n_chains=N, seed=3,
+                                                                    varepsilon=np.arange(d) + 1.0, history="none",
+                                                                    burnin_gen=10 ** 6, n_cr_gen=10),
+        N, d, 64 * d + 16 + 32 * d + 8 * d, gens=20, warm=12)
+
+
 if __name__ == "__main__":
+    if "c5shape" in (sys.argv[1:] or ["c5shape"]):
+        c5shape()
+        if sys.argv[1:] == ["c5shape"]:
+            sys.exit(0)
     main()
