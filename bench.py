@@ -172,7 +172,7 @@ def run_ours(args):
     s = DreamMpi(tgt.ln_like, np.zeros(DIM), n_chains=N, varepsilon=np.arange(DIM) + 1.0, seed=42,
                  n_cr_gen=50, burnin_gen=args.burnin_gen, device=local_rank,
                  history=args.history, history_reserve=K + W + SETUP_GENS + 8, fused=args.fused,
-                 exchange=args.exchange)
+                 exchange=args.exchange, subpop_k=args.subpop_k)
     lib, h = s._libh, s._handle
     n_local = len(s.rank_chain_ids)
 
@@ -270,7 +270,7 @@ def run_ours(args):
                "steps": ke, "ms_per_step": 1e3 * dt / ke,
                "note": "bpm_generations_host: pinned host population -> H2D -> one generation -> D2H, every step"}
 
-    if world > 1 and not args.no_e2e:
+    if world > 1 and not args.no_e2e and args.subpop_k == 0:
         # sharded end-to-end step: every rank copies ITS shard (states + cached likelihoods) in from
         # pinned host memory, the replicas are completed by an all-gather, one generation runs
         # through the same C-ABI calls run_mcmc makes, and the shard is copied back out
@@ -320,6 +320,8 @@ def run_ours(args):
                            "init": "theta_0 + N(0, diag(Sigma)), %d untimed setup generations" % SETUP_GENS,
                            "rng": "philox4x32-10 seed 42", "parallelism": "chains sharded x%d" % world,
                            "exchange": ("none (1 GPU)" if world == 1 else
+                                        "sub-population mode: islands of %d chains, re-dealt every %d generations "
+                                        "(all-to-all)" % (N_PER_GPU, args.subpop_k) if args.subpop_k > 0 else
                                         "accepted rows stored into peer replicas in-kernel (NVLink P2P) + barrier"
                                         if s._exchange == "p2p" else "NCCL all-gather of the shard per half-phase"),
                            "l2": "working set per generation (state 80 MB + moments 160 MB + history "
@@ -343,6 +345,8 @@ def main():
     ap.add_argument("--fused", type=int, default=1, help="1 fused v3 (default), 3 fused 12-producer variant, 2 two-halves fused kernel, 0 split path")
     ap.add_argument("--burnin-gen", type=int, default=2000, help="DREAM burnin_gen (2000 = tests/test_100dgauss.py:109)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "allgather"], help="multi-GPU state exchange")
+    ap.add_argument("--subpop-k", type=int, default=0,
+                    help="sub-population mode: islands re-dealt every K generations (0 = one population, the default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     args = ap.parse_args()

@@ -295,6 +295,13 @@ class DeMcMpi(object):
         self._exchange = kwargs.get("exchange", "p2p")
         if self._exchange not in ("p2p", "allgather"):
             raise ValueError("exchange must be 'p2p' or 'allgather'")
+        # sub-population ("island") mode for populations whose full replica does not fit or whose
+        # per-generation exchange would dominate (BASELINE config 5): every rank steps ITS chains
+        # as a self-contained population -- pairs come from the local opposite half, no replica,
+        # no per-generation communication -- and every `subpop_k` generations the chains are
+        # re-dealt across the ranks (one all-to-all), so each island receives 1/G of every island.
+        # A different sampler than the reference's single population, hence opt-in and stated.
+        self.subpop_k = int(kwargs.get("subpop_k", 0))
         self._peer_ptrs, self._own_X_ptr = [], None
         self.outlier_gen = int(kwargs.get("outlier_gen", 0))
         self.n_outlier_resets = 0
@@ -328,6 +335,21 @@ class DeMcMpi(object):
     def _dream_cfg(self):
         return dict(del_pairs=1, n_cr=1, burnin_gen=0, n_cr_gen=0, gamma_scale=1.0)
 
+    @property
+    def _subpop(self):
+        return self.subpop_k > 0 and self.comm.size > 1
+
+    @property
+    def _sharded(self):
+        """Several ranks stepping ONE population (replicas + exchange)."""
+        return self.comm.size > 1 and not self._subpop
+
+    def _local_range(self):
+        """Row range of this rank's chains inside self._X / self._lnl."""
+        if self._subpop:
+            return 0, len(self.rank_chain_ids)
+        return int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
+
     def _create_handle(self):
         d = self.dim
         self._ld = d if d <= 4 else ((d + 3) // 4) * 4
@@ -339,12 +361,19 @@ class DeMcMpi(object):
             if self.comm.size > 1:
                 self._seed = self._bcast_int(self._seed)
         dc = self._dream_cfg()
-        cfg = _lib.Config(algo=self._algo, n_chains=self.n_chains, dim=d, ld=self._ld,
+        if self._subpop:
+            # an island is a complete, unsharded population of its own with its own Philox key
+            n_eng, c_lo, c_hi = len(ids), 0, len(ids)
+            seed = (self._seed + 0x9E3779B97F4A7C15 * (self.comm.rank + 1)) % (1 << 64)
+        else:
+            n_eng, c_lo, c_hi, seed = self.n_chains, int(ids[0]), int(ids[-1]) + 1, self._seed
+        self._n_engine = n_eng
+        cfg = _lib.Config(algo=self._algo, n_chains=n_eng, dim=d, ld=self._ld,
                           del_pairs=dc["del_pairs"], n_cr=dc["n_cr"], burnin_gen=dc["burnin_gen"],
-                          n_cr_gen=dc["n_cr_gen"], shuffle=1, chain_lo=int(ids[0]),
-                          chain_hi=int(ids[-1]) + 1, device=self._device_index,
+                          n_cr_gen=dc["n_cr_gen"], shuffle=1, chain_lo=c_lo,
+                          chain_hi=c_hi, device=self._device_index,
                           gamma_scale=dc["gamma_scale"], flip=0.5, epsilon=0.0, u_epsilon=0.0,
-                          gamma=0.0, seed=self._seed)
+                          gamma=0.0, seed=seed)
         h = C.c_void_p()
         _lib.check(self._libh.bpm_create(C.byref(cfg), C.byref(h)))
         self._handle = h
@@ -392,7 +421,7 @@ class DeMcMpi(object):
         bpm_dev_alloc (a plain cudaMalloc block, so its IPC handle can be opened by the peers)
         and register every other rank's replica with the engine (bpm_set_peers)."""
         torch = _torch()
-        if self.comm.size == 1 or self._exchange != "p2p":
+        if not self._sharded or self._exchange != "p2p":
             return torch.zeros((N, ld), dtype=torch.float64, device=self._device)
         import torch.distributed as dist
         lib = self._libh
@@ -436,7 +465,7 @@ class DeMcMpi(object):
         """Make this half-phase's updates visible on every rank before the next one reads them.
         p2p: the rows are already in the peer replicas, only a barrier is needed (the CR
         all-reduce that follows the second half-phase of a DREAM generation is that barrier)."""
-        if self.comm.size == 1:
+        if not self._sharded:
             return
         if self._exchange == "p2p":
             if last and self._algo == _lib.BPM_ALGO_DREAM:
@@ -473,9 +502,12 @@ class DeMcMpi(object):
 
     def _set_population(self, x0, history=None):
         torch = _torch()
-        N, d, ld = self.n_chains, self.dim, self._ld
-        lo, hi = int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
+        N, d, ld = self._n_engine, self.dim, self._ld
+        lo, hi = self._local_range()
         nl = hi - lo
+        if self._subpop:          # x0 covers every chain of the job: keep this island's block
+            g0, g1 = int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
+            x0 = np.asarray(x0)[g0:g1]
         self._X = self._alloc_population(N, ld)
         self._X[:, :d] = torch.from_numpy(np.ascontiguousarray(x0)).to(self._device)
         if self.comm.size > 1:
@@ -496,6 +528,7 @@ class DeMcMpi(object):
         self.am_chains = _ChainList(self)
         self._lnl_valid = False
         self._mom_len = self._hist.length
+        self._gens_since_deal = 0
 
     def init_warmstart_chain(self, h5_file):
         """demc.py:46-51."""
@@ -504,7 +537,7 @@ class DeMcMpi(object):
 
     def _get_local_chain_state(self):
         """demc.py:53-57."""
-        lo, hi = int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
+        lo, hi = self._local_range()
         return self._X[lo:hi, :self.dim].cpu().numpy()
 
     # ------------------------------------------------------------------ C-ABI helpers
@@ -539,7 +572,7 @@ class DeMcMpi(object):
         burn-in), so ``rhat()`` and ``moment_estimates()`` cover only what follows.  The
         reference has no counterpart; note DREAM's CR adaptation then sees the standard
         deviation of the post-reset history only."""
-        lo, hi = int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
+        lo, hi = self._local_range()
         self._mean.copy_(self._X[lo:hi])
         self._m2.zero_()
         self._mom_len = 1
@@ -600,12 +633,12 @@ class DeMcMpi(object):
         n_reset = C.c_int32()
         stats = (C.c_double * 4)()
         st = self._state(None)
-        if self.comm.size == 1:
+        if not self._sharded:
             _lib.check(self._libh.bpm_outlier_reset(self._handle, C.byref(st), None, None,
                                                     C.byref(n_reset), stats, self._stream()))
         else:
             import torch.distributed as dist
-            lo, hi = int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
+            lo, hi = self._local_range()
             om = self._wrap_device(p.value, (self.n_chains,)) / float(cnt.value)
             self._allgather_rows(om, lo, hi)
             self._allgather_rows(self._lnl, lo, hi)
@@ -667,7 +700,7 @@ class DeMcMpi(object):
         return torch.from_numpy(vals).to(self._device)
 
     def _init_lnl(self):
-        lo, hi = int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
+        lo, hi = self._local_range()
         self._lnl[lo:hi] = self._eval_lnl_rows(self._X[lo:hi])
         self._lnl_valid = True
 
@@ -722,8 +755,10 @@ class DeMcMpi(object):
             if replay is not None:
                 self._replay_generation(st, replay[k_gen], k_gen + k_off, trace)
                 done = 1
-            elif mode == "device" and self.comm.size == 1:
+            elif mode == "device" and not self._sharded:
                 done = avail
+                if self._subpop:
+                    done = min(done, self.subpop_k - (self._gens_since_deal % self.subpop_k))
                 _lib.check(self._libh.bpm_step_generations(self._handle, C.byref(st), k_gen + k_off, done,
                                                            self._stream()))
             else:
@@ -732,6 +767,10 @@ class DeMcMpi(object):
             self._hist.advance(done)
             self._mom_len += done
             k_gen += done
+            if self._subpop:
+                self._gens_since_deal += done
+                if self._gens_since_deal % self.subpop_k == 0:
+                    self._redeal()
             if track_outliers and k_gen % self.outlier_gen == 0 and self._outlier_active(k_gen + k_off):
                 self.outlier_reset()
             if self.checkpoint > 0 and k_gen % self.checkpoint == 0:        # demc.py:138-140
@@ -783,7 +822,7 @@ class DeMcMpi(object):
             _lib.check(lib.bpm_accept(h, C.byref(st), phase, lnl_prop.data_ptr(), None, s))
             self._phase_exchange(last=last)
         _lib.check(lib.bpm_end_generation(h, C.byref(st), s))
-        if self.comm.size > 1 and self._algo == _lib.BPM_ALGO_DREAM:
+        if self._sharded and self._algo == _lib.BPM_ALGO_DREAM:
             self._allreduce_cr()
 
     def _wrap_device(self, ptr, shape):
@@ -802,8 +841,27 @@ class DeMcMpi(object):
 
     def _allgather_population(self):
         """comm.Allgather(current_chain_state) of demc.py:93,116 on the device replica."""
-        lo, hi = int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
+        lo, hi = self._local_range()
         self._allgather_rows(self._X, lo, hi)
+
+    def _redeal(self):
+        """Sub-population mode: re-deal the chains across the ranks.  Every rank cuts its chains
+        into G contiguous groups and sends group j to rank j (one all-to-all of states, cached
+        likelihoods and running moments), so afterwards every island holds 1/G of every island.
+        History rows stay with the slot, not with the travelling chain."""
+        torch = _torch()
+        import torch.distributed as dist
+        G, nl = self.comm.size, len(self.rank_chain_ids)
+        cuts = [b1 - b0 for b0, b1 in shard_bounds(nl, G)]
+        if len(set(len(np.array_split(np.arange(self.n_chains), G)[r]) for r in range(G))) != 1:
+            raise RuntimeError("subpop_k needs n_chains divisible by the number of ranks")
+        for t in (self._X, self._mean, self._m2):
+            out = torch.empty_like(t)
+            dist.all_to_all_single(out, t.contiguous(), output_split_sizes=cuts, input_split_sizes=cuts)
+            t.copy_(out)
+        out = torch.empty_like(self._lnl)
+        dist.all_to_all_single(out, self._lnl, output_split_sizes=cuts, input_split_sizes=cuts)
+        self._lnl.copy_(out)
 
     def _allreduce_cr(self):
         torch = _torch()
@@ -1034,5 +1092,5 @@ class DeMcMpi(object):
         """hist: (T, N, dim) array of every chain's history (what load_state reads)."""
         hist = np.asarray(hist, dtype=float)
         assert hist.shape[1] == self.n_chains and hist.shape[2] == self.dim
-        lo, hi = int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
+        lo, hi = self._local_range()
         self._set_population(hist[-1], history=hist[:, lo:hi, :])

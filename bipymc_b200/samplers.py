@@ -46,6 +46,7 @@ class DeMc(DeMcMpi):
         self._chunk_bytes = int(proposal_kwargs.get("history_chunk_bytes", 1 << 30))
         self._reserve_rows = int(proposal_kwargs.get("history_reserve", 0))
         self._exchange = proposal_kwargs.get("exchange", "p2p")
+        self.subpop_k = 0
         self._peer_ptrs, self._own_X_ptr = [], None
         self.outlier_gen, self.n_outlier_resets = 0, 0
         self._setup_device()
