@@ -970,55 +970,6 @@ __device__ __forceinline__ void tile_stage_propose_v3(const PhaseArgs& a, const 
   }
 }
 
-// write-back for d % 4 == 0: all global loads of a chain row are issued before the Welford math
-__device__ __forceinline__ void tile_stage_writeback_v3(const PhaseArgs& a, const TileScratch& T,
-                                                        const double* __restrict__ P, int pld, int gwarp,
-                                                        int gwarps, int lane) {
-  if (4 * lane >= a.d) return;
-  const bool keep = a.mean != nullptr || a.hist_row != nullptr;
-  for (int row = gwarp; row < kTileRows; row += gwarps) {
-    const int c = T.cid[row];
-    if (c < 0) continue;
-    const int acc = T.acc[row];
-    if (!acc && !keep) continue;
-    double* xc = a.X + (size_t)c * a.ld + 4 * lane;
-    const size_t o = (size_t)(c - a.chain_lo) * a.ld + 4 * lane;
-    double2 m0, m1, v0, v1;
-    if (a.mean) {
-      m0 = ld_stream2(a.mean + o); m1 = ld_stream2(a.mean + o + 2);
-      v0 = ld_stream2(a.m2 + o); v1 = ld_stream2(a.m2 + o + 2);
-    }
-    double s[4];
-    if (acc) {
-      const double* prow = P + row * pld + 4 * lane;
-      const double2 p0 = *reinterpret_cast<const double2*>(prow);
-      const double2 p1 = *reinterpret_cast<const double2*>(prow + 2);
-      s[0] = p0.x; s[1] = p0.y; s[2] = p1.x; s[3] = p1.y;
-      *reinterpret_cast<double2*>(xc) = make_double2(s[0], s[1]);
-      *reinterpret_cast<double2*>(xc + 2) = make_double2(s[2], s[3]);
-      store_peers4(a, (size_t)c * a.ld + 4 * lane, s[0], s[1], s[2], s[3]);
-    } else {
-      const double2 u0 = ldg2(xc), u1 = ldg2(xc + 2);
-      s[0] = u0.x; s[1] = u0.y; s[2] = u1.x; s[3] = u1.y;
-    }
-    if (a.mean) {
-      welford_update(s[0], a.inv_n1, m0.x, v0.x);
-      welford_update(s[1], a.inv_n1, m0.y, v0.y);
-      welford_update(s[2], a.inv_n1, m1.x, v1.x);
-      welford_update(s[3], a.inv_n1, m1.y, v1.y);
-      st_stream2(a.mean + o, m0.x, m0.y);
-      st_stream2(a.mean + o + 2, m1.x, m1.y);
-      st_stream2(a.m2 + o, v0.x, v0.y);
-      st_stream2(a.m2 + o + 2, v1.x, v1.y);
-    }
-    if (a.hist_row) {
-      st_stream2(a.hist_row + o, s[0], s[1]);
-      st_stream2(a.hist_row + o + 2, s[2], s[3]);
-    }
-  }
-}
-
-
 // ---- mbarrier helpers (CTA scope): variant 3 hands tiles over with these so that no producer
 // warp ever waits for another producer warp -------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -1239,9 +1190,7 @@ fused_gauss_v3_kernel(const PhaseArgs a, const GaussArgs g) {
 
   if (warp < kV3ConsWarps) {
     // ------------------------------ consumers ------------------------------------------
-#ifndef BPM_V3_EQUAL_REGS
     asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
-#endif
     unsigned n_acc = 0, n_rej = 0;
     for (int i = 0; i < n_my; ++i) {
       const int b = i & 1;
@@ -1264,9 +1213,7 @@ fused_gauss_v3_kernel(const PhaseArgs a, const GaussArgs g) {
     // ------------------------------ producers ------------------------------------------
     // each warp is an independent pipeline over ITS rows: draws + L2 prefetch of tile i+1 |
     // proposal of tile i | write-back of tile i-1; it synchronises only with the consumers
-#ifndef BPM_V3_EQUAL_REGS
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-#endif
     const int pw = warp - kV3ConsWarps;
     if (n_my > 0)
       warp_stage_draws<REPLAY>(a, L, tb, *reinterpret_cast<TileScratch*>(Tbuf), g_lo, g_hi, pw, lane);

@@ -401,6 +401,21 @@ class DeMcMpi(object):
         except Exception:
             pass
 
+    def close(self):
+        """Release the engine handle and (sharded runs) the peer mappings.  Collective when the
+        population is sharded over peer memory: every rank must call it, because a rank's
+        replica must not disappear while a peer kernel may still store into it."""
+        torch = _torch()
+        if getattr(self, "_handle", None) is None:
+            return
+        torch.cuda.synchronize(self._device)
+        if self._sharded and self._peer_ptrs:
+            import torch.distributed as dist
+            dist.barrier()
+        self._release_peer_memory()
+        self._libh.bpm_destroy(self._handle)
+        self._handle = None
+
     # ------------------------------------------------------------------ peer memory
     def _release_peer_memory(self):
         lib = getattr(self, "_libh", None)
