@@ -54,11 +54,15 @@ struct bpm_engine {
   // workspace (device)
   int32_t* perm = nullptr;
   int32_t* flip = nullptr;
-  int32_t* loc_list = nullptr;   // sharded: local chains of both halves, compacted (kernels_generic.cuh)
+  int32_t* inv = nullptr;        // inverse permutation (only when the packed lists are in use)
+  int32_t* loc_list = nullptr;   // local chains of both halves, packed in chain order (kernels_generic.cuh)
   int32_t* loc_cnt = nullptr;    // [2]
   int32_t* cmp_blk = nullptr;    // [2][nblk][2] block counts / offsets
   bool serial() const { return cfg.algo == BPM_ALGO_DEMC_SERIAL; }
   bool sharded() const { return cfg.chain_lo != 0 || cfg.chain_hi != cfg.n_chains; }
+  // packed, chain-ordered phase lists: always when sharded; unsharded for the 16/24/32-byte rows
+  // of d <= 4, where list order would waste half of every sector (serial DE-MC walks chains in order anyway)
+  bool packed() const { return sharded() || (cfg.dim <= 4 && !serial()); }
   double* prop = nullptr;
   double* lnl_prop = nullptr;
   double* cr_delta = nullptr;
@@ -126,7 +130,7 @@ struct bpm_engine {
   }
 
   ~bpm_engine() {
-    cudaFree(loc_list); cudaFree(loc_cnt); cudaFree(cmp_blk); cudaFree(cr_ticket);
+    cudaFree(inv); cudaFree(loc_list); cudaFree(loc_cnt); cudaFree(cmp_blk); cudaFree(cr_ticket);
     cudaFree(perm); cudaFree(flip); cudaFree(prop); cudaFree(lnl_prop); cudaFree(cr_delta);
     cudaFree(cr_pick); cudaFree(p_cr); cudaFree(cr_dm); cudaFree(cr_cnt); cudaFree(cr_part); cudaFree(cr_block);
     cudaFree(counters); cudaFree(nan_flag); cudaFree(tparams); cudaFree(hX); cudaFree(hL);
@@ -142,8 +146,9 @@ struct bpm_engine {
     CU_TRY(cudaSetDevice(cfg.device));
     CU_TRY(cudaMalloc(&perm, sizeof(int32_t) * N));
     CU_TRY(cudaMalloc(&flip, sizeof(int32_t)));
-    if (sharded()) {
-      const int nblk = cdiv(N, bpm::kCompactBlock);
+    if (packed()) {
+      const int nblk = cdiv(cfg.chain_hi - cfg.chain_lo, bpm::kCompactBlock);
+      CU_TRY(cudaMalloc(&inv, sizeof(int32_t) * N));
       CU_TRY(cudaMalloc(&loc_list, sizeof(int32_t) * N));
       CU_TRY(cudaMalloc(&loc_cnt, sizeof(int32_t) * 2));
       CU_TRY(cudaMalloc(&cmp_blk, sizeof(int32_t) * 4 * nblk));
@@ -224,20 +229,20 @@ struct bpm_engine {
     const int N = cfg.n_chains;
     prof_begin(0, s);
     if (serial()) {
-      bpm::identity_split_kernel<<<cdiv(N, 256), 256, 0, s>>>(perm, flip, N);
+      bpm::identity_split_kernel<<<cdiv(N, 256), 256, 0, s>>>(perm, inv, flip, N);
     } else if (rp) {
       CU_TRY(cudaMemcpyAsync(perm, rp->shuffle_idx, sizeof(int32_t) * N, cudaMemcpyDeviceToDevice, s));
       bpm::set_flag_kernel<<<1, 1, 0, s>>>(flip, rp->flip ? 1 : 0);
+      if (inv) bpm::invert_perm_kernel<<<cdiv(N, 256), 256, 0, s>>>(perm, inv, N);
     } else {
       bpm::RngCtx rng = bpm::make_rng(cfg.seed, (uint64_t)st->hist_len);
-      bpm::split_native_kernel<<<cdiv(N, 256), 256, 0, s>>>(perm, flip, N, cfg.shuffle, cfg.flip, rng);
+      bpm::split_native_kernel<<<cdiv(N, 256), 256, 0, s>>>(perm, inv, flip, N, cfg.shuffle, cfg.flip, rng);
     }
-    if (sharded()) {
-      const int nblk = cdiv(N, bpm::kCompactBlock);
-      bpm::compact_count_kernel<<<nblk, bpm::kCompactThreads, 0, s>>>(perm, N, nA, cfg.chain_lo, cfg.chain_hi,
-                                                                     cmp_blk);
+    if (packed()) {
+      const int nblk = cdiv(cfg.chain_hi - cfg.chain_lo, bpm::kCompactBlock);
+      bpm::compact_count_kernel<<<nblk, bpm::kCompactThreads, 0, s>>>(inv, nA, cfg.chain_lo, cfg.chain_hi, cmp_blk);
       bpm::compact_scan_kernel<<<1, 1024, 0, s>>>(cmp_blk, nblk, cmp_blk + 2 * nblk, loc_cnt);
-      bpm::compact_write_kernel<<<nblk, bpm::kCompactThreads, 0, s>>>(perm, N, nA, cfg.chain_lo, cfg.chain_hi,
+      bpm::compact_write_kernel<<<nblk, bpm::kCompactThreads, 0, s>>>(inv, nA, cfg.chain_lo, cfg.chain_hi,
                                                                      cmp_blk + 2 * nblk, loc_list);
     }
     prof_end(s);
@@ -656,7 +661,7 @@ int bpm_propose(bpm_handle h, bpm_state* st, int32_t phase, double** prop, int32
     CU_TRY(cudaMemcpy(&f, h->flip, sizeof(f), cudaMemcpyDeviceToHost));
     const bool first = ((phase ^ (f != 0)) == 0);
     *n_phase = first ? h->nA : h->cfg.n_chains - h->nA;
-    if (h->sharded()) {   // only this rank's chains of the half were proposed, densely packed
+    if (h->packed()) {    // only this rank's chains of the half were proposed, densely packed
       int32_t cnt[2];
       CU_TRY(cudaMemcpy(cnt, h->loc_cnt, sizeof(cnt), cudaMemcpyDeviceToHost));
       *n_phase = cnt[first ? 0 : 1];

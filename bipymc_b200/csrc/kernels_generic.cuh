@@ -16,8 +16,8 @@ constexpr int kMaxBlocksPerLane = 8;  // d <= 4 * 8 * LPC  (1024 at LPC = 32)
 constexpr int kThreads = 256;
 
 // ---- demc.py:81-100: flip coin + shuffled split (native RNG) ----------------------
-__global__ void split_native_kernel(int32_t* __restrict__ perm, int32_t* __restrict__ flip, int N,
-                                    int shuffle, double flip_p, RngCtx rng) {
+__global__ void split_native_kernel(int32_t* __restrict__ perm, int32_t* __restrict__ inv,
+                                    int32_t* __restrict__ flip, int N, int shuffle, double flip_p, RngCtx rng) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j == 0) {
     Philox4 q = draw4(rng, 0xFFFFFFFFu, RNG_GEN, 0);
@@ -25,27 +25,40 @@ __global__ void split_native_kernel(int32_t* __restrict__ perm, int32_t* __restr
     *flip = u53(q.x, q.y) < thr ? 1 : 0;
   }
   if (j >= N) return;
+  int32_t c = j;
   if (shuffle) {
     FeistelKey f = make_feistel(rng, (uint32_t)N);
-    perm[j] = (int32_t)feistel_perm(f, (uint32_t)j);
-  } else {
-    perm[j] = j;
+    c = (int32_t)feistel_perm(f, (uint32_t)j);
   }
+  perm[j] = c;
+  if (inv) inv[c] = j;        // list position of chain c (used to pack the phase lists in chain order)
+}
+__global__ void invert_perm_kernel(const int32_t* __restrict__ perm, int32_t* __restrict__ inv, int N) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < N) inv[perm[j]] = j;
 }
 
 __global__ void set_flag_kernel(int32_t* flag, int32_t v) { *flag = v; }
-__global__ void identity_split_kernel(int32_t* __restrict__ perm, int32_t* __restrict__ flip, int N) {
+__global__ void identity_split_kernel(int32_t* __restrict__ perm, int32_t* __restrict__ inv,
+                                      int32_t* __restrict__ flip, int N) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j == 0) *flip = 0;
-  if (j < N) perm[j] = j;
+  if (j < N) {
+    perm[j] = j;
+    if (inv) inv[j] = j;
+  }
 }
 
-// ---- sharded ranks: ordered compaction of the chains this rank owns -----------------
+// ---- packed phase lists: the chains this rank owns, per half, in CHAIN order ----------
 // A rank steps only its own chains (demc.py:103-107 loops over the local ids and tests
 // `c_id in a_ids`).  Walking the global half-lists and skipping foreign chains would leave
 // every 64-chain tile 1/G full on G GPUs, so each generation the local members of the two
-// halves are packed (in list order, deterministically) into loc_list with three small
-// kernels: per-block counts, a one-block scan of the block counts, per-block write.
+// halves are packed into loc_list with three small kernels (per-block counts, a one-block
+// scan, per-block write) that walk the LOCAL chains c in [lo, hi) in ascending order and
+// look their half up in the inverse permutation.  Chain order also makes every per-chain
+// access of a phase kernel (own row, moments, cached lnL, CR slots) monotone in memory, which
+// is what the 16-byte rows of the d <= 4 targets need to share 32-byte sectors; unsharded
+// small-d handles use the packed lists for that reason alone.
 constexpr int kCompactThreads = 256, kCompactPer = 8, kCompactBlock = kCompactThreads * kCompactPer;
 // exclusive prefix sums of (xa, xb) over the threads of a block (NT <= 1024), warp shuffles + one smem hop
 template <int NT>
@@ -75,26 +88,23 @@ __device__ __forceinline__ void block_excl_scan2(int xa, int xb, int& ea, int& e
   tota = wa[NT / 32 - 1];
   totb = wb[NT / 32 - 1];
 }
-__device__ __forceinline__ void compact_flags(const int32_t* __restrict__ perm, int N, int nA, int lo, int hi,
-                                              int j0, int& cA, int& cB, unsigned& mA, unsigned& mB) {
+__device__ __forceinline__ void compact_flags(const int32_t* __restrict__ inv, int nA, int hi, int c0, int& cA,
+                                              int& cB, unsigned& mA, unsigned& mB) {
   cA = cB = 0; mA = mB = 0u;
 #pragma unroll
   for (int k = 0; k < kCompactPer; ++k) {
-    const int j = j0 + k;
-    if (j < N) {
-      const int c = perm[j];
-      if (c >= lo && c < hi) {
-        if (j < nA) { ++cA; mA |= 1u << k; } else { ++cB; mB |= 1u << k; }
-      }
+    const int c = c0 + k;
+    if (c < hi) {
+      if (inv[c] < nA) { ++cA; mA |= 1u << k; } else { ++cB; mB |= 1u << k; }
     }
   }
 }
-__global__ void __launch_bounds__(kCompactThreads) compact_count_kernel(const int32_t* __restrict__ perm, int N,
+__global__ void __launch_bounds__(kCompactThreads) compact_count_kernel(const int32_t* __restrict__ inv,
                                                                         int nA, int lo, int hi,
                                                                         int32_t* __restrict__ blk_cnt) {
   __shared__ int sa[kCompactThreads / 32], sb[kCompactThreads / 32];
   int cA, cB; unsigned mA, mB;
-  compact_flags(perm, N, nA, lo, hi, blockIdx.x * kCompactBlock + threadIdx.x * kCompactPer, cA, cB, mA, mB);
+  compact_flags(inv, nA, hi, lo + blockIdx.x * kCompactBlock + threadIdx.x * kCompactPer, cA, cB, mA, mB);
   cA = __reduce_add_sync(0xFFFFFFFFu, cA);
   cB = __reduce_add_sync(0xFFFFFFFFu, cB);
   if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = cA; sb[threadIdx.x >> 5] = cB; }
@@ -122,21 +132,21 @@ __global__ void __launch_bounds__(1024) compact_scan_kernel(const int32_t* __res
     ra += blk_cnt[2 * b]; rb += blk_cnt[2 * b + 1];
   }
 }
-__global__ void __launch_bounds__(kCompactThreads) compact_write_kernel(const int32_t* __restrict__ perm, int N,
+__global__ void __launch_bounds__(kCompactThreads) compact_write_kernel(const int32_t* __restrict__ inv,
                                                                         int nA, int lo, int hi,
                                                                         const int32_t* __restrict__ blk_off,
                                                                         int32_t* __restrict__ loc_list) {
-  const int j0 = blockIdx.x * kCompactBlock + threadIdx.x * kCompactPer;
+  const int c0 = lo + blockIdx.x * kCompactBlock + threadIdx.x * kCompactPer;
   int cA, cB; unsigned mA, mB;
-  compact_flags(perm, N, nA, lo, hi, j0, cA, cB, mA, mB);
+  compact_flags(inv, nA, hi, c0, cA, cB, mA, mB);
   int ea, eb, ta, tb;
   block_excl_scan2<kCompactThreads>(cA, cB, ea, eb, ta, tb);
   int oa = blk_off[2 * blockIdx.x] + ea;
   int ob = nA + blk_off[2 * blockIdx.x + 1] + eb;
 #pragma unroll
   for (int k = 0; k < kCompactPer; ++k) {
-    if (mA & (1u << k)) loc_list[oa++] = perm[j0 + k];
-    if (mB & (1u << k)) loc_list[ob++] = perm[j0 + k];
+    if (mA & (1u << k)) loc_list[oa++] = c0 + k;
+    if (mB & (1u << k)) loc_list[ob++] = c0 + k;
   }
 }
 
