@@ -18,11 +18,11 @@
 
 namespace bpm {
 
-constexpr int kGdM = 64, kGdN = 128, kGdK = 16, kGdStages = 3;
+constexpr int kGdN = 128, kGdK = 16, kGdStages = 3;     // CTA tile: (16 MT) rows x 128 columns
 constexpr int kGdLda = kGdK + 4;      // 20: (4 row + k) mod 16 distinct over a half warp
 constexpr int kGdLdb = kGdN + 4;      // 132
 constexpr int kGdThreads = 256;
-constexpr size_t kGdStageDoubles = (size_t)kGdM * kGdLda + (size_t)kGdK * kGdLdb;
+__host__ __device__ constexpr size_t gd_stage_doubles(int M) { return (size_t)M * kGdLda + (size_t)kGdK * kGdLdb; }
 
 __device__ __forceinline__ void gd_cp16(void* dst, const void* src, bool ok) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
@@ -34,18 +34,21 @@ __device__ __forceinline__ void gd_dmma(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// requires d % 2 == 0, r % 2 == 0, ld % 2 == 0 (16-byte chunks)
-template <bool CENTER>
+// requires d % 2 == 0, r % 2 == 0, ld % 2 == 0 (16-byte chunks).  MT = DMMA m-tiles per warp: 4 -> 64-row
+// CTAs (best reuse), 2 -> 32-row CTAs for launches too small to give every SM two 64-row CTAs.
+template <bool CENTER, int MT>
 __global__ void __launch_bounds__(kGdThreads, 2)
 gauss_dmma_kernel(const double* __restrict__ P, int n, int ld, int d, int r, const double* __restrict__ mu,
                   const double* __restrict__ W, double c0, int log_of_pdf, double* __restrict__ out) {
+  constexpr int kGdM = 16 * MT;
+  constexpr size_t kGdStageDoubles = gd_stage_doubles(kGdM);
   extern __shared__ __align__(16) double gsm[];
   double* mus = gsm;                                           // [dpad]
   const int dpad = (d + kGdK - 1) / kGdK * kGdK;
   double* ring = gsm + dpad;
   double* red = ring + kGdStages * kGdStageDoubles;            // [4][64] row sums per column-warp
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wr = warp >> 2, wc = warp & 3;                     // warp tile: rows 32 wr, cols 32 wc
+  const int wr = warp >> 2, wc = warp & 3;                     // warp tile: rows 8 MT wr, cols 32 wc
   const int lq = lane >> 2, lk = lane & 3;
   const int m0 = blockIdx.x * kGdM;
   if (CENTER)
@@ -79,15 +82,15 @@ gauss_dmma_kernel(const double* __restrict__ P, int n, int ld, int d, int r, con
 
   issue(0);
   issue(1);
-  double rs[4][1];                                             // per m-tile partial row sums of this lane
+  double rs[MT][1];                                            // per m-tile partial row sums of this lane
 #pragma unroll
-  for (int i = 0; i < 4; ++i) rs[i][0] = 0.0;
-  double acc[4][4][2];
+  for (int i = 0; i < MT; ++i) rs[i][0] = 0.0;
+  double acc[MT][4][2];
   for (int step = 0; step < total; ++step) {
     const int cb = step / nkt, kt = step - cb * nkt;
     if (kt == 0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < MT; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     }
@@ -98,22 +101,22 @@ gauss_dmma_kernel(const double* __restrict__ P, int n, int ld, int d, int r, con
     const double* Bs = As + (size_t)kGdM * kGdLda;
 #pragma unroll
     for (int k4 = 0; k4 < kGdK / 4; ++k4) {
-      double af[4], bf[4];
+      double af[MT], bf[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        af[i] = As[(32 * wr + 8 * i + lq) * kGdLda + 4 * k4 + lk];
+      for (int i = 0; i < MT; ++i) {
+        af[i] = As[(8 * MT * wr + 8 * i + lq) * kGdLda + 4 * k4 + lk];
         if (CENTER) af[i] = __dsub_rn(af[i], mus[kt * kGdK + 4 * k4 + lk]);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) bf[j] = Bs[(4 * k4 + lk) * kGdLdb + 32 * wc + 8 * j + lq];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < MT; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) gd_dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
     if (kt == nkt - 1) {                                       // column block finished: fold its squares
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < MT; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           rs[i][0] = fma(acc[i][j][0], acc[i][j][0], rs[i][0]);
@@ -124,11 +127,11 @@ gauss_dmma_kernel(const double* __restrict__ P, int n, int ld, int d, int r, con
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   // quad lanes hold disjoint columns of the same rows; then the 4 column-warps of a row group
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < MT; ++i) {
     double v = rs[i][0];
     v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
     v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
-    if (lk == 0) red[wc * kGdM + 32 * wr + 8 * i + lq] = v;
+    if (lk == 0) red[wc * kGdM + 8 * MT * wr + 8 * i + lq] = v;
   }
   __syncthreads();
   if (tid < kGdM) {
@@ -143,27 +146,32 @@ gauss_dmma_kernel(const double* __restrict__ P, int n, int ld, int d, int r, con
   }
 }
 
-inline size_t gauss_dmma_smem(int d) {
+inline size_t gauss_dmma_smem(int d, int M) {
   const int dpad = (d + kGdK - 1) / kGdK * kGdK;
-  return sizeof(double) * ((size_t)dpad + kGdStages * kGdStageDoubles + 4 * kGdM);
+  return sizeof(double) * ((size_t)dpad + kGdStages * gd_stage_doubles(M) + 4 * (size_t)M);
 }
 inline bool gauss_dmma_supported(int d, int r, int ld) { return (d % 2) == 0 && (r % 2) == 0 && (ld % 2) == 0 && d >= 16; }
 
+template <bool CENTER, int MT>
+inline int launch_gauss_dmma_t(const double* P, int n, int ld, int d, int r, const double* mu, const double* W,
+                               double c0, int log_of_pdf, double* out, cudaStream_t s) {
+  constexpr int M = 16 * MT;
+  const size_t sm = gauss_dmma_smem(d, M);
+  cudaError_t e = cudaFuncSetAttribute(gauss_dmma_kernel<CENTER, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) return 1;
+  gauss_dmma_kernel<CENTER, MT><<<(n + M - 1) / M, kGdThreads, sm, s>>>(P, n, ld, d, r, mu, W, c0, log_of_pdf, out);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 inline int launch_gauss_dmma(const double* P, int n, int ld, int d, int r, const double* mu, const double* W,
                              double c0, int log_of_pdf, int mu_is_zero, double* out, cudaStream_t s) {
-  const size_t sm = gauss_dmma_smem(d);
-  const int grid = (n + kGdM - 1) / kGdM;
-  cudaError_t e;
-  if (mu_is_zero) {
-    e = cudaFuncSetAttribute(gauss_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    if (e != cudaSuccess) return 1;
-    gauss_dmma_kernel<false><<<grid, kGdThreads, sm, s>>>(P, n, ld, d, r, mu, W, c0, log_of_pdf, out);
-  } else {
-    e = cudaFuncSetAttribute(gauss_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    if (e != cudaSuccess) return 1;
-    gauss_dmma_kernel<true><<<grid, kGdThreads, sm, s>>>(P, n, ld, d, r, mu, W, c0, log_of_pdf, out);
-  }
-  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+  // 64-row CTAs once there are enough of them to put two on every SM, else 32-row CTAs
+  const bool small = (n + 63) / 64 < 2 * 148;
+  if (mu_is_zero)
+    return small ? launch_gauss_dmma_t<false, 2>(P, n, ld, d, r, mu, W, c0, log_of_pdf, out, s)
+                 : launch_gauss_dmma_t<false, 4>(P, n, ld, d, r, mu, W, c0, log_of_pdf, out, s);
+  return small ? launch_gauss_dmma_t<true, 2>(P, n, ld, d, r, mu, W, c0, log_of_pdf, out, s)
+               : launch_gauss_dmma_t<true, 4>(P, n, ld, d, r, mu, W, c0, log_of_pdf, out, s);
 }
 
 }  // namespace bpm
