@@ -452,14 +452,22 @@ __global__ void __launch_bounds__(256) cr_update_kernel(const double* __restrict
   if (n_cr <= 4) {
     // one pass over the block's chains, the (at most four) CR classes in registers
     double s[4] = {0.0, 0.0, 0.0, 0.0}, k[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
-      const int m = cr_pick[c];
-      if (m >= 0) {
-        const double v = cr_delta[c];
+    // eight independent (pick, statistic) loads in flight per thread, folded in chain order
+    for (int base = c0; base < c1; base += 8 * 256) {
+      int mm[8];
+      double vv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = base + u * 256 + (int)threadIdx.x;
+        const bool ok = c < c1;
+        mm[u] = ok ? cr_pick[c] : -1;
+        vv[u] = ok ? cr_delta[c] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (m == q) { s[q] += v; k[q] += 1.0; }
-      }
+          if (mm[u] == q) { s[q] += vv[u]; k[q] += 1.0; }
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
