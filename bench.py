@@ -260,15 +260,20 @@ def run_ours(args):
         for i in range(2):
             _lib.check(lib.bpm_generations_host(h, Xh.data_ptr(), Lh.data_ptr(), k_done + i, g0 + i, 1))
         torch.cuda.synchronize(dev)
+        d2h, b = 0, C.c_uint64()
         t0 = time.perf_counter()
         for i in range(ke):
             _lib.check(lib.bpm_generations_host(h, Xh.data_ptr(), Lh.data_ptr(), k_done + 2 + i, g0 + 2 + i, 1))
+            lib.bpm_last_d2h_bytes(h, C.byref(b))
+            d2h += b.value
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         nb = N * s._ld * 8 + N * 8
-        e2e = {"value": N * ke / dt, "unit": UNIT, "h2d_bytes_per_step": nb, "d2h_bytes_per_step": nb,
+        e2e = {"value": N * ke / dt, "unit": UNIT, "h2d_bytes_per_step": nb, "d2h_bytes_per_step": d2h / ke,
                "steps": ke, "ms_per_step": 1e3 * dt / ke,
-               "note": "bpm_generations_host: pinned host population -> H2D -> one generation -> D2H, every step"}
+               "note": "bpm_generations_host: pinned host population -> H2D (all chains) -> one generation -> "
+                       "the device stores the rows of the chains that moved (and their lnL) back into the "
+                       "pinned host arrays, every step; the host arrays hold the full updated population"}
 
     if world > 1 and not args.no_e2e and args.subpop_k == 0:
         # sharded end-to-end step: every rank copies ITS shard (states + cached likelihoods) in from

@@ -94,6 +94,10 @@ struct bpm_engine {
   // host-entry buffers
   double* hX = nullptr;
   double* hL = nullptr;
+  int32_t* h_accept = nullptr;   // host entry: accept flags of a generation / rows that moved in this call
+  int32_t* h_changed = nullptr;
+  unsigned long long* h_nrows = nullptr;
+  uint64_t last_d2h_bytes = 0;
   int fused_ok = 1;  // allow the fused fast paths
   double* peers[BPM_MAX_PEERS] = {nullptr};   // other ranks' X replicas mapped here (bpm_set_peers)
   int n_peers = 0;
@@ -134,6 +138,7 @@ struct bpm_engine {
     cudaFree(perm); cudaFree(flip); cudaFree(prop); cudaFree(lnl_prop); cudaFree(cr_delta);
     cudaFree(cr_pick); cudaFree(p_cr); cudaFree(cr_dm); cudaFree(cr_cnt); cudaFree(cr_part); cudaFree(cr_block);
     cudaFree(counters); cudaFree(nan_flag); cudaFree(tparams); cudaFree(hX); cudaFree(hL);
+    cudaFree(h_accept); cudaFree(h_changed); cudaFree(h_nrows);
     cudaFree(omega_sum); cudaFree(omega_buf); cudaFree(diag_out); cudaFree(diag_i); cudaFree(sort_tmp);
     cudaFree(rh_mean); cudaFree(rh_m2); cudaFree(rh_out);
     for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -714,11 +719,27 @@ int bpm_generations_host(bpm_handle h, double* X_host, double* lnl_host, int64_t
   if (h->cfg.chain_lo != 0 || h->cfg.chain_hi != h->cfg.n_chains)
     return fail("host entry is single-rank");
   CU_TRY(cudaSetDevice(h->cfg.device));
-  const size_t nx = sizeof(double) * (size_t)h->cfg.n_chains * h->cfg.ld;
-  const size_t nl = sizeof(double) * (size_t)h->cfg.n_chains;
+  const int N = h->cfg.n_chains;
+  const size_t nx = sizeof(double) * (size_t)N * h->cfg.ld;
+  const size_t nl = sizeof(double) * (size_t)N;
   if (!h->hX) {
     CU_TRY(cudaMalloc(&h->hX, nx));
     CU_TRY(cudaMalloc(&h->hL, nl));
+    CU_TRY(cudaMalloc(&h->h_accept, sizeof(int32_t) * N));
+    CU_TRY(cudaMalloc(&h->h_changed, sizeof(int32_t) * N));
+    CU_TRY(cudaMalloc(&h->h_nrows, sizeof(unsigned long long)));
+  }
+  // pinned (mapped) host buffers can be written by the device directly: only rows that moved go back
+  double *X_map = nullptr, *L_map = nullptr;
+  {
+    cudaPointerAttributes ax, al;
+    if (cudaPointerGetAttributes(&ax, X_host) == cudaSuccess && cudaPointerGetAttributes(&al, lnl_host) == cudaSuccess &&
+        ax.type == cudaMemoryTypeHost && al.type == cudaMemoryTypeHost && ax.devicePointer && al.devicePointer) {
+      X_map = (double*)ax.devicePointer;
+      L_map = (double*)al.devicePointer;
+    } else {
+      cudaGetLastError();
+    }
   }
   cudaStream_t s = 0;
   CU_TRY(cudaMemcpyAsync(h->hX, X_host, nx, cudaMemcpyHostToDevice, s));
@@ -726,10 +747,37 @@ int bpm_generations_host(bpm_handle h, double* X_host, double* lnl_host, int64_t
   bpm_state st;
   memset(&st, 0, sizeof(st));
   st.X = h->hX; st.lnl = h->hL; st.hist_len = g_abs0;
-  for (int g = 0; g < n_gen; ++g) BPM_TRY(h->generation<false>(&st, k_gen0 + g, nullptr, nullptr, s));
-  CU_TRY(cudaMemcpyAsync(X_host, h->hX, nx, cudaMemcpyDeviceToHost, s));
-  CU_TRY(cudaMemcpyAsync(lnl_host, h->hL, nl, cudaMemcpyDeviceToHost, s));
-  CU_TRY(cudaStreamSynchronize(s));
+  bpm_trace_out tr;
+  memset(&tr, 0, sizeof(tr));
+  tr.accept = h->h_accept;
+  if (X_map) {
+    CU_TRY(cudaMemsetAsync(h->h_changed, 0, sizeof(int32_t) * N, s));
+    CU_TRY(cudaMemsetAsync(h->h_nrows, 0, sizeof(unsigned long long), s));
+  }
+  for (int g = 0; g < n_gen; ++g) {
+    BPM_TRY(h->generation<false>(&st, k_gen0 + g, nullptr, X_map ? &tr : nullptr, s));
+    if (X_map) bpm::or_flags_kernel<<<cdiv(N, 256), 256, 0, s>>>(h->h_changed, h->h_accept, N);
+  }
+  if (X_map) {
+    bpm::scatter_changed_rows_kernel<<<cdiv((int64_t)N * 32, 256), 256, 0, s>>>(h->hX, h->hL, h->h_changed, X_map,
+                                                                               L_map, N, h->cfg.ld, h->h_nrows);
+    CU_TRY(cudaGetLastError());
+    unsigned long long rows = 0;
+    CU_TRY(cudaMemcpyAsync(&rows, h->h_nrows, sizeof(rows), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    h->last_d2h_bytes = rows * (sizeof(double) * (h->cfg.ld + 1)) + sizeof(rows);
+  } else {
+    CU_TRY(cudaMemcpyAsync(X_host, h->hX, nx, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(lnl_host, h->hL, nl, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    h->last_d2h_bytes = nx + nl;
+  }
+  return 0;
+}
+
+int bpm_last_d2h_bytes(bpm_handle h, uint64_t* bytes) {
+  if (!h || !bytes) return fail("null argument");
+  *bytes = h->last_d2h_bytes;
   return 0;
 }
 

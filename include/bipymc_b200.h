@@ -217,6 +217,10 @@ int bpm_set_peers(bpm_handle h, double* const* peer_X, int32_t n_peers);
  * history, copies the result back.  Synchronous. */
 int bpm_generations_host(bpm_handle h, double* X_host, double* lnl_host, int64_t k_gen0,
                          int64_t g_abs0, int32_t n_gen);
+/* When both host arrays are pinned (device-mapped) memory, bpm_generations_host writes back only
+ * the rows of chains that moved (the device stores them straight into the host arrays; rows of
+ * chains that did not move are already correct there).  Bytes the last call moved device->host. */
+int bpm_last_d2h_bytes(bpm_handle h, uint64_t* bytes);
 
 /* Rebuild running moments from a stored history (load_state / warm start). */
 int bpm_moments_from_history(bpm_handle h, bpm_state* st, bpm_stream stream);

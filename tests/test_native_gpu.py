@@ -376,3 +376,40 @@ def test_large_d_quadratic_form_matches_numpy(dim, n, shift):
     got = s._eval_lnl_rows(rows).cpu().numpy()
     want = np.array([t.ln_like(x) for x in X])
     np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-10)
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_buffer_entry_equals_device_resident_generations(pinned):
+    """bpm_generations_host (the end-to-end entry: HOST population in, HOST population out) must
+    leave exactly the population a device-resident run produces -- both with pinned buffers (only
+    the rows that moved are written back by the device) and with pageable ones (full copy)."""
+    import ctypes as C
+    import torch
+    from bipymc_b200 import DreamMpi, targets, _lib
+    N, d, G = 4096, 100, 5
+    tgt = targets.Gauss_100D()
+    np.random.seed(1)
+    a = DreamMpi(tgt.ln_like, np.zeros(d), n_chains=N, seed=8, varepsilon=1.0, history="none", burnin_gen=0)
+    np.random.seed(1)
+    b = DreamMpi(tgt.ln_like, np.zeros(d), n_chains=N, seed=8, varepsilon=1.0, history="none", burnin_gen=0)
+    b.run_mcmc(N)                                   # sets run parameters, evaluates the initial likelihoods
+    Xh = torch.empty((N, b._ld), dtype=torch.float64)
+    Lh = torch.empty((N,), dtype=torch.float64)
+    if pinned:
+        Xh, Lh = Xh.pin_memory(), Lh.pin_memory()
+    Xh.copy_(b._X.cpu()); Lh.copy_(b._lnl.cpu())
+    moved = 0
+    for g in range(G):
+        before = Xh.clone()
+        _lib.check(b._libh.bpm_generations_host(b._handle, Xh.data_ptr(), Lh.data_ptr(), g, 1 + g, 1))
+        nb = C.c_uint64()
+        _lib.check(b._libh.bpm_last_d2h_bytes(b._handle, C.byref(nb)))
+        rows = int((before != Xh).any(dim=1).sum())
+        moved += rows
+        if pinned:
+            assert nb.value == rows * (b._ld + 1) * 8 + 8
+        else:
+            assert nb.value == N * (b._ld + 1) * 8
+    a.run_mcmc(N * (G + 1))
+    assert torch.equal(a._X.cpu(), Xh) and torch.equal(a._lnl.cpu(), Lh)
+    assert moved == a.n_accepted
