@@ -105,6 +105,23 @@ class McmcChain(object):
     def load_chain_state(self, chain_state):
         self.chain = chain_state
 
+    # chain.py:31-49: transition-kernel helpers nothing on the sampler path calls; kept so the
+    # McmcChain surface is complete
+    def set_t_kernel(self, t_kernel):
+        t_kernel = np.asarray(t_kernel)
+        assert t_kernel.shape[1] == self.chain.shape[1]
+        assert t_kernel.shape[1] == t_kernel.shape[0]          # must be square
+        self.t_kernel = t_kernel
+
+    def t_kernel_eig(self):
+        return np.linalg.eig(self.t_kernel)
+
+    def apply_t_kernel(self, apply_new_state=True):
+        new_state = np.dot(self.t_kernel, self.chain[:-1])
+        if apply_new_state:
+            self.append_sample(new_state)
+        return new_state
+
     def auto_corr(self, lag):
         pass
 

@@ -157,6 +157,12 @@ def test_free_standing_mcmc_chain_behaves_like_reference():
     assert ch.chain_len == 1
     with pytest.raises(AssertionError):
         ch.chain = np.zeros((3, 5))
+    ch.set_t_kernel(np.array([[0.0, 1.0], [1.0, 0.0]]))            # chain.py:31-43
+    w, _ = ch.t_kernel_eig()
+    assert sorted(np.round(w.real, 12)) == [-1.0, 1.0]
+    with pytest.raises(AssertionError):
+        ch.set_t_kernel(np.zeros((3, 3)))
+    assert ch.auto_corr(1) is None
 
 
 def test_history_store_chunks_and_super_chain_layout():
