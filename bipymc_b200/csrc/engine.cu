@@ -57,6 +57,7 @@ struct bpm_engine {
   int32_t* inv = nullptr;        // inverse permutation (only when the packed lists are in use)
   int32_t* loc_list = nullptr;   // local chains of both halves, packed in chain order (kernels_generic.cuh)
   int32_t* loc_cnt = nullptr;    // [2]
+  int32_t* phase_cnt = nullptr;  // [1] rows of the phase being stepped (selected from loc_cnt on the device)
   int32_t* cmp_blk = nullptr;    // [2][nblk][2] block counts / offsets
   bool serial() const { return cfg.algo == BPM_ALGO_DEMC_SERIAL; }
   bool sharded() const { return cfg.chain_lo != 0 || cfg.chain_hi != cfg.n_chains; }
@@ -134,7 +135,7 @@ struct bpm_engine {
   }
 
   ~bpm_engine() {
-    cudaFree(inv); cudaFree(loc_list); cudaFree(loc_cnt); cudaFree(cmp_blk); cudaFree(cr_ticket);
+    cudaFree(inv); cudaFree(loc_list); cudaFree(loc_cnt); cudaFree(phase_cnt); cudaFree(cmp_blk); cudaFree(cr_ticket);
     cudaFree(perm); cudaFree(flip); cudaFree(prop); cudaFree(lnl_prop); cudaFree(cr_delta);
     cudaFree(cr_pick); cudaFree(p_cr); cudaFree(cr_dm); cudaFree(cr_cnt); cudaFree(cr_part); cudaFree(cr_block);
     cudaFree(counters); cudaFree(nan_flag); cudaFree(tparams); cudaFree(hX); cudaFree(hL);
@@ -156,6 +157,7 @@ struct bpm_engine {
       CU_TRY(cudaMalloc(&inv, sizeof(int32_t) * N));
       CU_TRY(cudaMalloc(&loc_list, sizeof(int32_t) * N));
       CU_TRY(cudaMalloc(&loc_cnt, sizeof(int32_t) * 2));
+      CU_TRY(cudaMalloc(&phase_cnt, sizeof(int32_t)));
       CU_TRY(cudaMalloc(&cmp_blk, sizeof(int32_t) * 4 * nblk));
     }
     CU_TRY(cudaMalloc(&prop, sizeof(double) * (size_t)nA * cfg.ld));
@@ -282,7 +284,9 @@ struct bpm_engine {
     return 0;
   }
 
-  int eval_lnl(const double* P, int n, int ld, double* out, cudaStream_t s) {
+  // n_dev (optional): device-side number of valid rows (a packed phase list counted on the
+  // device); n is then only the launch bound and the large-d kernel skips the tiles beyond it
+  int eval_lnl(const double* P, int n, int ld, double* out, cudaStream_t s, const int32_t* n_dev = nullptr) {
     if (n <= 0) return 0;
     switch (target) {
       case BPM_TARGET_BANANA:
@@ -303,7 +307,7 @@ struct bpm_engine {
         }
         else if (bpm::gauss_dmma_supported(cfg.dim, gauss_r, ld)) {   // large d: FP64 tensor-pipe GEMM
           if (bpm::launch_gauss_dmma(P, n, ld, cfg.dim, gauss_r, mu, W, gauss_c0, gauss_logpdf_flag,
-                                     gauss_mu_zero, out, s))
+                                     gauss_mu_zero, out, n_dev, s))
             return fail("gauss dmma kernel launch failed");
         } else
           bpm::lnl_gauss_tiled_kernel<<<cdiv(n, 64), 256, 0, s>>>(P, n, ld, cfg.dim, gauss_r, mu, W,
@@ -371,7 +375,18 @@ struct bpm_engine {
     BPM_TRY(launch_propose<REPLAY>(a, s));
     prof_end(s);
     prof_begin(2, s);
-    BPM_TRY(eval_lnl(prop, nA, cfg.ld, lnl_prop, s));
+    {
+      // packed lists hold at most this rank's chains; their exact number lives on the device
+      int n_rows = nA;
+      const int32_t* n_dev = nullptr;
+      if (packed()) {
+        const int n_local = cfg.chain_hi - cfg.chain_lo;
+        n_rows = n_local < nA ? n_local : nA;
+        bpm::phase_count_kernel<<<1, 1, 0, s>>>(loc_cnt, flip, ph, serial() ? 1 : 0, phase_cnt);
+        n_dev = phase_cnt;
+      }
+      BPM_TRY(eval_lnl(prop, n_rows, cfg.ld, lnl_prop, s, n_dev));
+    }
     prof_end(s);
     prof_begin(3, s);
     BPM_TRY(launch_accept<REPLAY>(a, s));

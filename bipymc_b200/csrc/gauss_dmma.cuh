@@ -39,8 +39,13 @@ __device__ __forceinline__ void gd_dmma(double& c0, double& c1, double a, double
 template <bool CENTER, int MT>
 __global__ void __launch_bounds__(kGdThreads, 2)
 gauss_dmma_kernel(const double* __restrict__ P, int n, int ld, int d, int r, const double* __restrict__ mu,
-                  const double* __restrict__ W, double c0, int log_of_pdf, double* __restrict__ out) {
+                  const double* __restrict__ W, double c0, int log_of_pdf, double* __restrict__ out,
+                  const int32_t* __restrict__ n_dev) {
   constexpr int kGdM = 16 * MT;
+  if (n_dev) {                       // rows actually present (device-counted packed list); n is the launch bound
+    n = min(n, *n_dev);
+    if ((int)blockIdx.x * kGdM >= n) return;
+  }
   constexpr size_t kGdStageDoubles = gd_stage_doubles(kGdM);
   extern __shared__ __align__(16) double gsm[];
   double* mus = gsm;                                           // [dpad]
@@ -154,24 +159,26 @@ inline bool gauss_dmma_supported(int d, int r, int ld) { return (d % 2) == 0 && 
 
 template <bool CENTER, int MT>
 inline int launch_gauss_dmma_t(const double* P, int n, int ld, int d, int r, const double* mu, const double* W,
-                               double c0, int log_of_pdf, double* out, cudaStream_t s) {
+                               double c0, int log_of_pdf, double* out, const int32_t* n_dev, cudaStream_t s) {
   constexpr int M = 16 * MT;
   const size_t sm = gauss_dmma_smem(d, M);
   cudaError_t e = cudaFuncSetAttribute(gauss_dmma_kernel<CENTER, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) return 1;
-  gauss_dmma_kernel<CENTER, MT><<<(n + M - 1) / M, kGdThreads, sm, s>>>(P, n, ld, d, r, mu, W, c0, log_of_pdf, out);
+  gauss_dmma_kernel<CENTER, MT><<<(n + M - 1) / M, kGdThreads, sm, s>>>(P, n, ld, d, r, mu, W, c0, log_of_pdf, out,
+                                                                      n_dev);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
 inline int launch_gauss_dmma(const double* P, int n, int ld, int d, int r, const double* mu, const double* W,
-                             double c0, int log_of_pdf, int mu_is_zero, double* out, cudaStream_t s) {
+                             double c0, int log_of_pdf, int mu_is_zero, double* out, const int32_t* n_dev,
+                             cudaStream_t s) {
   // 64-row CTAs once there are enough of them to put two on every SM, else 32-row CTAs
   const bool small = (n + 63) / 64 < 2 * 148;
   if (mu_is_zero)
-    return small ? launch_gauss_dmma_t<false, 2>(P, n, ld, d, r, mu, W, c0, log_of_pdf, out, s)
-                 : launch_gauss_dmma_t<false, 4>(P, n, ld, d, r, mu, W, c0, log_of_pdf, out, s);
-  return small ? launch_gauss_dmma_t<true, 2>(P, n, ld, d, r, mu, W, c0, log_of_pdf, out, s)
-               : launch_gauss_dmma_t<true, 4>(P, n, ld, d, r, mu, W, c0, log_of_pdf, out, s);
+    return small ? launch_gauss_dmma_t<false, 2>(P, n, ld, d, r, mu, W, c0, log_of_pdf, out, n_dev, s)
+                 : launch_gauss_dmma_t<false, 4>(P, n, ld, d, r, mu, W, c0, log_of_pdf, out, n_dev, s);
+  return small ? launch_gauss_dmma_t<true, 2>(P, n, ld, d, r, mu, W, c0, log_of_pdf, out, n_dev, s)
+               : launch_gauss_dmma_t<true, 4>(P, n, ld, d, r, mu, W, c0, log_of_pdf, out, n_dev, s);
 }
 
 }  // namespace bpm

@@ -49,6 +49,13 @@ __global__ void identity_split_kernel(int32_t* __restrict__ perm, int32_t* __res
   }
 }
 
+// number of rows of the half being stepped, picked on the device (the flip flag lives there)
+__global__ void phase_count_kernel(const int32_t* __restrict__ loc_cnt, const int32_t* __restrict__ flip, int phase,
+                                   int serial, int32_t* __restrict__ out) {
+  const int first = serial ? 1 : ((phase ^ (*flip != 0)) == 0);
+  *out = loc_cnt[first ? 0 : 1];
+}
+
 // ---- packed phase lists: the chains this rank owns, per half, in CHAIN order ----------
 // A rank steps only its own chains (demc.py:103-107 loops over the local ids and tests
 // `c_id in a_ids`).  Walking the global half-lists and skipping foreign chains would leave

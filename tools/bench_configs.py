@@ -74,7 +74,45 @@ def c5shape():
         N, d, 64 * d + 16 + 32 * d + 8 * d, gens=20, warm=12)
 
 
+def c5multi():
+    """configs[4] shape sharded over the GPUs of one box (launch under torchrun): DREAM on the
+    1000-D Gaussian, 2.5 x 10^4 chains per GPU, once as ONE population (replicas + peer-memory
+    exchange) and once in the stated sub-population mode (islands re-dealt every 10 generations)."""
+    import torch.distributed as dist
+    from bipymc_b200 import DreamMpi, targets
+    rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    world = dist.get_world_size()
+    N, d, gens, warm = 25000 * world, 1000, 20, 10
+    t = targets.Gauss_100D(dim=d)
+    for mode, kw in (("one population, p2p exchange", {}), ("sub-population mode k=10", dict(subpop_k=10))):
+        np.random.seed(1)
+        s = DreamMpi(t.ln_like, np.zeros(d), n_chains=N, seed=3, varepsilon=np.arange(d) + 1.0, history="none",
+                     burnin_gen=10 ** 6, n_cr_gen=5, device=local, **kw)
+        s.run_mcmc(N * (warm + 1))
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        s.run_mcmc(N * (gens + 1), _k_gen0=warm)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(json.dumps({"config": "c5-shape DREAM Gauss_1000D, %d GPUs x 2.5e4 chains, %s" % (world, mode),
+                              "n_chains": N, "chain_steps_per_s": N * gens / (float(ms.item()) * 1e-3),
+                              "ms_per_generation": float(ms.item()) / gens,
+                              "acceptance_fraction": s.acceptance_fraction}), flush=True)
+        s.close()
+        dist.barrier()
+    dist.destroy_process_group()
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["c5multi"]:
+        c5multi()
+        sys.exit(0)
     if "c5shape" in (sys.argv[1:] or ["c5shape"]):
         c5shape()
         if sys.argv[1:] == ["c5shape"]:

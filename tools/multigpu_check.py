@@ -28,6 +28,8 @@ def main():
         ("dream-gauss100", DreamMpi, targets.Gauss_100D(), np.zeros(100), 4096 + 2 * world, dict(burnin_gen=0), 1.0),
         ("dream-gauss100-adapt", DreamMpi, targets.Gauss_100D(), np.zeros(100), 2048, dict(burnin_gen=1000, n_cr_gen=2), 1.0),
         ("demc-banana", DeMcMpi, targets.Banana_2D(), [0.0, 0.0], 1000 * world, {}, 0.5),
+        # d > 112: generic split path with the FP64 tensor-pipe likelihood and device-counted row lists
+        ("dream-gauss128", DreamMpi, targets.Gauss_100D(dim=128), np.zeros(128), 640 + 2 * world, dict(burnin_gen=0), 1.0),
         ("dream-linefit-outlier", DreamMpi, targets.LineFit(), [-0.8, 4.5, 0.2], 512 * world,
          dict(burnin_gen=1000, n_cr_gen=3, outlier_gen=5), 1e-2),
     ]
