@@ -24,12 +24,13 @@ __global__ void split_native_kernel(int32_t* __restrict__ perm, int32_t* __restr
     double thr = __ddiv_rn(flip_p, __dadd_rn(flip_p, __dsub_rn(1.0, flip_p)));
     *flip = u53(q.x, q.y) < thr ? 1 : 0;
   }
+  // the Feistel keys cost two Philox calls: drawn once per block, not once per element
+  __shared__ FeistelKey fkey;
+  if (shuffle && threadIdx.x == 0) fkey = make_feistel(rng, (uint32_t)N);
+  __syncthreads();
   if (j >= N) return;
   int32_t c = j;
-  if (shuffle) {
-    FeistelKey f = make_feistel(rng, (uint32_t)N);
-    c = (int32_t)feistel_perm(f, (uint32_t)j);
-  }
+  if (shuffle) c = (int32_t)feistel_perm(fkey, (uint32_t)j);
   perm[j] = c;
   if (inv) inv[c] = j;        // list position of chain c (used to pack the phase lists in chain order)
 }
