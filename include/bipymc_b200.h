@@ -181,7 +181,7 @@ int bpm_dump_draws(bpm_handle h, const bpm_state* st, int64_t k_gen, bpm_replay*
  *   -> bpm_accept; bpm_end_generation.
  * prop is [n_phase][ld] in phase order; *n_phase returns the number of chains: all chains of
  * the half on an unsharded handle, only this rank's chains of the half (densely packed, in
- * list order) on a sharded one. */
+ * ascending chain order) on a sharded one (and on d <= 4 handles, which use the packed lists too). */
 int bpm_begin_generation(bpm_handle h, bpm_state* st, int64_t k_gen, const bpm_replay* rp_or_null,
                          bpm_stream stream);
 int bpm_propose(bpm_handle h, bpm_state* st, int32_t phase, double** prop, int32_t* n_phase,
