@@ -35,6 +35,8 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
+        if not force and os.path.exists(LIB):
+            return LIB          # a prebuilt library travelled with the tree; nothing to rebuild it with
         raise RuntimeError("nvcc not found; cannot build %s" % LIB)
     os.makedirs(LIBDIR, exist_ok=True)
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
