@@ -722,72 +722,60 @@ __device__ __forceinline__ void load_W_fragments(double* Wf, double* mus, const 
   for (int k = tid; k < d; k += nthreads) mus[k] = mu[k];
 }
 
-// maha[row] = |(P[row] - mu) . W|^2 for the 16 rows [16 cw, 16 cw + 16) of a 64-row tile.
-// Column tiles are processed in two groups of <= 7 so that 28 accumulators stay in registers.
+// maha = |(P[row] - mu) . W|^2 for one m-tile (8 rows) per warp, no cross-warp hand-off: the four
+// lanes of a quad end up holding the finished Mahalanobis distance of row 8 cw + lane / 4.
+// A lone warp issues one DMMA.8x8x4 every ~50 cycles (profiles/r1_final_*: four consumer warps with
+// 16 rows each were 90 % busy at a third of the FP64 tensor rate); two consumer warps per scheduler
+// overlap each other's issue gaps (profiles/r1_consumer_experiments.txt).
 template <bool CENTER>
-__device__ __forceinline__ void gauss_tile_maha_dmma(const double* __restrict__ P, int pld,
-                                                     const double* __restrict__ Wf,
-                                                     const double* __restrict__ mus, int d, int NT,
-                                                     double* __restrict__ maha, int cw, int lane) {
-  const int r0 = 16 * cw + (lane >> 2), kq = lane & 3;
+__device__ __forceinline__ double gauss_tile_maha_dmma8(const double* __restrict__ P, int pld,
+                                                        const double* __restrict__ Wf,
+                                                        const double* __restrict__ mus, int d, int NT,
+                                                        int cw, int lane) {
+  const int r0 = 8 * cw + (lane >> 2), kq = lane & 3;
   const double* pa0 = P + r0 * pld + kq;
-  const double* pa1 = pa0 + 8 * pld;
   const int nk4 = d >> 2;
-  double s0 = 0.0, s1 = 0.0;
+  double s0 = 0.0;
+  // column tiles in two groups of <= 7: 14 accumulators + the next k step's 7 B fragments fit the
+  // 80 registers a consumer thread owns
 #pragma unroll 1
   for (int g = 0; g < 2; ++g) {
     const int nt0 = 7 * g;
     const int cnt = NT - nt0 < 7 ? NT - nt0 : 7;
     if (cnt <= 0) break;
-    double acc0[7][2], acc1[7][2];
+    double acc[7][2];
 #pragma unroll
-    for (int j = 0; j < 7; ++j) acc0[j][0] = acc0[j][1] = acc1[j][0] = acc1[j][1] = 0.0;
+    for (int j = 0; j < 7; ++j) acc[j][0] = acc[j][1] = 0.0;
     const double* wf = Wf + nt0 * 32 + lane;
 #pragma unroll 2
     for (int k4 = 0; k4 < nk4; ++k4) {
-      double a0 = pa0[4 * k4], a1 = pa1[4 * k4];
-      if (CENTER) {
-        const double m = mus[4 * k4 + kq];
-        a0 = __dsub_rn(a0, m);
-        a1 = __dsub_rn(a1, m);
-      }
+      double a0 = pa0[4 * k4];
+      if (CENTER) a0 = __dsub_rn(a0, mus[4 * k4 + kq]);
       const double* wk = wf + (size_t)k4 * NT * 32;
 #pragma unroll
       for (int j = 0; j < 7; ++j)
-        if (j < cnt) {
-          const double b = wk[j * 32];
-          dmma884(acc0[j][0], acc0[j][1], a0, b);
-          dmma884(acc1[j][0], acc1[j][1], a1, b);
-        }
+        if (j < cnt) dmma884(acc[j][0], acc[j][1], a0, wk[j * 32]);
     }
 #pragma unroll
     for (int j = 0; j < 7; ++j)
       if (j < cnt) {
-        s0 = fma(acc0[j][0], acc0[j][0], s0);
-        s0 = fma(acc0[j][1], acc0[j][1], s0);
-        s1 = fma(acc1[j][0], acc1[j][0], s1);
-        s1 = fma(acc1[j][1], acc1[j][1], s1);
+        s0 = fma(acc[j][0], acc[j][0], s0);
+        s0 = fma(acc[j][1], acc[j][1], s0);
       }
   }
-  // the four lanes of a quad hold disjoint column sets of the same two rows
   s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, 1);
-  s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, 1);
   s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, 2);
-  s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, 2);
-  if (kq == 0) {
-    maha[r0] = s0;
-    maha[r0 + 8] = s1;
-  }
+  return s0;
 }
 
-// Metropolis decision from a finished Mahalanobis distance (one thread per chain row; whole warps)
-__device__ __forceinline__ void tile_stage_decide_maha(const PhaseArgs& a, const GaussArgs& g, TileScratch& T,
-                                                       const double* __restrict__ maha, int row,
-                                                       unsigned& n_acc, unsigned& n_rej) {
-  const int c = T.cid[row];
+// Metropolis decision for one chain row whose Mahalanobis distance is in a register; called by whole
+// warps, `row < 0` = this lane decides nothing.
+__device__ __forceinline__ int tile_stage_decide_reg(const PhaseArgs& a, const GaussArgs& g, TileScratch& T,
+                                                     double maha, int row, unsigned& n_acc, unsigned& n_rej) {
+  const int c = row >= 0 ? T.cid[row] : -1;
   int acc = 0;
   if (c >= 0) {
-    const double lp = gauss_finish(g.c0, maha[row], g.log_of_pdf);
+    const double lp = gauss_finish(g.c0, maha, g.log_of_pdf);
     acc = metropolis(a.lnl[c], lp, T.accept_u[row]);
     if (acc < 0) {
       *a.nan_flag = 1;
@@ -797,9 +785,10 @@ __device__ __forceinline__ void tile_stage_decide_maha(const PhaseArgs& a, const
     if (a.tr.accept) a.tr.accept[c] = acc;
     if (a.tr.lnl_prop) a.tr.lnl_prop[c] = lp;
   }
-  T.acc[row] = acc;
+  if (row >= 0) T.acc[row] = acc;
   n_acc += __popc(__ballot_sync(0xFFFFFFFFu, c >= 0 && acc));
   n_rej += __popc(__ballot_sync(0xFFFFFFFFu, c >= 0 && !acc));
+  return acc;
 }
 
 // =====================================================================================
@@ -816,7 +805,7 @@ __device__ __forceinline__ void tile_stage_decide_maha(const PhaseArgs& a, const
 // Draw values and proposal arithmetic are those of the other variants (identical proposals);
 // the quadratic form is summed in the DMMA fragment order, so ln_like agrees with them to
 // rounding (~1e-15 relative), not bit for bit.
-constexpr int kV3ConsWarps = 4, kV3ProdWarps = 16;
+constexpr int kV3ConsWarps = 8, kV3ProdWarps = 16;
 constexpr int kV3Threads = 32 * (kV3ConsWarps + kV3ProdWarps);   // 640
 constexpr int kV3ProdThreads = 32 * kV3ProdWarps;
 constexpr int kV3ConsThreads = 32 * kV3ConsWarps;
@@ -1070,69 +1059,96 @@ __device__ __forceinline__ void warp_stage_draws(const PhaseArgs& a, const Phase
   __syncwarp();
 }
 
-// One chain row of the write-back, split so two rows can be in flight per warp.
+// One chain row of the write-back, split into issue / finish so that every load of a row pair
+// (moments of both rows, and the own row of a rejected chain -- an L2 hit, the proposal stage
+// read it moments ago) is in flight before the first one is consumed.
+// Lane -> dimension map of the write-back (every array it touches is per-dimension independent):
+// BPM_V3_WB_SECTOR = 1: lane l owns dims {2l, 2l+1} and {64+2l, 65+2l}, so one 128-bit warp access
+// covers 512 contiguous bytes = whole 32-byte sectors; 0: dims 4l .. 4l+3 (each access touches
+// half of every sector, and every sector twice).
+#ifndef BPM_V3_WB_SECTOR
+#define BPM_V3_WB_SECTOR 1
+#endif
+struct WbMap {
+  int o0, o1;      // element offsets of the lane's two 16-byte chunks inside a row
+  bool h0, h1;     // chunk inside the row
+};
+__device__ __forceinline__ WbMap wb_map(int d, int lane) {
+  WbMap m;
+#if BPM_V3_WB_SECTOR
+  m.o0 = 2 * lane; m.o1 = 64 + 2 * lane;
+#else
+  m.o0 = 4 * lane; m.o1 = 4 * lane + 2;
+#endif
+  m.h0 = m.o0 < d; m.h1 = m.o1 < d;     // d is even
+  return m;
+}
 struct WbRow {
-  double2 m0, m1, v0, v1;
+  double2 m0, m1, v0, v1, x0, x1;
   int c, acc;
 };
-__device__ __forceinline__ void wb_issue(const PhaseArgs& a, const TileScratch& T, int row, int lane, bool keep,
-                                         WbRow& w) {
+__device__ __forceinline__ void wb_issue(const PhaseArgs& a, const TileScratch& T, const double* __restrict__ P,
+                                         int pld, int row, const WbMap& mp, bool keep, WbRow& w) {
+  const double2 z = make_double2(0.0, 0.0);
+  w.m0 = z; w.m1 = z; w.v0 = z; w.v1 = z; w.x0 = z; w.x1 = z;
   w.c = T.cid[row];
   w.acc = w.c >= 0 ? T.acc[row] : 0;
   if (w.c < 0 || (!w.acc && !keep)) { w.c = -1; return; }
-  const size_t o = (size_t)(w.c - a.chain_lo) * a.ld + 4 * lane;
+  const size_t o = (size_t)(w.c - a.chain_lo) * a.ld;
   if (a.mean) {
-    w.m0 = ld_stream2(a.mean + o); w.m1 = ld_stream2(a.mean + o + 2);
-    w.v0 = ld_stream2(a.m2 + o); w.v1 = ld_stream2(a.m2 + o + 2);
+    if (mp.h0) { w.m0 = ld_stream2(a.mean + o + mp.o0); w.v0 = ld_stream2(a.m2 + o + mp.o0); }
+    if (mp.h1) { w.m1 = ld_stream2(a.mean + o + mp.o1); w.v1 = ld_stream2(a.m2 + o + mp.o1); }
+  }
+  if (w.acc) {
+    const double* prow = P + row * pld;
+    if (mp.h0) w.x0 = *reinterpret_cast<const double2*>(prow + mp.o0);
+    if (mp.h1) w.x1 = *reinterpret_cast<const double2*>(prow + mp.o1);
+  } else {
+    const double* xc = a.X + (size_t)w.c * a.ld;
+    if (mp.h0) w.x0 = ldg2(xc + mp.o0);
+    if (mp.h1) w.x1 = ldg2(xc + mp.o1);
   }
 }
-__device__ __forceinline__ void wb_finish(const PhaseArgs& a, const double* __restrict__ P, int pld, int row,
-                                          int lane, WbRow& w) {
+__device__ __forceinline__ void wb_finish(const PhaseArgs& a, const WbMap& mp, WbRow& w) {
   if (w.c < 0) return;
-  const size_t o = (size_t)(w.c - a.chain_lo) * a.ld + 4 * lane;
-  double s[4];
+  const size_t o = (size_t)(w.c - a.chain_lo) * a.ld;
   if (w.acc) {
-    double* xc = a.X + (size_t)w.c * a.ld + 4 * lane;
-    const double* prow = P + row * pld + 4 * lane;
-    const double2 p0 = *reinterpret_cast<const double2*>(prow);
-    const double2 p1 = *reinterpret_cast<const double2*>(prow + 2);
-    s[0] = p0.x; s[1] = p0.y; s[2] = p1.x; s[3] = p1.y;
-    *reinterpret_cast<double2*>(xc) = p0;
-    *reinterpret_cast<double2*>(xc + 2) = p1;
-    store_peers4(a, (size_t)w.c * a.ld + 4 * lane, s[0], s[1], s[2], s[3]);
-  } else {
-    // rejected: the chain's own row was read by the proposal stage moments ago (an L2 hit)
-    const double* xc = a.X + (size_t)w.c * a.ld + 4 * lane;
-    const double2 u0 = ldg2(xc), u1 = ldg2(xc + 2);
-    s[0] = u0.x; s[1] = u0.y; s[2] = u1.x; s[3] = u1.y;
+    const size_t ox = (size_t)w.c * a.ld;
+    if (mp.h0) {
+      *reinterpret_cast<double2*>(a.X + ox + mp.o0) = w.x0;
+      store_peers2(a, ox + mp.o0, w.x0.x, w.x0.y);
+    }
+    if (mp.h1) {
+      *reinterpret_cast<double2*>(a.X + ox + mp.o1) = w.x1;
+      store_peers2(a, ox + mp.o1, w.x1.x, w.x1.y);
+    }
   }
   if (a.mean) {
-    welford_update(s[0], a.inv_n1, w.m0.x, w.v0.x);
-    welford_update(s[1], a.inv_n1, w.m0.y, w.v0.y);
-    welford_update(s[2], a.inv_n1, w.m1.x, w.v1.x);
-    welford_update(s[3], a.inv_n1, w.m1.y, w.v1.y);
-    st_stream2(a.mean + o, w.m0.x, w.m0.y);
-    st_stream2(a.mean + o + 2, w.m1.x, w.m1.y);
-    st_stream2(a.m2 + o, w.v0.x, w.v0.y);
-    st_stream2(a.m2 + o + 2, w.v1.x, w.v1.y);
+    welford_update(w.x0.x, a.inv_n1, w.m0.x, w.v0.x);
+    welford_update(w.x0.y, a.inv_n1, w.m0.y, w.v0.y);
+    welford_update(w.x1.x, a.inv_n1, w.m1.x, w.v1.x);
+    welford_update(w.x1.y, a.inv_n1, w.m1.y, w.v1.y);
+    if (mp.h0) { st_stream2(a.mean + o + mp.o0, w.m0.x, w.m0.y); st_stream2(a.m2 + o + mp.o0, w.v0.x, w.v0.y); }
+    if (mp.h1) { st_stream2(a.mean + o + mp.o1, w.m1.x, w.m1.y); st_stream2(a.m2 + o + mp.o1, w.v1.x, w.v1.y); }
   }
   if (a.hist_row) {
-    st_stream2(a.hist_row + o, s[0], s[1]);
-    st_stream2(a.hist_row + o + 2, s[2], s[3]);
+    if (mp.h0) st_stream2(a.hist_row + o + mp.o0, w.x0.x, w.x0.y);
+    if (mp.h1) st_stream2(a.hist_row + o + mp.o1, w.x1.x, w.x1.y);
   }
 }
 // write-back of the warp's rows of one tile (d % 4 == 0), two rows' loads in flight at a time
 __device__ __forceinline__ void warp_stage_writeback(const PhaseArgs& a, const TileScratch& T,
                                                      const double* __restrict__ P, int pld, int pw, int lane) {
-  if (4 * lane >= a.d) return;
+  const WbMap mp = wb_map(a.d, lane);
+  if (!mp.h0) return;
   const bool keep = a.mean != nullptr || a.hist_row != nullptr;
 #pragma unroll 1
   for (int row = pw; row < kTileRows; row += 2 * kV3ProdWarps) {
     WbRow w0, w1;
-    wb_issue(a, T, row, lane, keep, w0);
-    wb_issue(a, T, row + kV3ProdWarps, lane, keep, w1);
-    wb_finish(a, P, pld, row, lane, w0);
-    wb_finish(a, P, pld, row + kV3ProdWarps, lane, w1);
+    wb_issue(a, T, P, pld, row, mp, keep, w0);
+    wb_issue(a, T, P, pld, row + kV3ProdWarps, mp, keep, w1);
+    wb_finish(a, mp, w0);
+    wb_finish(a, mp, w1);
   }
 }
 
@@ -1140,9 +1156,10 @@ __host__ __device__ inline size_t v3_ptile_doubles(int d) { return (size_t)kTile
 inline size_t fused_v3_smem(int d) {
   return sizeof(double) * (gauss_table_doubles(d) + 2 * v3_ptile_doubles(d) + 3 * gauss_scratch_doubles() + 4);
 }
+// the small proposal-stage tables; W (83 KB) is loaded by the consumers alone, in the shadow of
+// the producers' first tile
 __device__ __forceinline__ void fill_tables_v3(const PhaseArgs& a, const GaussArgs& g, const GaussTables& t,
                                                int tid, int nthreads) {
-  load_W_fragments(t.Ws, t.mus, g.W, g.mu, a.d, g.r, tid, nthreads);
   for (int dp = tid; dp <= a.d; dp += nthreads)
     t.gam[dp] = dp == 0 ? 0.0
                         : __ddiv_rn(a.gamma_num, __dsqrt_rn(__dmul_rn(__dmul_rn(2.0, (double)a.del_pairs),
@@ -1170,14 +1187,15 @@ fused_gauss_v3_kernel(const PhaseArgs a, const GaussArgs g) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* Pbuf = smem + gauss_table_doubles(d);
   const size_t p_stride = v3_ptile_doubles(d);
-  const size_t part_off = (size_t)kTileRows * pld;   // maha[64] after the tile
   double* Tbuf = Pbuf + 2 * p_stride;
   const size_t t_stride = gauss_scratch_doubles();
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Tbuf + 3 * t_stride);   // full[2], done[2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Tbuf + 3 * t_stride);
+  uint64_t* FULL = bars;       // [2] every producer warp filled its rows of the tile buffer
+  uint64_t* DONE = bars + 2;   // [2] every row of the tile is decided (T.acc, lnl final)
   fill_tables_v3(a, g, tb, threadIdx.x, kV3Threads);
   if (threadIdx.x == 0) {
-    mbar_init(bars + 0, kV3ProdWarps); mbar_init(bars + 1, kV3ProdWarps);   // FULL: one arrival per producer warp
-    mbar_init(bars + 2, kTileRows); mbar_init(bars + 3, kTileRows);         // DONE: one per deciding thread
+    mbar_init(FULL + 0, kV3ProdWarps); mbar_init(FULL + 1, kV3ProdWarps);   // one arrival per producer warp
+    mbar_init(DONE + 0, kTileRows); mbar_init(DONE + 1, kTileRows);         // one per deciding thread
   }
   __syncthreads();
   const PhaseLists L = phase_lists(a);
@@ -1190,20 +1208,23 @@ fused_gauss_v3_kernel(const PhaseArgs a, const GaussArgs g) {
 
   if (warp < kV3ConsWarps) {
     // ------------------------------ consumers ------------------------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+    // 8 warps x 8 rows: tile product on the FP64 tensor pipe, Metropolis decision and DONE arrival
+    // all inside the warp.  768 threads launch with 80 registers each; the consumers hand 16 of
+    // theirs to the producers (16 x 88 + 8 x 64 = 24 x 80: setmaxnreg only moves registers inside
+    // the CTA's allocation).  They also load W, in the shadow of the producers' first tile.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    load_W_fragments(tb.Ws, tb.mus, g.W, g.mu, d, g.r, threadIdx.x, kV3ConsThreads);
+    nbar_sync(BAR_CONS, kV3ConsThreads);
     unsigned n_acc = 0, n_rej = 0;
     for (int i = 0; i < n_my; ++i) {
       const int b = i & 1;
-      double* P = Pbuf + b * p_stride;
-      double* part = P + part_off;
+      const double* P = Pbuf + b * p_stride;
       TileScratch& T = *reinterpret_cast<TileScratch*>(Tbuf + (i % 3) * t_stride);
-      mbar_wait(bars + b, (i >> 1) & 1);                // every producer warp filled its rows of buffer b
-      gauss_tile_maha_dmma<CENTER>(P, pld, tb.Ws, tb.mus, d, NT, part, warp, lane);
-      nbar_sync(BAR_CONS, kV3ConsThreads);
-      if (threadIdx.x < kTileRows) {
-        tile_stage_decide_maha(a, g, T, part, threadIdx.x, n_acc, n_rej);
-        mbar_arrive(bars + 2 + b);                      // T.acc / lnl of this row are final
-      }
+      mbar_wait(FULL + b, (i >> 1) & 1);
+      const double maha = gauss_tile_maha_dmma8<CENTER>(P, pld, tb.Ws, tb.mus, d, NT, warp, lane);
+      const bool decider = (lane & 3) == 0;
+      tile_stage_decide_reg(a, g, T, maha, decider ? 8 * warp + (lane >> 2) : -1, n_acc, n_rej);
+      if (decider) mbar_arrive(DONE + b);
     }
     if (lane == 0) {
       if (n_acc) atomicAdd(a.n_acc, (unsigned long long)n_acc);
@@ -1211,29 +1232,29 @@ fused_gauss_v3_kernel(const PhaseArgs a, const GaussArgs g) {
     }
   } else {
     // ------------------------------ producers ------------------------------------------
-    // each warp is an independent pipeline over ITS rows: draws + L2 prefetch of tile i+1 |
-    // proposal of tile i | write-back of tile i-1; it synchronises only with the consumers
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    // each warp is an independent pipeline over ITS rows: draws of tile i+1 | proposal of tile i |
+    // write-back of tile i-1; it synchronises only with the consumers
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     const int pw = warp - kV3ConsWarps;
     if (n_my > 0)
       warp_stage_draws<REPLAY>(a, L, tb, *reinterpret_cast<TileScratch*>(Tbuf), g_lo, g_hi, pw, lane);
     for (int i = 0; i <= n_my; ++i) {
-      if (i + 1 < n_my)
-        warp_stage_draws<REPLAY>(a, L, tb, *reinterpret_cast<TileScratch*>(Tbuf + ((i + 1) % 3) * t_stride),
-                                 g_lo + (i + 1) * kTileRows, g_hi, pw, lane);
       if (i < n_my) {
         const int b = i & 1;
+        if (i + 1 < n_my)
+          warp_stage_draws<REPLAY>(a, L, tb, *reinterpret_cast<TileScratch*>(Tbuf + ((i + 1) % 3) * t_stride),
+                                   g_lo + (i + 1) * kTileRows, g_hi, pw, lane);
         double* P = Pbuf + b * p_stride;
         TileScratch& T = *reinterpret_cast<TileScratch*>(Tbuf + (i % 3) * t_stride);
         tile_stage_propose_v3<REPLAY, NPAIR>(a, tb, T, P, pld, pw, kV3ProdWarps, lane);
         __syncwarp();
-        if (lane == 0) mbar_arrive(bars + b);
+        if (lane == 0) mbar_arrive(FULL + b);
       }
       if (i >= 1) {
         const int b2 = (i - 1) & 1;
         const double* P = Pbuf + b2 * p_stride;
         const TileScratch& T = *reinterpret_cast<const TileScratch*>(Tbuf + ((i - 1) % 3) * t_stride);
-        mbar_wait(bars + 2 + b2, ((i - 1) >> 1) & 1);   // consumers decided tile i-1
+        mbar_wait(DONE + b2, ((i - 1) >> 1) & 1);
         warp_stage_writeback(a, T, P, pld, pw, lane);
       }
     }

@@ -74,6 +74,9 @@ __device__ __forceinline__ void store_peers4(const PhaseArgs& a, size_t elem_off
     *reinterpret_cast<double2*>(q + 2) = make_double2(s2, s3);
   }
 }
+__device__ __forceinline__ void store_peers2(const PhaseArgs& a, size_t elem_off, double s0, double s1) {
+  for (int p = 0; p < a.n_peers; ++p) *reinterpret_cast<double2*>(a.peers[p] + elem_off) = make_double2(s0, s1);
+}
 __device__ __forceinline__ void store_peers1(const PhaseArgs& a, size_t elem_off, double s) {
   for (int p = 0; p < a.n_peers; ++p) a.peers[p][elem_off] = s;
 }
