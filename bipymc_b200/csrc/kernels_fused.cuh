@@ -795,8 +795,9 @@ __device__ __forceinline__ int tile_stage_decide_reg(const PhaseArgs& a, const G
 // Variant 3 (default): the same producer / consumer pipeline re-balanced after profiling
 // variant 2 (profiles/r1_v2_*): its 8 consumer warps sat at the FULL barrier 76 % of the
 // time while each of the 12 producer warps walked its chains serially at ~0.2 IPC.  Here
-//   * 4 consumer warps each own 16 rows of the tile product and run it on the FP64 tensor
-//     pipe (mma.sync.m8n8k4.f64, W pre-arranged in fragment order in shared memory);
+//   * 8 consumer warps (64 registers) each own 8 rows of the tile product and run it on the FP64
+//     tensor pipe (mma.sync.m8n8k4.f64, W pre-arranged in fragment order in shared memory), decide
+//     their rows in registers and load W in the shadow of the producers' first tile;
 //   * 16 producer warps (88 registers) own exactly 4 chains of every 64-chain tile;
 //   * the producer stages are specialised at compile time (DREAM with 3 pairs, or the
 //     runtime-general form), need d % 4 == 0 so every row access is a 16-byte vector, test
@@ -816,16 +817,38 @@ __device__ __forceinline__ double2 ldg2(const double* p) { return __ldcg(reinter
 __device__ __forceinline__ double2 ldg2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 #endif
 
-// NPAIR: 3 = DREAM with del_pairs == 3 (the reference default), 0 = read algo / del_pairs at run time
-struct NoMid {
-  __device__ __forceinline__ void operator()(int) const {}
+// ---- lane -> dimension map of the write-back ----------------------------------------------
+// A lane owns two 16-byte chunks of a chain row.  "Sector" map (BPM_V3_WB_SECTOR = 1, default):
+// dims {2l, 2l+1} and {64+2l, 65+2l}, so a 128-bit warp access covers 512 contiguous bytes = whole
+// 32-byte sectors.  The plain map (dims 4l .. 4l+3) makes every access touch half of each sector,
+// and every sector twice.  Every array the write-back touches is per-dimension independent, so the
+// map is free there: 148.8 -> 141.8 us per launch (profiles/r1_consumer_experiments.txt).  The
+// proposal stage keeps the plain map: in the sector map the Philox words of a 4-dim slot and the
+// jump statistic have to be passed between lanes by ~20 shuffles, which cost more than the halved
+// sector count saved (153.2 against 143.6 us, branch exp/split-writeback).
+#ifndef BPM_V3_WB_SECTOR
+#define BPM_V3_WB_SECTOR 1
+#endif
+struct WbMap {
+  int o0, o1;      // element offsets of the lane's two 16-byte chunks inside a row
+  bool h0, h1;     // chunk inside the row
 };
-// `mid(row)` runs once per tile row between the issue of that row's gathers and their first
-// use: independent work (the write-back of the previous tile's row) placed in the memory shadow.
-template <bool REPLAY, int NPAIR, typename Mid = NoMid>
+__device__ __forceinline__ WbMap wb_map(int d, int lane) {
+  WbMap m;
+#if BPM_V3_WB_SECTOR
+  m.o0 = 2 * lane; m.o1 = 64 + 2 * lane;
+#else
+  m.o0 = 4 * lane; m.o1 = 4 * lane + 2;
+#endif
+  m.h0 = m.o0 < d; m.h1 = m.o1 < d;     // d is even
+  return m;
+}
+
+// NPAIR: 3 = DREAM with del_pairs == 3 (the reference default), 0 = read algo / del_pairs at run time
+template <bool REPLAY, int NPAIR>
 __device__ __forceinline__ void tile_stage_propose_v3(const PhaseArgs& a, const GaussTables& tb,
                                                       TileScratch& T, double* __restrict__ P, int pld,
-                                                      int gwarp, int gwarps, int lane, Mid mid = Mid()) {
+                                                      int gwarp, int gwarps, int lane) {
   const int d = a.d;
   const bool dream = NPAIR == 3 ? true : a.algo == BPM_ALGO_DREAM;
   const int npair = NPAIR == 3 ? 3 : (dream ? a.del_pairs : 1);
@@ -840,7 +863,6 @@ __device__ __forceinline__ void tile_stage_propose_v3(const PhaseArgs& a, const 
         *reinterpret_cast<double2*>(prow) = make_double2(0.0, 0.0);
         *reinterpret_cast<double2*>(prow + 2) = make_double2(0.0, 0.0);
       }
-      mid(row);
       continue;
     }
     double cur[4] = {0, 0, 0, 0}, S[4] = {0, 0, 0, 0}, var[4] = {0, 0, 0, 0};
@@ -863,7 +885,6 @@ __device__ __forceinline__ void tile_stage_propose_v3(const PhaseArgs& a, const 
         }
       }
     }
-    mid(row);
     if (act) {
       if (welford_var) { var[0] = w0.x; var[1] = w0.y; var[2] = w1.x; var[3] = w1.y; }
       cur[0] = u0.x; cur[1] = u0.y; cur[2] = u1.x; cur[3] = u1.y;
@@ -1062,27 +1083,6 @@ __device__ __forceinline__ void warp_stage_draws(const PhaseArgs& a, const Phase
 // One chain row of the write-back, split into issue / finish so that every load of a row pair
 // (moments of both rows, and the own row of a rejected chain -- an L2 hit, the proposal stage
 // read it moments ago) is in flight before the first one is consumed.
-// Lane -> dimension map of the write-back (every array it touches is per-dimension independent):
-// BPM_V3_WB_SECTOR = 1: lane l owns dims {2l, 2l+1} and {64+2l, 65+2l}, so one 128-bit warp access
-// covers 512 contiguous bytes = whole 32-byte sectors; 0: dims 4l .. 4l+3 (each access touches
-// half of every sector, and every sector twice).
-#ifndef BPM_V3_WB_SECTOR
-#define BPM_V3_WB_SECTOR 1
-#endif
-struct WbMap {
-  int o0, o1;      // element offsets of the lane's two 16-byte chunks inside a row
-  bool h0, h1;     // chunk inside the row
-};
-__device__ __forceinline__ WbMap wb_map(int d, int lane) {
-  WbMap m;
-#if BPM_V3_WB_SECTOR
-  m.o0 = 2 * lane; m.o1 = 64 + 2 * lane;
-#else
-  m.o0 = 4 * lane; m.o1 = 4 * lane + 2;
-#endif
-  m.h0 = m.o0 < d; m.h1 = m.o1 < d;     // d is even
-  return m;
-}
 struct WbRow {
   double2 m0, m1, v0, v1, x0, x1;
   int c, acc;
