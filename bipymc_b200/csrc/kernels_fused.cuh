@@ -109,6 +109,7 @@ __device__ __forceinline__ void load_W_shared(double* Ws, double* mus, const dou
 }
 
 inline bool gauss_rows_supported(int d, int r) { return d <= 112 && r <= kWld && d >= 5; }
+constexpr size_t kMaxDynSmem = 232448;   // opt-in dynamic shared memory per CTA on sm_100
 inline int gauss_pld(int d) { return d | 1; }
 
 // ---- stand-alone batched likelihood with the same tile arithmetic ------------------
@@ -1392,6 +1393,12 @@ inline int try_fused_phase(const TargetView& tv, const PhaseArgs& a, cudaStream_
     const size_t sm = fused_gauss_smem(a.d);
     const int n_tiles = (a.nA + kTileRows - 1) / kTileRows;
     cudaError_t e;
+    // shared memory decides which variants exist for this d (227 KB per CTA): d = 108 fits variant 3
+    // only, d = 112 none -- the caller then runs the split path
+    const bool v3_ok = (a.d % 4) == 0 && a.ld == a.d && fused_v3_smem(a.d) <= kMaxDynSmem;
+    const bool v12_ok = sm <= kMaxDynSmem;
+    if (!v3_ok && !v12_ok) return 0;
+    if (variant == 2 && !v12_ok) variant = 1;
     if (variant == 2) {
       int grid = (n_tiles + 1) / 2;
       grid = grid > 148 ? 148 : (grid < 1 ? 1 : grid);
@@ -1406,7 +1413,7 @@ inline int try_fused_phase(const TargetView& tv, const PhaseArgs& a, cudaStream_
         if (e != cudaSuccess) return 1;
         fused_gauss_kernel<REPLAY, true><<<grid, 2 * kHalfThreads, sm, s>>>(a, g);
       }
-    } else if (variant == 3 || (a.d % 4) != 0 || a.ld != a.d) {
+    } else if (v12_ok && (variant == 3 || !v3_ok)) {
       const int grid = n_tiles > 148 ? 148 : (n_tiles < 1 ? 1 : n_tiles);
       if (tv.mu_is_zero) {
         e = cudaFuncSetAttribute(fused_gauss_ws_kernel<REPLAY, false>,

@@ -97,6 +97,19 @@ def test_native_dream_gauss_matches_oracle_replay(dim, n, fused):
     _native_vs_oracle(s, otargets.GaussND(dim=dim).ln_like, gens=8, k0=3)
 
 
+@pytest.mark.parametrize("dim,n", [(8, 20), (64, 70), (68, 70), (104, 300), (108, 130), (112, 130)])
+def test_native_dream_gauss_fused_edge_dims(dim, n):
+    """Dimensions at the edges of the default fused kernel: one / two / partially filled 16-byte chunks
+    per lane in the write-back map (8, 64, 68), 104 with five tiles, the largest d whose tiles fit shared
+    memory (108, default variant only), and the first that does not (112: the engine falls back to the
+    split path).  More than one tile, last tile partial."""
+    from bipymc_b200 import DreamMpi, targets
+    np.random.seed(4)
+    s = DreamMpi(targets.Gauss_100D(dim=dim).ln_like, np.zeros(dim), n_chains=n, n_cr_gen=2,
+                 burnin_gen=1000, seed=17, fused=1, varepsilon=0.5)
+    _native_vs_oracle(s, otargets.GaussND(dim=dim).ln_like, gens=6, k0=2)
+
+
 def test_native_linefit_matches_oracle_replay():
     from bipymc_b200 import DreamMpi, targets
     np.random.seed(4)
