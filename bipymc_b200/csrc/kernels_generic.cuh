@@ -269,7 +269,6 @@ __global__ void __launch_bounds__(kThreads) accept_kernel(const PhaseArgs a) {
   bool valid = gid < L.n_self;
   const int c = valid ? L.self[gid] : 0;
   valid = valid && c >= a.chain_lo && c < a.chain_hi;
-  const int nblk = (a.d + 3) >> 2;
   int acc = 0;
   double lp = 0.0;
   if (valid) {
@@ -282,31 +281,25 @@ __global__ void __launch_bounds__(kThreads) accept_kernel(const PhaseArgs a) {
     }
     double* xc = a.X + (size_t)c * a.ld;
     const double* pr = a.prop + (size_t)gid * a.ld;
-#pragma unroll
-    for (int t = 0; t < kMaxBlocksPerLane; ++t) {
-      const int b = sub + t * LPC;
-      if (b < nblk) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int i = 4 * b + q;
-          if (i < a.d) {
-            double s = xc[i];
-            if (acc) {
-              s = pr[i];
-              xc[i] = s;
-              store_peers1(a, (size_t)c * a.ld + i, s);
-            }
-            if (a.mean) {  // Welford update with the appended row (chain.py:51-54)
-              const size_t o = (size_t)(c - a.chain_lo) * a.ld + i;
-              double mu = a.mean[o], v = a.m2[o];
-              welford_update(s, a.inv_n1, mu, v);
-              a.mean[o] = mu;
-              a.m2[o] = v;
-            }
-            if (a.hist_row) a.hist_row[(size_t)(c - a.chain_lo) * a.ld + i] = s;
-          }
-        }
+    // every array here is per-dimension independent, so the lanes of a chain take CONSECUTIVE
+    // dimensions (whole 32-byte sectors per access) instead of the proposal stage's 4-dim blocks
+    // (d = 1000 generation 3.34 -> 3.30 ms, gpurun_out/ab10 in profiles/r1_consumer_experiments.txt)
+#pragma unroll 4
+    for (int i = sub; i < a.d; i += LPC) {
+      double s = xc[i];
+      if (acc) {
+        s = pr[i];
+        xc[i] = s;
+        store_peers1(a, (size_t)c * a.ld + i, s);
       }
+      if (a.mean) {  // Welford update with the appended row (chain.py:51-54)
+        const size_t o = (size_t)(c - a.chain_lo) * a.ld + i;
+        double mu = a.mean[o], v = a.m2[o];
+        welford_update(s, a.inv_n1, mu, v);
+        a.mean[o] = mu;
+        a.m2[o] = v;
+      }
+      if (a.hist_row) a.hist_row[(size_t)(c - a.chain_lo) * a.ld + i] = s;
     }
     if (sub == 0) {
       if (acc) a.lnl[c] = lp;
