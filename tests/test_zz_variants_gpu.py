@@ -1,0 +1,46 @@
+"""Native-stream parity (device step == oracle replay of the dumped draws, 1e-12) for the code paths of the
+default fused Gaussian kernel that the golden / headline configurations do not reach:
+  * the run-time-general proposal stage (DREAM with del_pairs != 3, DE-MC) at d = 100, several tiles;
+  * a target with a non-zero mean (the CENTER instantiation of the tile product).
+Runs last (file name) so that a regression here does not mask the main parity suite under `pytest -x`."""
+import numpy as np
+import pytest
+from scipy.stats import multivariate_normal
+
+from oracle import targets as otargets
+from test_native_gpu import _native_vs_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("del_pairs,n_cr", [(1, 3), (2, 5), (5, 2)])
+def test_native_dream_gauss100_other_pair_counts(del_pairs, n_cr):
+    from bipymc_b200 import DreamMpi, targets
+    np.random.seed(11)
+    s = DreamMpi(targets.Gauss_100D().ln_like, np.zeros(100), n_chains=150, n_cr_gen=2, burnin_gen=1000,
+                 seed=5, fused=1, varepsilon=0.5, del_pairs=del_pairs, n_cr=n_cr)
+    _native_vs_oracle(s, otargets.GaussND(dim=100).ln_like, gens=6, k0=2)
+
+
+def test_native_demc_gauss100_several_tiles():
+    from bipymc_b200 import DeMcMpi, targets
+    np.random.seed(12)
+    s = DeMcMpi(targets.Gauss_100D().ln_like, np.zeros(100), n_chains=150, seed=6, fused=1, varepsilon=0.5)
+    _native_vs_oracle(s, otargets.GaussND(dim=100).ln_like, gens=12, k0=5, run_kwargs=dict(epsilon=1e-9))
+
+
+@pytest.mark.parametrize("dim", [40, 100])
+def test_native_dream_gauss_with_nonzero_mean(dim):
+    from bipymc_b200 import DreamMpi, targets
+    rs = np.random.RandomState(3)
+    mean = rs.randn(dim)
+    t = targets.Gauss_100D(dim=dim, mean=mean)
+    rv = multivariate_normal(mean, t.cov)
+
+    def oracle_lnl(y):
+        with np.errstate(divide="ignore"):
+            return np.log(rv.pdf(y))
+
+    np.random.seed(13)
+    s = DreamMpi(t.ln_like, mean, n_chains=130, n_cr_gen=2, burnin_gen=1000, seed=8, fused=1, varepsilon=0.5)
+    _native_vs_oracle(s, oracle_lnl, gens=6, k0=2)
