@@ -1257,6 +1257,9 @@ fused_gauss_v3_kernel(const PhaseArgs a, const GaussArgs g) {
         const TileScratch& T = *reinterpret_cast<const TileScratch*>(Tbuf + ((i - 1) % 3) * t_stride);
         mbar_wait(DONE + b2, ((i - 1) >> 1) & 1);
         warp_stage_writeback(a, T, P, pld, pw, lane);
+        // the write-back reads the tile in its own lane map: order those reads before the lanes that
+        // overwrite the same rows in the proposal stage of tile i+1
+        __syncwarp();
       }
     }
   }
