@@ -39,6 +39,24 @@ CASES = {
 }
 
 
+# Second batch (same recipe): the run-time-general proposal stage at d = 100 / 40 -- DREAM with one and
+# with five difference pairs, other n_cr, DE-MC with an explicit gamma, an odd population and two
+# k % 10 jump generations; chains start dispersed (varepsilon) so that proposals do get rejected.
+# Kept apart from CASES so that the GPU suite runs them last.
+EXTRA_CASES = {
+    "gauss100_dream_pairs1": _case("dream", "gauss100", np.zeros(100), 10, 12, seed=49,
+                                   ctor_kwargs=dict(n_cr_gen=3, burnin_gen=9, del_pairs=1, n_cr=5, varepsilon=0.25)),
+    "gauss40_dream_pairs5": _case("dream", "gauss40", np.zeros(40), 16, 10, seed=50,
+                                  ctor_kwargs=dict(n_cr_gen=2, burnin_gen=100, del_pairs=5, n_cr=2,
+                                                   gamma_scale=1.1, varepsilon=0.25),
+                                  run_kwargs=dict(u_epsilon=5e-3)),
+    "gauss100_demc_gamma": _case("demc", "gauss100", np.zeros(100), 9, 22, seed=53,
+                                 ctor_kwargs=dict(varepsilon=1.0),
+                                 run_kwargs=dict(gamma=0.3, epsilon=1e-8, flip=0.7)),
+}
+ALL_CASES = dict(CASES, **EXTRA_CASES)
+
+
 # Serial DeMc (bipymc/samplers.py:237-324, delayed accept): run_mcmc(n, theta_0, **run_kwargs)
 SERIAL_CASES = {
     "serial_banana": dict(target="banana", theta_0=[0.0, 0.0], n_chains=12, n=12 * 41, seed=51,

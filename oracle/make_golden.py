@@ -12,7 +12,8 @@ tests/test_oracle_golden.py replays the same seeds through oracle/demc_dream.py 
 demands bit-identical results; the GPU parity tests compare the CUDA path against the
 same files.
 
-Usage:  python oracle/make_golden.py            (rewrites tests/golden/ref_*.npz)
+Usage:  python oracle/make_golden.py                      (rewrites tests/golden/ref_*.npz)
+        python oracle/make_golden.py --only=name1,name2   (only those cases)
 """
 import os
 import sys
@@ -32,7 +33,7 @@ from bipymc.utils import banana_rv, dblgauss_rv, d100_gauss  # noqa: E402
 
 from bipymc.samplers import DeMc  # noqa: E402
 
-from oracle.cases import CASES, SERIAL_CASES, linefit_lnprob_ref  # noqa: E402
+from oracle.cases import ALL_CASES, SERIAL_CASES, linefit_lnprob_ref  # noqa: E402
 
 
 def target_fn(name):
@@ -82,7 +83,11 @@ def run_serial_case(case):
 def main():
     gdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gdir, exist_ok=True)
+    only = [a.split("=", 1)[1].split(",") for a in sys.argv if a.startswith("--only=")]
+    only = set(only[0]) if only else None
     for name, case in SERIAL_CASES.items():
+        if only is not None and name not in only:
+            continue
         out = run_serial_case(case)
         path = os.path.join(gdir, "ref_%s.npz" % name)
         np.savez_compressed(path, **out)
@@ -91,7 +96,9 @@ def main():
             out["n_accepted"], out["n_rejected"], os.path.relpath(path, ROOT)))
     if "--serial-only" in sys.argv:
         return
-    for name, case in CASES.items():
+    for name, case in ALL_CASES.items():
+        if only is not None and name not in only:
+            continue
         out = run_case(case)
         path = os.path.join(gdir, "ref_%s.npz" % name)
         np.savez_compressed(path, **out)

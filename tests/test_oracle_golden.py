@@ -8,7 +8,7 @@ import warnings
 import numpy as np
 import pytest
 
-from oracle.cases import CASES, oracle_target
+from oracle.cases import ALL_CASES, oracle_target
 from oracle.demc_dream import OracleSampler
 from oracle import replay as orp
 
@@ -16,7 +16,7 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
 def run_oracle(name, record=False):
-    case = CASES[name]
+    case = ALL_CASES[name]
     fn, kw = oracle_target(case["target"])
     np.random.seed(case["seed"])
     s = OracleSampler(fn, case["theta_0"], n_chains=case["n_chains"], algo=case["algo"],
@@ -27,7 +27,7 @@ def run_oracle(name, record=False):
     return s, tr
 
 
-@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("name", sorted(ALL_CASES))
 def test_oracle_matches_reference_bit_for_bit(name):
     g = np.load(os.path.join(GOLD, "ref_%s.npz" % name))
     s, _ = run_oracle(name)
@@ -37,7 +37,7 @@ def test_oracle_matches_reference_bit_for_bit(name):
     assert int(s.n_accepted) == int(g["n_accepted"])
     assert int(s.n_rejected) == int(g["n_rejected"])
     assert s.acceptance_fraction == float(g["acceptance_fraction"])
-    if CASES[name]["algo"] == "dream":
+    if ALL_CASES[name]["algo"] == "dream":
         assert np.array_equal(s.p_cr, g["p_cr"])
         assert np.array_equal(s.delta_m, g["delta_m"])
         assert np.array_equal(s.n_cr_updates, g["n_cr_updates"])
@@ -45,11 +45,11 @@ def test_oracle_matches_reference_bit_for_bit(name):
     assert np.array_equal(mean, g["mean"]) and np.array_equal(std, g["std"])
 
 
-@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("name", sorted(ALL_CASES))
 def test_replay_form_matches_scalar_oracle(name):
     """Feeding the recorded draws to oracle/replay.py reproduces every generation's state
     and accept flags exactly, and p_cr at generation boundaries to rounding."""
-    case = CASES[name]
+    case = ALL_CASES[name]
     s, traces = run_oracle(name, record=True)
     fn, kw = oracle_target(case["target"])
     lnl = orp.scalar_batch(lambda th: fn(th, **kw))

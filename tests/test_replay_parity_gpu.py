@@ -9,7 +9,7 @@ import warnings
 import numpy as np
 import pytest
 
-from oracle.cases import CASES, oracle_target
+from oracle.cases import ALL_CASES, CASES, oracle_target
 from oracle.demc_dream import OracleSampler
 
 pytestmark = pytest.mark.gpu
@@ -31,7 +31,7 @@ def device_target(name):
 
 
 def oracle_traces(name):
-    case = CASES[name]
+    case = ALL_CASES[name]
     fn, kw = oracle_target(case["target"])
     np.random.seed(case["seed"])
     s = OracleSampler(fn, case["theta_0"], n_chains=case["n_chains"], algo=case["algo"],
@@ -44,7 +44,7 @@ def oracle_traces(name):
 
 def make_sampler(name, mode, fused=True):
     from bipymc_b200 import DeMcMpi, DreamMpi
-    case = CASES[name]
+    case = ALL_CASES[name]
     cls = DreamMpi if case["algo"] == "dream" else DeMcMpi
     np.random.seed(case["seed"])
     kw = dict(case["ctor_kwargs"])
@@ -69,7 +69,7 @@ def make_sampler(name, mode, fused=True):
 
 
 def check_against_reference(name, s, sink, traces, osampler):
-    case = CASES[name]
+    case = ALL_CASES[name]
     g = np.load(os.path.join(GOLD, "ref_%s.npz" % name))
     ref = g["history"]
     hist = s._hist.tensor()[:, :, :s.dim].cpu().numpy()
@@ -115,7 +115,7 @@ def test_replay_device_target(name, fused):
     osampler, traces = oracle_traces(name)
     s = make_sampler(name, "device", fused=fused)
     sink = []
-    s.run_mcmc(CASES[name]["n"], _replay=traces, _trace=sink, **CASES[name]["run_kwargs"])
+    s.run_mcmc(ALL_CASES[name]["n"], _replay=traces, _trace=sink, **ALL_CASES[name]["run_kwargs"])
     check_against_reference(name, s, sink, traces, osampler)
 
 
@@ -130,7 +130,7 @@ def test_replay_user_likelihoods(name, mode):
     s = make_sampler(name, mode)
     assert s._mode() == mode
     sink = []
-    s.run_mcmc(CASES[name]["n"], _replay=traces, _trace=None, **CASES[name]["run_kwargs"])
+    s.run_mcmc(ALL_CASES[name]["n"], _replay=traces, _trace=None, **ALL_CASES[name]["run_kwargs"])
     g = np.load(os.path.join(GOLD, "ref_%s.npz" % name))
     hist = s._hist.tensor()[:, :, :s.dim].cpu().numpy()
     err = np.abs(hist - g["history"]) / np.maximum(1.0, np.abs(g["history"]))

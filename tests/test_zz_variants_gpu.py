@@ -44,3 +44,16 @@ def test_native_dream_gauss_with_nonzero_mean(dim):
     np.random.seed(13)
     s = DreamMpi(t.ln_like, mean, n_chains=130, n_cr_gen=2, burnin_gen=1000, seed=8, fused=1, varepsilon=0.5)
     _native_vs_oracle(s, oracle_lnl, gens=6, k0=2)
+
+
+# ---- RNG-replay parity against the second batch of golden vectors (oracle/cases.py: EXTRA_CASES) --------
+@pytest.mark.parametrize("fused", [1, 0], ids=["fused", "split"])
+@pytest.mark.parametrize("name", sorted(__import__("oracle.cases", fromlist=["EXTRA_CASES"]).EXTRA_CASES))
+def test_replay_extra_golden_cases(name, fused):
+    from oracle.cases import ALL_CASES
+    from test_replay_parity_gpu import check_against_reference, make_sampler, oracle_traces
+    osampler, traces = oracle_traces(name)
+    s = make_sampler(name, "device", fused=fused)
+    sink = []
+    s.run_mcmc(ALL_CASES[name]["n"], _replay=traces, _trace=sink, **ALL_CASES[name]["run_kwargs"])
+    check_against_reference(name, s, sink, traces, osampler)
