@@ -347,6 +347,9 @@ def run_ours(args):
                            "l2": "working set per generation (state 80 MB + moments 160 MB + history "
                                  "row 80 MB per GPU) exceeds the 126 MB L2; no explicit flush"},
                 "ms_per_step_event_pass": ms_prof / K,
+                # one proposal + ONE likelihood evaluation per chain-step (the cached ln_like of the current
+                # state replaces the reference's second evaluation, samplers.py:330)
+                "proposals_and_lnl_evals_per_s": value,
                 "acceptance_fraction": acc_frac, "gpu_launches": launches,
                 "kernel_ms": dict(zip(kinds, ms_k)), "kernel_launches": dict(zip(kinds, n_k)),
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": ck}
