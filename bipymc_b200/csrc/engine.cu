@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -757,6 +758,33 @@ int bpm_generations_host(bpm_handle h, double* X_host, double* lnl_host, int64_t
     }
   }
   cudaStream_t s = 0;
+  // Opt-in (BIPYMC_B200_HOST_PEER=1, not yet measured -- DESIGN.md section 9): the mapped host population is
+  // handed to the phase kernels as one more peer replica, so every accepted row is stored to the host from
+  // inside the write-back (overlapped with compute) and no changed-rows pass follows the generation; the
+  // cached likelihoods (8 N bytes) come back with one plain copy.
+  static const bool host_peer_opt = [] {
+    const char* e = getenv("BIPYMC_B200_HOST_PEER");
+    return e && e[0] == '1';
+  }();
+  if (X_map && host_peer_opt && h->n_peers < BPM_MAX_PEERS) {
+    unsigned long long acc0 = 0, acc1 = 0;
+    CU_TRY(cudaMemcpyAsync(&acc0, h->counters, sizeof(acc0), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(h->hX, X_host, nx, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(h->hL, lnl_host, nl, cudaMemcpyHostToDevice, s));
+    bpm_state st;
+    memset(&st, 0, sizeof(st));
+    st.X = h->hX; st.lnl = h->hL; st.hist_len = g_abs0;
+    h->peers[h->n_peers++] = X_map;
+    int rc = 0;
+    for (int g = 0; g < n_gen && rc == 0; ++g) rc = h->generation<false>(&st, k_gen0 + g, nullptr, nullptr, s);
+    h->peers[--h->n_peers] = nullptr;
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(lnl_host, h->hL, nl, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(&acc1, h->counters, sizeof(acc1), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    h->last_d2h_bytes = (acc1 - acc0) * (sizeof(double) * h->cfg.ld) + nl + 2 * sizeof(acc0);
+    return 0;
+  }
   CU_TRY(cudaMemcpyAsync(h->hX, X_host, nx, cudaMemcpyHostToDevice, s));
   CU_TRY(cudaMemcpyAsync(h->hL, lnl_host, nl, cudaMemcpyHostToDevice, s));
   bpm_state st;
