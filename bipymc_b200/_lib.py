@@ -28,7 +28,8 @@ class Config(C.Structure):
 
 class State(C.Structure):
     _fields_ = [("X", C.c_void_p), ("lnl", C.c_void_p), ("mean", C.c_void_p), ("m2", C.c_void_p),
-                ("history", C.c_void_p), ("hist_len", C.c_int64), ("mom_len", C.c_int64)]
+                ("history", C.c_void_p), ("hist_len", C.c_int64), ("mom_len", C.c_int64),
+                ("pending", C.c_int64)]
 
 
 class Replay(C.Structure):
@@ -95,6 +96,7 @@ SIGNATURES = {
     "bpm_set_peers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32]),
     "bpm_last_d2h_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "bpm_moments_from_history": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p]),
+    "bpm_flush": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p]),
     "bpm_omega_track": (C.c_int, [C.c_void_p, C.c_int32]),
     "bpm_omega": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "bpm_outlier_reset": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p, C.c_void_p,

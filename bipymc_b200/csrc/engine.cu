@@ -91,6 +91,8 @@ struct bpm_engine {
   // split-path generation context
   bpm::PhaseArgs cur;
   bool cur_replay = false;
+  bool cur_lazy = false;       // this generation's bpm_phase launches follow the lazy protocol
+  int cur_phases_run = 0;
   bool in_generation = false;
   int64_t cur_k_gen = 0;
   // host-entry buffers
@@ -189,13 +191,17 @@ struct bpm_engine {
 
   // Parameter block of one half-phase of generation k_gen.
   bpm::PhaseArgs make_args(const bpm_state* st, int64_t k_gen, int phase, const bpm_replay* rp,
-                           const bpm_trace_out* tr) const {
+                           const bpm_trace_out* tr, bool lazy = false) const {
     bpm::PhaseArgs a;
     memset(&a, 0, sizeof(a));
     a.X = st->X; a.lnl = st->lnl; a.mean = st->mean; a.m2 = st->m2;
     a.hist_base = (rp && st->history) ? st->history : nullptr;
-    a.hist_row = st->history ? st->history + (size_t)st->hist_len * (cfg.chain_hi - cfg.chain_lo) * cfg.ld
-                             : nullptr;
+    const size_t hstride = (size_t)(cfg.chain_hi - cfg.chain_lo) * cfg.ld;
+    a.hist_row = st->history ? st->history + (size_t)st->hist_len * hstride : nullptr;
+    a.lazy = lazy ? 1 : 0;
+    a.pending = (lazy && st->pending) ? 1 : 0;
+    a.hist_cur = (a.pending && st->history && st->hist_len > 0) ? st->history + (size_t)(st->hist_len - 1) * hstride
+                                                                 : nullptr;
     a.perm = perm; a.flip = flip; a.phase = phase;
     a.loc_list = loc_list; a.loc_cnt = loc_cnt;     // both nullptr on an unsharded handle
     a.N = cfg.n_chains; a.nA = nA; a.d = cfg.dim; a.ld = cfg.ld;
@@ -231,6 +237,26 @@ struct bpm_engine {
     if (rp) a.rp = *rp;
     if (tr) a.tr = *tr;
     return a;
+  }
+
+  // Does phase() run the lazy-protocol kernel for this handle?  (kernels_fused.cuh: fused_plan_is_v3)
+  bool lazy_plan() const {
+    return fused_ok && !serial() && bpm::fused_plan_is_v3(target, cfg.dim, cfg.ld, gauss_r, fused_ok);
+  }
+  // bpm_flush: history row hist_len - 1 and its moment sample, left pending by a lazy generation
+  int flush(bpm_state* st, cudaStream_t s) {
+    if (!st->pending) return 0;
+    const int nloc = cfg.chain_hi - cfg.chain_lo;
+    const int64_t mom = st->mom_len > 0 ? st->mom_len : st->hist_len;
+    double* hist_cur = (st->history && st->hist_len > 0)
+                           ? st->history + (size_t)(st->hist_len - 1) * nloc * cfg.ld : nullptr;
+    if (st->mean || hist_cur) {
+      bpm::flush_pending_kernel<<<cdiv((int64_t)nloc * cfg.ld, 256), 256, 0, s>>>(
+          st->X, st->mean, st->m2, hist_cur, cfg.chain_lo, cfg.chain_hi, cfg.dim, cfg.ld, 1.0 / (double)mom);
+      CU_TRY(cudaGetLastError());
+    }
+    st->pending = 0;
+    return 0;
   }
 
   int begin(const bpm_state* st, const bpm_replay* rp, cudaStream_t s) {
@@ -363,15 +389,17 @@ struct bpm_engine {
 
   template <bool REPLAY>
   int phase(const bpm_state* st, int64_t k_gen, int ph, const bpm_replay* rp, const bpm_trace_out* tr,
-            cudaStream_t s) {
-    bpm::PhaseArgs a = make_args(st, k_gen, ph, rp, tr);
-    if (fused_ok && !a.tr.prop && !serial()) {
+            cudaStream_t s, bool lazy) {
+    bpm::PhaseArgs a = make_args(st, k_gen, ph, rp, tr, lazy);
+    if (fused_ok && !serial()) {
       int done = 0;
       prof_begin(4, s);
-      BPM_TRY(bpm::try_fused_phase<REPLAY>(*this_target(), a, s, fused_ok, &done));
+      if (bpm::try_fused_phase<REPLAY>(*this_target(), a, s, fused_ok, &done))
+        return fail(std::string("fused half-phase launch failed: ") + cudaGetErrorString(cudaGetLastError()));
       if (done) { prof_end(s); return 0; }
       if (prof_on) { ev_pool.push_back(recs.back().a); ev_pool.push_back(recs.back().b); recs.pop_back(); }
     }
+    if (lazy) return fail("internal: lazy protocol planned but the fused kernel did not launch");
     prof_begin(1, s);
     BPM_TRY(launch_propose<REPLAY>(a, s));
     prof_end(s);
@@ -415,13 +443,19 @@ struct bpm_engine {
   template <bool REPLAY>
   int generation(bpm_state* st, int64_t k_gen, const bpm_replay* rp, const bpm_trace_out* tr,
                  cudaStream_t s) {
+    // lazy protocol: the v3 kernel folds the row the previous generation left pending and leaves its own
+    // pending; every other path (and a replay step, whose exact np.std walks the stored history) needs
+    // the row materialised first
+    const bool lazy = lazy_plan();
+    if (st->pending && (!lazy || REPLAY)) BPM_TRY(flush(st, s));
     BPM_TRY(begin(st, rp, s));
-    BPM_TRY(phase<REPLAY>(st, k_gen, 0, rp, tr, s));
-    if (!serial()) BPM_TRY(phase<REPLAY>(st, k_gen, 1, rp, tr, s));
+    BPM_TRY(phase<REPLAY>(st, k_gen, 0, rp, tr, s, lazy));
+    if (!serial()) BPM_TRY(phase<REPLAY>(st, k_gen, 1, rp, tr, s, lazy));
     BPM_TRY(end(s));
     BPM_TRY(track_omega(st, s));
     st->hist_len += 1;
     if (st->mom_len > 0) st->mom_len += 1;
+    st->pending = lazy ? 1 : 0;
     return 0;
   }
 };
@@ -657,6 +691,10 @@ int bpm_begin_generation(bpm_handle h, bpm_state* st, int64_t k_gen, const bpm_r
                          bpm_stream stream) {
   if (!h || !st) return fail("null argument");
   CU_TRY(cudaSetDevice(h->cfg.device));
+  // bpm_phase may run the lazy-protocol kernel; bpm_propose / bpm_accept are eager
+  h->cur_lazy = h->lazy_plan() && !(h->target == BPM_TARGET_EXTERNAL);
+  h->cur_phases_run = 0;
+  if (st->pending && (!h->cur_lazy || rp)) BPM_TRY(h->flush(st, (cudaStream_t)stream));
   BPM_TRY(h->begin(st, rp, (cudaStream_t)stream));
   h->cur = h->make_args(st, k_gen, 0, rp, nullptr);
   h->cur_replay = rp != nullptr;
@@ -670,6 +708,12 @@ int bpm_propose(bpm_handle h, bpm_state* st, int32_t phase, double** prop, int32
   if (!h || !st) return fail("null argument");
   if (!h->in_generation) return fail("bpm_propose outside bpm_begin_generation / bpm_end_generation");
   CU_TRY(cudaSetDevice(h->cfg.device));
+  if (h->cur_lazy) {     // the caller drives a built-in target through the split API after all: go eager
+    if (h->cur_phases_run) return fail("bpm_propose after bpm_phase in the same generation");
+    BPM_TRY(h->flush(st, (cudaStream_t)stream));
+    h->cur_lazy = false;
+    h->cur = h->make_args(st, h->cur_k_gen, 0, h->cur_replay ? &h->cur.rp : nullptr, nullptr);
+  }
   h->cur.phase = phase;
   h->cur.X = st->X; h->cur.lnl = st->lnl;
   if (h->cur_replay) BPM_TRY(h->launch_propose<true>(h->cur, (cudaStream_t)stream));
@@ -713,8 +757,9 @@ int bpm_phase(bpm_handle h, bpm_state* st, int32_t phase, bpm_stream stream) {
   CU_TRY(cudaSetDevice(h->cfg.device));
   const bpm_replay* rp = h->cur_replay ? &h->cur.rp : nullptr;
   const int64_t k_gen = h->cur_k_gen;
-  if (h->cur_replay) return h->phase<true>(st, k_gen, phase, rp, nullptr, (cudaStream_t)stream);
-  return h->phase<false>(st, k_gen, phase, nullptr, nullptr, (cudaStream_t)stream);
+  h->cur_phases_run += 1;
+  if (h->cur_replay) return h->phase<true>(st, k_gen, phase, rp, nullptr, (cudaStream_t)stream, h->cur_lazy);
+  return h->phase<false>(st, k_gen, phase, nullptr, nullptr, (cudaStream_t)stream, h->cur_lazy);
 }
 
 int bpm_end_generation(bpm_handle h, bpm_state* st, bpm_stream stream) {
@@ -725,6 +770,7 @@ int bpm_end_generation(bpm_handle h, bpm_state* st, bpm_stream stream) {
   BPM_TRY(h->track_omega(st, (cudaStream_t)stream));
   st->hist_len += 1;
   if (st->mom_len > 0) st->mom_len += 1;
+  st->pending = h->cur_lazy ? 1 : 0;
   h->in_generation = false;
   return 0;
 }
@@ -869,9 +915,16 @@ int bpm_set_peers(bpm_handle h, double* const* peer_X, int32_t n_peers) {
   return 0;
 }
 
+int bpm_flush(bpm_handle h, bpm_state* st, bpm_stream stream) {
+  if (!h || !st || !st->X) return fail("null argument");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  return h->flush(st, (cudaStream_t)stream);
+}
+
 int bpm_moments_from_history(bpm_handle h, bpm_state* st, bpm_stream stream) {
   if (!h || !st || !st->history || !st->mean || !st->m2) return fail("null argument");
   CU_TRY(cudaSetDevice(h->cfg.device));
+  BPM_TRY(h->flush(st, (cudaStream_t)stream));       // the last history row may still be pending
   const int64_t tot = (int64_t)(h->cfg.chain_hi - h->cfg.chain_lo) * h->cfg.ld;
   bpm::moments_from_history_kernel<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>(
       st->history, st->hist_len, h->cfg.n_chains, h->cfg.dim, h->cfg.ld, h->cfg.chain_lo,
@@ -942,6 +995,7 @@ int bpm_outlier_reset(bpm_handle h, bpm_state* st, const double* omega, int32_t*
   if (!h || !st || !st->X || !st->lnl) return fail("null argument");
   CU_TRY(cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
+  BPM_TRY(h->flush(st, s));        // a reset overwrites X: the pending row is the PRE-reset state
   const int N = h->cfg.n_chains;
   const bool sharded = h->cfg.chain_lo != 0 || h->cfg.chain_hi != N;
   if (!h->omega_buf) {
@@ -990,6 +1044,7 @@ int bpm_outlier_reset(bpm_handle h, bpm_state* st, const double* omega, int32_t*
 
 int bpm_rhat(bpm_handle h, const bpm_state* st, int64_t t0, double* rhat_host, bpm_stream stream) {
   if (!h || !st || !rhat_host) return fail("null argument");
+  if (st->pending) return fail("bpm_rhat: the state has a pending row; call bpm_flush first");
   CU_TRY(cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   const int nloc = h->cfg.chain_hi - h->cfg.chain_lo, d = h->cfg.dim, ld = h->cfg.ld;

@@ -439,6 +439,7 @@ __device__ __forceinline__ void tile_stage_propose(const PhaseArgs& a, const Gau
             pr = demc_prop(cur[q], S[q], nn[q], gamma);
           }
           prow[i] = pr;
+          if (REPLAY && a.tr.prop) a.tr.prop[(size_t)c * d + i] = pr;
         }
       }
     }
@@ -856,6 +857,11 @@ __device__ __forceinline__ void tile_stage_propose_v3(const PhaseArgs& a, const 
   const bool act = 4 * lane < d;                      // d % 4 == 0: a lane owns 4 dims or none
   const bool adapt = dream && a.adapt;
   const bool welford_var = adapt && !(REPLAY && a.hist_base != nullptr);
+  // lazy protocol (PhaseArgs::pending): the chain's CURRENT row -- already in registers here -- is the
+  // history row / moment sample the previous generation left pending; it is folded in now, so the
+  // kernel's tail never re-reads a moment row or a rejected chain's state
+  const bool fold = a.pending && a.mean != nullptr;
+  const bool need_m2 = fold || welford_var;
   for (int row = gwarp; row < kTileRows; row += gwarps) {
     const int c = T.cid[row];
     double* prow = P + row * pld + 4 * lane;          // pld even: 16-byte aligned
@@ -872,9 +878,9 @@ __device__ __forceinline__ void tile_stage_propose_v3(const PhaseArgs& a, const 
       // every row gather of this chain is issued before anything consumes one
       const double* xc = a.X + (size_t)c * a.ld + 4 * lane;
       u0 = ldg2(xc); u1 = ldg2(xc + 2);
-      if (welford_var) {
+      if (need_m2) {
         const double* mp = a.m2 + (size_t)(c - a.chain_lo) * a.ld + 4 * lane;
-        w0 = ldg2(mp); w1 = ldg2(mp + 2);                    // kept in L2: the write-back re-reads it
+        w0 = ld_stream2(mp); w1 = ld_stream2(mp + 2);        // read once per generation
       }
       if constexpr (NPAIR == 3) {
 #pragma unroll
@@ -887,7 +893,7 @@ __device__ __forceinline__ void tile_stage_propose_v3(const PhaseArgs& a, const 
       }
     }
     if (act) {
-      if (welford_var) { var[0] = w0.x; var[1] = w0.y; var[2] = w1.x; var[3] = w1.y; }
+      if (need_m2) { var[0] = w0.x; var[1] = w0.y; var[2] = w1.x; var[3] = w1.y; }
       cur[0] = u0.x; cur[1] = u0.y; cur[2] = u1.x; cur[3] = u1.y;
       if constexpr (NPAIR == 3) {
 #pragma unroll
@@ -911,6 +917,17 @@ __device__ __forceinline__ void tile_stage_propose_v3(const PhaseArgs& a, const 
           S[2] = p == 0 ? df2 : __dadd_rn(S[2], df2);
           S[3] = p == 0 ? df3 : __dadd_rn(S[3], df3);
         }
+      }
+    }
+    // the partner rows are consumed: their landing registers now take the mean row, whose latency hides
+    // behind the draws below; the pending history row leaves straight from the registers
+    double2 mn0 = make_double2(0.0, 0.0), mn1 = mn0;
+    if (act && a.pending) {
+      const size_t o = (size_t)(c - a.chain_lo) * a.ld + 4 * lane;
+      if (fold) { mn0 = ld_stream2(a.mean + o); mn1 = ld_stream2(a.mean + o + 2); }
+      if (a.hist_cur) {
+        st_stream2(a.hist_cur + o, cur[0], cur[1]);
+        st_stream2(a.hist_cur + o + 2, cur[2], cur[3]);
       }
     }
     uint32_t mbits = 0xFu;
@@ -948,6 +965,17 @@ __device__ __forceinline__ void tile_stage_propose_v3(const PhaseArgs& a, const 
     if (act) {
       double e[4], nn[4], prv[4];
       en4<REPLAY>(a, c, lane, e, nn);
+      if (fold) {
+        // Welford update with the pending row (same arithmetic, same order as an eager write-back):
+        // afterwards var[] / mom_len is np.std(chain.chain)^2 over the whole history (dream.py:128)
+        welford_update(cur[0], a.inv_mom, mn0.x, var[0]);
+        welford_update(cur[1], a.inv_mom, mn0.y, var[1]);
+        welford_update(cur[2], a.inv_mom, mn1.x, var[2]);
+        welford_update(cur[3], a.inv_mom, mn1.y, var[3]);
+        const size_t o = (size_t)(c - a.chain_lo) * a.ld + 4 * lane;
+        st_stream2(a.mean + o, mn0.x, mn0.y); st_stream2(a.mean + o + 2, mn1.x, mn1.y);
+        st_stream2(a.m2 + o, var[0], var[1]); st_stream2(a.m2 + o + 2, var[2], var[3]);
+      }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         double pr;
@@ -970,6 +998,11 @@ __device__ __forceinline__ void tile_stage_propose_v3(const PhaseArgs& a, const 
       }
       *reinterpret_cast<double2*>(prow) = make_double2(prv[0], prv[1]);
       *reinterpret_cast<double2*>(prow + 2) = make_double2(prv[2], prv[3]);
+      if (REPLAY && a.tr.prop) {          // replay trace: the proposal vector the reference built (dream.py:85-89)
+        double* tp = a.tr.prop + (size_t)c * d + 4 * lane;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tp[q] = prv[q];
+      }
     }
     if (dream) {
       delta = group_sum_d<32>(delta);
@@ -1081,75 +1114,22 @@ __device__ __forceinline__ void warp_stage_draws(const PhaseArgs& a, const Phase
   __syncwarp();
 }
 
-// One chain row of the write-back, split into issue / finish so that every load of a row pair
-// (moments of both rows, and the own row of a rejected chain -- an L2 hit, the proposal stage
-// read it moments ago) is in flight before the first one is consumed.
-struct WbRow {
-  double2 m0, m1, v0, v1, x0, x1;
-  int c, acc;
-};
-__device__ __forceinline__ void wb_issue(const PhaseArgs& a, const TileScratch& T, const double* __restrict__ P,
-                                         int pld, int row, const WbMap& mp, bool keep, WbRow& w) {
-  const double2 z = make_double2(0.0, 0.0);
-  w.m0 = z; w.m1 = z; w.v0 = z; w.v1 = z; w.x0 = z; w.x1 = z;
-  w.c = T.cid[row];
-  w.acc = w.c >= 0 ? T.acc[row] : 0;
-  if (w.c < 0 || (!w.acc && !keep)) { w.c = -1; return; }
-  const size_t o = (size_t)(w.c - a.chain_lo) * a.ld;
-  if (a.mean) {
-    if (mp.h0) { w.m0 = ld_stream2(a.mean + o + mp.o0); w.v0 = ld_stream2(a.m2 + o + mp.o0); }
-    if (mp.h1) { w.m1 = ld_stream2(a.mean + o + mp.o1); w.v1 = ld_stream2(a.m2 + o + mp.o1); }
+// Accepted rows leave the tile from the CONSUMER warp that decided them: the proposal row is still in
+// shared memory, the stores need no landing registers and nobody waits for them.  Lane map = wb_map
+// (whole 32-byte sectors per warp access).  Rejected chains cost nothing here: their state, history row
+// and moments are handled by the lazy protocol in the next generation's proposal stage.
+__device__ __forceinline__ void cons_store_row(const PhaseArgs& a, const double* __restrict__ prow, int c,
+                                               const WbMap& mp) {
+  const size_t ox = (size_t)c * a.ld;
+  if (mp.h0) {
+    const double2 x = *reinterpret_cast<const double2*>(prow + mp.o0);
+    *reinterpret_cast<double2*>(a.X + ox + mp.o0) = x;
+    store_peers2(a, ox + mp.o0, x.x, x.y);
   }
-  if (w.acc) {
-    const double* prow = P + row * pld;
-    if (mp.h0) w.x0 = *reinterpret_cast<const double2*>(prow + mp.o0);
-    if (mp.h1) w.x1 = *reinterpret_cast<const double2*>(prow + mp.o1);
-  } else {
-    const double* xc = a.X + (size_t)w.c * a.ld;
-    if (mp.h0) w.x0 = ldg2(xc + mp.o0);
-    if (mp.h1) w.x1 = ldg2(xc + mp.o1);
-  }
-}
-__device__ __forceinline__ void wb_finish(const PhaseArgs& a, const WbMap& mp, WbRow& w) {
-  if (w.c < 0) return;
-  const size_t o = (size_t)(w.c - a.chain_lo) * a.ld;
-  if (w.acc) {
-    const size_t ox = (size_t)w.c * a.ld;
-    if (mp.h0) {
-      *reinterpret_cast<double2*>(a.X + ox + mp.o0) = w.x0;
-      store_peers2(a, ox + mp.o0, w.x0.x, w.x0.y);
-    }
-    if (mp.h1) {
-      *reinterpret_cast<double2*>(a.X + ox + mp.o1) = w.x1;
-      store_peers2(a, ox + mp.o1, w.x1.x, w.x1.y);
-    }
-  }
-  if (a.mean) {
-    welford_update(w.x0.x, a.inv_n1, w.m0.x, w.v0.x);
-    welford_update(w.x0.y, a.inv_n1, w.m0.y, w.v0.y);
-    welford_update(w.x1.x, a.inv_n1, w.m1.x, w.v1.x);
-    welford_update(w.x1.y, a.inv_n1, w.m1.y, w.v1.y);
-    if (mp.h0) { st_stream2(a.mean + o + mp.o0, w.m0.x, w.m0.y); st_stream2(a.m2 + o + mp.o0, w.v0.x, w.v0.y); }
-    if (mp.h1) { st_stream2(a.mean + o + mp.o1, w.m1.x, w.m1.y); st_stream2(a.m2 + o + mp.o1, w.v1.x, w.v1.y); }
-  }
-  if (a.hist_row) {
-    if (mp.h0) st_stream2(a.hist_row + o + mp.o0, w.x0.x, w.x0.y);
-    if (mp.h1) st_stream2(a.hist_row + o + mp.o1, w.x1.x, w.x1.y);
-  }
-}
-// write-back of the warp's rows of one tile (d % 4 == 0), two rows' loads in flight at a time
-__device__ __forceinline__ void warp_stage_writeback(const PhaseArgs& a, const TileScratch& T,
-                                                     const double* __restrict__ P, int pld, int pw, int lane) {
-  const WbMap mp = wb_map(a.d, lane);
-  if (!mp.h0) return;
-  const bool keep = a.mean != nullptr || a.hist_row != nullptr;
-#pragma unroll 1
-  for (int row = pw; row < kTileRows; row += 2 * kV3ProdWarps) {
-    WbRow w0, w1;
-    wb_issue(a, T, P, pld, row, mp, keep, w0);
-    wb_issue(a, T, P, pld, row + kV3ProdWarps, mp, keep, w1);
-    wb_finish(a, mp, w0);
-    wb_finish(a, mp, w1);
+  if (mp.h1) {
+    const double2 x = *reinterpret_cast<const double2*>(prow + mp.o1);
+    *reinterpret_cast<double2*>(a.X + ox + mp.o1) = x;
+    store_peers2(a, ox + mp.o1, x.x, x.y);
   }
 }
 
@@ -1217,6 +1197,7 @@ fused_gauss_v3_kernel(const PhaseArgs a, const GaussArgs g) {
     load_W_fragments(tb.Ws, tb.mus, g.W, g.mu, d, g.r, threadIdx.x, kV3ConsThreads);
     nbar_sync(BAR_CONS, kV3ConsThreads);
     unsigned n_acc = 0, n_rej = 0;
+    const WbMap mp = wb_map(d, lane);
     for (int i = 0; i < n_my; ++i) {
       const int b = i & 1;
       const double* P = Pbuf + b * p_stride;
@@ -1224,7 +1205,14 @@ fused_gauss_v3_kernel(const PhaseArgs a, const GaussArgs g) {
       mbar_wait(FULL + b, (i >> 1) & 1);
       const double maha = gauss_tile_maha_dmma8<CENTER>(P, pld, tb.Ws, tb.mus, d, NT, warp, lane);
       const bool decider = (lane & 3) == 0;
-      tile_stage_decide_reg(a, g, T, maha, decider ? 8 * warp + (lane >> 2) : -1, n_acc, n_rej);
+      const int acc = tile_stage_decide_reg(a, g, T, maha, decider ? 8 * warp + (lane >> 2) : -1, n_acc, n_rej);
+      unsigned am = __ballot_sync(0xFFFFFFFFu, decider && acc);
+      while (am) {                                   // ~1 accepted row per 8-row m-tile
+        const int row = 8 * warp + ((__ffs(am) - 1) >> 2);
+        am &= am - 1;
+        cons_store_row(a, P + row * pld, T.cid[row], mp);
+      }
+      __syncwarp();                                  // the tile reads above precede the buffer's release
       if (decider) mbar_arrive(DONE + b);
     }
     if (lane == 0) {
@@ -1233,34 +1221,25 @@ fused_gauss_v3_kernel(const PhaseArgs a, const GaussArgs g) {
     }
   } else {
     // ------------------------------ producers ------------------------------------------
-    // each warp is an independent pipeline over ITS rows: draws of tile i+1 | proposal of tile i |
-    // write-back of tile i-1; it synchronises only with the consumers
+    // each warp is an independent pipeline over ITS rows: draws of tile i+1 | proposal of tile i; it
+    // synchronises only with the consumers (FULL: tile handed over; DONE: tile buffer and scratch slot of
+    // tile i-2 are free again -- the consumers decided it and stored its accepted rows)
     asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     const int pw = warp - kV3ConsWarps;
     if (n_my > 0)
       warp_stage_draws<REPLAY>(a, L, tb, *reinterpret_cast<TileScratch*>(Tbuf), g_lo, g_hi, pw, lane);
-    for (int i = 0; i <= n_my; ++i) {
-      if (i < n_my) {
-        const int b = i & 1;
-        if (i + 1 < n_my)
-          warp_stage_draws<REPLAY>(a, L, tb, *reinterpret_cast<TileScratch*>(Tbuf + ((i + 1) % 3) * t_stride),
-                                   g_lo + (i + 1) * kTileRows, g_hi, pw, lane);
-        double* P = Pbuf + b * p_stride;
-        TileScratch& T = *reinterpret_cast<TileScratch*>(Tbuf + (i % 3) * t_stride);
-        tile_stage_propose_v3<REPLAY, NPAIR>(a, tb, T, P, pld, pw, kV3ProdWarps, lane);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(FULL + b);
-      }
-      if (i >= 1) {
-        const int b2 = (i - 1) & 1;
-        const double* P = Pbuf + b2 * p_stride;
-        const TileScratch& T = *reinterpret_cast<const TileScratch*>(Tbuf + ((i - 1) % 3) * t_stride);
-        mbar_wait(DONE + b2, ((i - 1) >> 1) & 1);
-        warp_stage_writeback(a, T, P, pld, pw, lane);
-        // the write-back reads the tile in its own lane map: order those reads before the lanes that
-        // overwrite the same rows in the proposal stage of tile i+1
-        __syncwarp();
-      }
+    for (int i = 0; i < n_my; ++i) {
+      const int b = i & 1;
+      // scratch slot (i + 1) % 3 was tile i-2's
+      if (i >= 2) mbar_wait(DONE + b, ((i - 2) >> 1) & 1);
+      if (i + 1 < n_my)
+        warp_stage_draws<REPLAY>(a, L, tb, *reinterpret_cast<TileScratch*>(Tbuf + ((i + 1) % 3) * t_stride),
+                                 g_lo + (i + 1) * kTileRows, g_hi, pw, lane);
+      double* P = Pbuf + b * p_stride;
+      TileScratch& T = *reinterpret_cast<TileScratch*>(Tbuf + (i % 3) * t_stride);
+      tile_stage_propose_v3<REPLAY, NPAIR>(a, tb, T, P, pld, pw, kV3ProdWarps, lane);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(FULL + b);
     }
   }
 }
@@ -1347,6 +1326,10 @@ __global__ void __launch_bounds__(128) fused_small_kernel(const PhaseArgs a, con
       a.cr_pick[c] = a.adapt ? D.cr_idx : -1;
       a.cr_delta[c] = delta;
     }
+    if (REPLAY && a.tr.prop)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < d) a.tr.prop[(size_t)c * d + q] = pr[q];
     double lp;
     if (TARGET == BPM_TARGET_BANANA) lp = banana_lnl(tv.banana, pr[0], pr[1]);
     else if (TARGET == BPM_TARGET_BIMODAL) lp = bimodal_lnl(tv.bimodal, pr[0], pr[1]);
@@ -1384,6 +1367,19 @@ __global__ void __launch_bounds__(128) fused_small_kernel(const PhaseArgs a, con
     if (am) atomicAdd(a.n_acc, (unsigned long long)__popc(am));
     if (rm) atomicAdd(a.n_rej, (unsigned long long)__popc(rm));
   }
+}
+
+// Will try_fused_phase run the lazy-protocol kernel (fused_gauss_v3_kernel) for this configuration?
+// The engine asks BEFORE building the phase arguments, because that kernel leaves the generation's new
+// history row / moment sample pending (PhaseArgs::lazy) and the others do not.
+inline bool fused_plan_is_v3(int target, int d, int ld, int r, int variant) {
+  if (!(target == BPM_TARGET_GAUSS && gauss_rows_supported(d, r) && (ld % 2) == 0)) return false;
+  const bool v3_ok = (d % 4) == 0 && ld == d && fused_v3_smem(d) <= kMaxDynSmem;
+  const bool v12_ok = fused_gauss_smem(d) <= kMaxDynSmem;
+  if (!v3_ok) return false;
+  if (variant == 2 && v12_ok) return false;
+  if (variant == 3 && v12_ok) return false;
+  return true;
 }
 
 template <bool REPLAY>
@@ -1430,6 +1426,7 @@ inline int try_fused_phase(const TargetView& tv, const PhaseArgs& a, cudaStream_
         fused_gauss_ws_kernel<REPLAY, true><<<grid, kWsThreads, sm, s>>>(a, g);
       }
     } else {
+      if (!a.lazy) return 1;       // the engine must have planned the lazy protocol (fused_plan_is_v3)
       const int grid = n_tiles > 148 ? 148 : (n_tiles < 1 ? 1 : n_tiles);
       const bool d3 = a.algo == BPM_ALGO_DREAM && a.del_pairs == 3;
       const size_t sm = fused_v3_smem(a.d);

@@ -575,6 +575,26 @@ __global__ void __launch_bounds__(256) scatter_changed_rows_kernel(const double*
   }
 }
 
+// ---- lazy protocol: materialise the pending row (bpm_flush) ---------------------------
+// history row hist_len - 1 <- X, and the same row folded into the running moments with the kernels'
+// own Welford arithmetic (inv_n = 1 / mom_len: the row is already counted).
+__global__ void flush_pending_kernel(const double* __restrict__ X, double* __restrict__ mean,
+                                     double* __restrict__ m2, double* __restrict__ hist_cur, int lo, int hi,
+                                     int d, int ld, double inv_n) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)(hi - lo) * ld) return;
+  const int co = (int)(idx / ld), i = (int)(idx % ld);
+  if (i >= d) return;
+  const double s = X[(size_t)(lo + co) * ld + i];
+  if (mean) {
+    double mu = mean[idx], v = m2[idx];
+    welford_update(s, inv_n, mu, v);
+    mean[idx] = mu;
+    m2[idx] = v;
+  }
+  if (hist_cur) hist_cur[idx] = s;
+}
+
 // ---- moments rebuilt from a stored history (load_state / warm start) -------------
 __global__ void moments_from_history_kernel(const double* __restrict__ hist, int64_t T, int N, int d,
                                             int ld, int lo, int hi, double* __restrict__ mean,

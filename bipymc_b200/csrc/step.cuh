@@ -17,7 +17,13 @@ struct PhaseArgs {
   double* lnl;
   double* mean;
   double* m2;
-  double* hist_row;  // destination row block [n_local][ld] for this generation, or nullptr
+  double* hist_row;  // destination row block [n_local][ld] for this generation, or nullptr (eager kernels)
+  // lazy protocol (fused_gauss_v3_kernel): the kernel does NOT append the new state to the history /
+  // running moments; it leaves that row pending and folds the row the PREVIOUS generation left pending
+  // -- each chain's current state, which its proposal stage holds in registers anyway -- instead.
+  double* hist_cur;  // history row hist_len - 1 (the pending one) [n_local][ld], or nullptr
+  int32_t lazy;      // this launch follows the lazy protocol
+  int32_t pending;   // the current row of every chain is not yet in mean / m2 / history: fold it now
   const double* hist_base;  // row 0 of the stored history (replay mode: exact np.std), or nullptr
   // phase lists: perm[0:nA) is half "a", perm[nA:N) half "b" before the flip swap
   const int32_t* perm;

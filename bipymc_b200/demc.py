@@ -139,6 +139,20 @@ class HistoryStore(object):
         self.stored = 0
         self.length = 0
         self._current = None  # [n_local, ld] view of the live population rows
+        # the fused kernels leave the newest row pending (bpm_state.pending); the owner sets this to a
+        # callable that materialises it, run before anything reads the stored rows
+        self._before_read = None
+
+    def will_grow(self):
+        """The next reserve() allocates a new chunk."""
+        return self.policy == "full" and (not self.chunks or self._used_in_last() == self.chunks[-1].shape[0])
+
+    def flat_base(self):
+        """Address row 0 of one flat [T][n_local][ld] array would have so that the rows of the LAST chunk
+        sit where they are (what reserve() returned for that chunk); None when nothing is kept."""
+        if self.policy != "full" or not self.chunks:
+            return None
+        return self.chunks[-1].data_ptr() - (self.length - self._used_in_last()) * self.row_bytes
 
     def _used_in_last(self):
         return self.stored - sum(c.shape[0] for c in self.chunks[:-1]) if self.chunks else 0
@@ -186,6 +200,8 @@ class HistoryStore(object):
     def tensor(self):
         """[stored, n_local, ld] (concatenates chunks when there are several)."""
         torch = self._torch
+        if self._before_read is not None:
+            self._before_read()
         parts, left = [], self.stored
         for c in self.chunks:
             take = min(left, c.shape[0])
@@ -530,11 +546,13 @@ class DeMcMpi(object):
             torch.cuda.synchronize(self._device)
             dist.barrier()          # nobody steps before every replica holds the initial states
         self._lnl = torch.zeros((N,), dtype=torch.float64, device=self._device)
-        self._mean = self._X[lo:hi].clone()
-        self._m2 = torch.zeros((nl, ld), dtype=torch.float64, device=self._device)
+        self._pending = 0
+        self._mean_t = self._X[lo:hi].clone()
+        self._m2_t = torch.zeros((nl, ld), dtype=torch.float64, device=self._device)
         self._hist = HistoryStore(nl, d, ld, self._device, policy=self._history_policy,
                                   chunk_bytes=self._chunk_bytes, reserve_rows=self._reserve_rows)
         self._hist._current = self._X[lo:hi]
+        self._hist._before_read = self._flush
         if history is None:
             self._hist.set_initial(self._X[lo:hi])
         else:
@@ -564,19 +582,41 @@ class DeMcMpi(object):
         st = _lib.State()
         st.X = self._X.data_ptr()
         st.lnl = self._lnl.data_ptr()
-        st.mean = self._mean.data_ptr()
-        st.m2 = self._m2.data_ptr()
+        st.mean = self._mean_t.data_ptr()
+        st.m2 = self._m2_t.data_ptr()
         st.history = hist_base
         st.hist_len = self._hist.length
         st.mom_len = self._mom_len
+        st.pending = self._pending
         return st
+
+    # The fused 100-D kernel leaves every chain's newest row pending (include/bipymc_b200.h,
+    # bpm_state.pending): counted by the lengths, not yet written to the history / folded into the running
+    # moments -- the next generation does that from registers.  Anything that READS the history or the
+    # moments goes through _flush() first (HistoryStore.tensor(), the _mean / _m2 properties).
+    def _flush(self):
+        if not getattr(self, "_pending", 0):
+            return
+        st = self._state(self._hist.flat_base())
+        _lib.check(self._libh.bpm_flush(self._handle, C.byref(st), self._stream()))
+        self._pending = int(st.pending)
+
+    @property
+    def _mean(self):
+        self._flush()
+        return self._mean_t
+
+    @property
+    def _m2(self):
+        self._flush()
+        return self._m2_t
 
     def _rebuild_moments(self):
         """Running mean / M2 of every local chain from the stored history."""
         torch = _torch()
         h = self._hist.tensor()
-        self._mean = torch.zeros_like(h[0])
-        self._m2 = torch.zeros_like(h[0])
+        self._mean_t = torch.zeros_like(h[0])
+        self._m2_t = torch.zeros_like(h[0])
         self._mom_len = self._hist.length
         st = self._state(h.data_ptr())
         _lib.check(self._libh.bpm_moments_from_history(self._handle, C.byref(st), self._stream()))
@@ -588,8 +628,9 @@ class DeMcMpi(object):
         reference has no counterpart; note DREAM's CR adaptation then sees the standard
         deviation of the post-reset history only."""
         lo, hi = self._local_range()
-        self._mean.copy_(self._X[lo:hi])
-        self._m2.zero_()
+        self._flush()
+        self._mean_t.copy_(self._X[lo:hi])
+        self._m2_t.zero_()
         self._mom_len = 1
 
     def _gathered_moments(self):
@@ -616,6 +657,7 @@ class DeMcMpi(object):
             raise RuntimeError("rhat() needs at least two rows in the running moments")
         if self.comm.size == 1:
             out = np.zeros(self.dim)
+            self._flush()
             st = self._state(None)
             _lib.check(self._libh.bpm_rhat(self._handle, C.byref(st), -1, out.ctypes.data, self._stream()))
             return out
@@ -647,6 +689,7 @@ class DeMcMpi(object):
             raise RuntimeError("outlier_reset(): no generations tracked yet")
         n_reset = C.c_int32()
         stats = (C.c_double * 4)()
+        self._flush()          # a reset overwrites X: the pending row is the pre-reset state
         st = self._state(None)
         if not self._sharded:
             _lib.check(self._libh.bpm_outlier_reset(self._handle, C.byref(st), None, None,
@@ -760,6 +803,8 @@ class DeMcMpi(object):
         _lib.check(self._libh.bpm_omega_track(self._handle, 1 if track_outliers else 0))
         mode = self._mode()
         while k_gen < G:
+            if self._pending and self._hist.will_grow():
+                self._flush()      # the pending row belongs to the chunk that is full now
             base, avail = self._hist.reserve(G - k_gen)
             avail = min(avail, G - k_gen)
             if self.checkpoint > 0:
@@ -779,6 +824,7 @@ class DeMcMpi(object):
             else:
                 self._split_generation(st, k_gen + k_off)
                 done = 1
+            self._pending = int(st.pending)
             self._hist.advance(done)
             self._mom_len += done
             k_gen += done
@@ -867,6 +913,7 @@ class DeMcMpi(object):
         torch = _torch()
         import torch.distributed as dist
         G, nl = self.comm.size, len(self.rank_chain_ids)
+        self._flush()          # moments travel with the chains: fold the pending sample first
         cuts = [b1 - b0 for b0, b1 in shard_bounds(nl, G)]
         if len(set(len(np.array_split(np.arange(self.n_chains), G)[r]) for r in range(G))) != 1:
             raise RuntimeError("subpop_k needs n_chains divisible by the number of ranks")

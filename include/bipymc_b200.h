@@ -85,6 +85,13 @@ typedef struct bpm_state {
   int64_t mom_len;  /* rows the running moments (mean, m2) currently cover; equals hist_len
                        for the reference's np.std-over-the-whole-history semantics, smaller
                        after a diagnostics reset.  0 is read as hist_len.              */
+  int64_t pending;  /* set by the step entry points.  1 = the LAST of those rows -- every chain's
+                       current state X[c], i.e. McmcChain.chain[-1] (chain.py:51-54) -- is counted
+                       by hist_len / mom_len but not yet materialised: history row hist_len - 1 is
+                       unwritten and mean / m2 lack that sample.  The fused 100-D kernel leaves the
+                       row pending because the next generation's proposal stage holds it in registers
+                       anyway (no second pass over the moments).  Pass the value back unchanged on the
+                       next call; call bpm_flush before reading history / mean / m2.  0 on a new state. */
 } bpm_state;
 
 /* RNG-replay buffers for ONE generation: the reference's numpy draws, indexed by
@@ -221,6 +228,13 @@ int bpm_generations_host(bpm_handle h, double* X_host, double* lnl_host, int64_t
  * the rows of chains that moved (the device stores them straight into the host arrays; rows of
  * chains that did not move are already correct there).  Bytes the last call moved device->host. */
 int bpm_last_d2h_bytes(bpm_handle h, uint64_t* bytes);
+
+/* Materialise a pending row (bpm_state.pending): writes history row hist_len - 1 from X and folds it
+ * into mean / m2 with the kernels' own Welford arithmetic, then clears st->pending.  No-op when nothing
+ * is pending.  st->history must be the base the step call that left the row pending was given.
+ * Every entry point that needs the row (replay steps, the eager kernels, diagnostics) calls it itself;
+ * the host calls it before READING history / mean / m2 (McmcChain.chain, param_est, save_state). */
+int bpm_flush(bpm_handle h, bpm_state* st, bpm_stream stream);
 
 /* Rebuild running moments from a stored history (load_state / warm start). */
 int bpm_moments_from_history(bpm_handle h, bpm_state* st, bpm_stream stream);

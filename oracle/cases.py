@@ -54,6 +54,14 @@ EXTRA_CASES = {
                                  ctor_kwargs=dict(varepsilon=1.0),
                                  run_kwargs=dict(gamma=0.3, epsilon=1e-8, flip=0.7)),
 }
+# Third batch: a 100-D DREAM population that spans MORE THAN ONE 64-chain tile of the fused kernel
+# (136 chains: 68 per half-phase = one full tile + a 4-row partial tile), dispersed start, adaptation
+# switching on (len(chain) > 2) and off (k >= 5) inside the fixture.
+TILE_CASES = {
+    "gauss100_dream_tiles": _case("dream", "gauss100", np.zeros(100), 136, 7, seed=54,
+                                  ctor_kwargs=dict(n_cr_gen=2, burnin_gen=5, varepsilon=0.25)),
+}
+EXTRA_CASES.update(TILE_CASES)
 ALL_CASES = dict(CASES, **EXTRA_CASES)
 
 

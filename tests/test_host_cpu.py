@@ -36,7 +36,7 @@ def test_library_exports_every_header_symbol():
 def test_struct_layouts_match_header():
     # sizes the C compiler would produce for the header's structs (LP64)
     assert C.sizeof(_lib.Config) == 12 * 4 + 5 * 8 + 8
-    assert C.sizeof(_lib.State) == 7 * 8
+    assert C.sizeof(_lib.State) == 8 * 8
     assert C.sizeof(_lib.Replay) == 8 + 9 * 8
     assert C.sizeof(_lib.TraceOut) == 3 * 8
 

@@ -109,14 +109,40 @@ def check_against_reference(name, s, sink, traces, osampler):
     assert np.array_equal(c.current_pos, hist[-1, 1, :]) and c.chain_len == ref.shape[0]
 
 
+def launches_by_kind(s):
+    """Launch counts the engine recorded since bpm_profile(h, 1): split, propose, likelihood, accept,
+    fused half-phase, CR reduction (include/bipymc_b200.h: bpm_profile_read)."""
+    import ctypes as C
+    from bipymc_b200 import _lib
+    ms, n = (C.c_double * 8)(), (C.c_int64 * 8)()
+    _lib.check(s._libh.bpm_profile_read(s._handle, ms, n))
+    return dict(zip(("split", "propose", "likelihood", "accept", "fused_phase", "cr_reduce"), [int(v) for v in n]))
+
+
+def replay_and_check(name, fused):
+    """Replay the reference's recorded draws through the device step with the full trace sink (accept
+    flags, proposal likelihoods AND proposal vectors) and prove WHICH kernels ran: the fused ids must have
+    launched one fused half-phase kernel per phase and no split-path kernel, the split id the opposite."""
+    from bipymc_b200 import _lib
+    osampler, traces = oracle_traces(name)
+    s = make_sampler(name, "device", fused=fused)
+    _lib.check(s._libh.bpm_profile(s._handle, 1))
+    sink = []
+    s.run_mcmc(ALL_CASES[name]["n"], _replay=traces, _trace=sink, **ALL_CASES[name]["run_kwargs"])
+    k = launches_by_kind(s)
+    _lib.check(s._libh.bpm_profile(s._handle, 0))
+    gens = len(traces)
+    if fused:
+        assert k["fused_phase"] == 2 * gens and k["propose"] == 0 and k["accept"] == 0, k
+    else:
+        assert k["fused_phase"] == 0 and k["propose"] == 2 * gens and k["accept"] == 2 * gens, k
+    check_against_reference(name, s, sink, traces, osampler)
+
+
 @pytest.mark.parametrize("fused", [1, 0, 2, 3], ids=["fused", "split", "fused-halves", "fused-ws12"])
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_replay_device_target(name, fused):
-    osampler, traces = oracle_traces(name)
-    s = make_sampler(name, "device", fused=fused)
-    sink = []
-    s.run_mcmc(ALL_CASES[name]["n"], _replay=traces, _trace=sink, **ALL_CASES[name]["run_kwargs"])
-    check_against_reference(name, s, sink, traces, osampler)
+    replay_and_check(name, fused)
 
 
 @pytest.mark.parametrize("mode", ["scalar", "batched"])

@@ -47,13 +47,10 @@ def test_native_dream_gauss_with_nonzero_mean(dim):
 
 
 # ---- RNG-replay parity against the second batch of golden vectors (oracle/cases.py: EXTRA_CASES) --------
-@pytest.mark.parametrize("fused", [1, 0], ids=["fused", "split"])
+@pytest.mark.parametrize("fused", [1, 0, 2, 3], ids=["fused", "split", "fused-halves", "fused-ws12"])
 @pytest.mark.parametrize("name", sorted(__import__("oracle.cases", fromlist=["EXTRA_CASES"]).EXTRA_CASES))
 def test_replay_extra_golden_cases(name, fused):
-    from oracle.cases import ALL_CASES
-    from test_replay_parity_gpu import check_against_reference, make_sampler, oracle_traces
-    osampler, traces = oracle_traces(name)
-    s = make_sampler(name, "device", fused=fused)
-    sink = []
-    s.run_mcmc(ALL_CASES[name]["n"], _replay=traces, _trace=sink, **ALL_CASES[name]["run_kwargs"])
-    check_against_reference(name, s, sink, traces, osampler)
+    """Includes gauss100_dream_tiles: 136 chains at d = 100, i.e. one full 64-chain tile plus a partial tile per
+    half-phase of the fused kernel (the other 100-D goldens hold 8-12 chains)."""
+    from test_replay_parity_gpu import replay_and_check
+    replay_and_check(name, fused)
