@@ -14,6 +14,7 @@
 #include "kernels_fused.cuh"
 #include "diagnostics.cuh"
 #include "gauss_dmma.cuh"
+#include "sync.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
 namespace {
@@ -105,6 +106,11 @@ struct bpm_engine {
   int fused_ok = 1;  // allow the fused fast paths
   double* peers[BPM_MAX_PEERS] = {nullptr};   // other ranks' X replicas mapped here (bpm_set_peers)
   int n_peers = 0;
+  // peer-memory barrier / CR exchange (sync.cuh, bpm_set_sync): replaces the per-generation NCCL collectives
+  bpm::SyncArgs sync;
+  bool sync_on = false;
+  unsigned long long sync_epoch = 0, sync_cr_seq = 0;
+  int32_t* sync_err = nullptr;
   // diagnostics (diagnostics.cuh): Omega tracking, IQR reset, R-hat scratch
   double* omega_sum = nullptr;   // [N] sum of lnL per chain since tracking started
   double* omega_buf = nullptr;   // [2][N] Omega means / sorted copy
@@ -144,7 +150,7 @@ struct bpm_engine {
     cudaFree(counters); cudaFree(nan_flag); cudaFree(tparams); cudaFree(hX); cudaFree(hL);
     cudaFree(h_accept); cudaFree(h_changed); cudaFree(h_nrows);
     cudaFree(omega_sum); cudaFree(omega_buf); cudaFree(diag_out); cudaFree(diag_i); cudaFree(sort_tmp);
-    cudaFree(rh_mean); cudaFree(rh_m2); cudaFree(rh_out);
+    cudaFree(rh_mean); cudaFree(rh_m2); cudaFree(rh_out); cudaFree(sync_err);
     for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ev_pool) cudaEventDestroy(e);
   }
@@ -387,6 +393,24 @@ struct bpm_engine {
     return 0;
   }
 
+  // cross-rank barrier between half-phases (demc.py:93,116,135) over peer memory
+  int peer_barrier(cudaStream_t s) {
+    prof_begin(6, s);
+    bpm::peer_barrier_kernel<<<1, 32, 0, s>>>(sync, ++sync_epoch);
+    CU_TRY(cudaGetLastError());
+    prof_end(s);
+    return 0;
+  }
+  // ... and the one that closes a DREAM generation, carrying the CR all-reduce
+  int peer_cr_exchange(cudaStream_t s) {
+    prof_begin(6, s);
+    bpm::peer_cr_exchange_kernel<<<1, 64, 0, s>>>(sync, ++sync_epoch, (int)(sync_cr_seq++ & 1ull), cr_part, cfg.n_cr,
+                                                  cr_dm, cr_cnt, p_cr);
+    CU_TRY(cudaGetLastError());
+    prof_end(s);
+    return 0;
+  }
+
   template <bool REPLAY>
   int phase(const bpm_state* st, int64_t k_gen, int ph, const bpm_replay* rp, const bpm_trace_out* tr,
             cudaStream_t s, bool lazy) {
@@ -450,8 +474,15 @@ struct bpm_engine {
     if (st->pending && (!lazy || REPLAY)) BPM_TRY(flush(st, s));
     BPM_TRY(begin(st, rp, s));
     BPM_TRY(phase<REPLAY>(st, k_gen, 0, rp, tr, s, lazy));
-    if (!serial()) BPM_TRY(phase<REPLAY>(st, k_gen, 1, rp, tr, s, lazy));
+    if (!serial()) {
+      if (sync_on) BPM_TRY(peer_barrier(s));          // every rank's phase-a rows are in every replica
+      BPM_TRY(phase<REPLAY>(st, k_gen, 1, rp, tr, s, lazy));
+    }
     BPM_TRY(end(s));
+    if (sync_on) {
+      if (cfg.algo == BPM_ALGO_DREAM) BPM_TRY(peer_cr_exchange(s));
+      else BPM_TRY(peer_barrier(s));
+    }
     BPM_TRY(track_omega(st, s));
     st->hist_len += 1;
     if (st->mom_len > 0) st->mom_len += 1;
@@ -654,6 +685,12 @@ int bpm_step_generations(bpm_handle h, bpm_state* st, int64_t k_gen0, int32_t n_
   if (!st->X || !st->lnl) return fail("state needs X and lnl");
   if (h->target == BPM_TARGET_EXTERNAL && !h->user_fn)
     return fail("bpm_step_generations needs a built-in target or a batched callback");
+  if (h->sharded() && !h->sync_on)
+    return fail("bpm_step_generations on a sharded handle needs bpm_set_sync (peer-memory barrier); without it "
+                "the host drives the half-phases: bpm_begin_generation / bpm_phase / exchange / bpm_end_generation");
+  if (h->sharded() && h->serial())
+    return fail("serial DE-MC steps every chain against the frozen population: sharded handles must use the "
+                "split API with an all-gather after the sweep");
   CU_TRY(cudaSetDevice(h->cfg.device));
   for (int g = 0; g < n_gen; ++g)
     BPM_TRY(h->generation<false>(st, k_gen0 + g, nullptr, nullptr, (cudaStream_t)stream));
@@ -912,6 +949,46 @@ int bpm_set_peers(bpm_handle h, double* const* peer_X, int32_t n_peers) {
     h->peers[p] = peer_X[p];
   }
   h->n_peers = n_peers;
+  return 0;
+}
+
+int bpm_sync_bytes(uint64_t* bytes) {
+  if (!bytes) return fail("null argument");
+  *bytes = (uint64_t)bpm::kSyncBytes;
+  return 0;
+}
+
+int bpm_set_sync(bpm_handle h, void* const* blocks, int32_t rank, int32_t world) {
+  if (!h) return fail("null handle");
+  if (world == 0) { h->sync_on = false; return 0; }
+  if (!blocks || world < 2 || world > bpm::kSyncRanks || rank < 0 || rank >= world) return fail("bad sync arguments");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  for (int r = 0; r < world; ++r) {
+    if (!blocks[r]) return fail("null sync block");
+    h->sync.blocks[r] = (unsigned char*)blocks[r];
+  }
+  if (!h->sync_err) {
+    CU_TRY(cudaMalloc(&h->sync_err, sizeof(int32_t)));
+    CU_TRY(cudaMemset(h->sync_err, 0, sizeof(int32_t)));
+  }
+  h->sync.rank = rank; h->sync.world = world; h->sync.err = h->sync_err;
+  h->sync_epoch = 0; h->sync_cr_seq = 0;
+  h->sync_on = true;
+  return 0;
+}
+
+int bpm_peer_barrier(bpm_handle h, bpm_stream stream) {
+  if (!h || !h->sync_on) return fail("bpm_peer_barrier: bpm_set_sync first");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  return h->peer_barrier((cudaStream_t)stream);
+}
+
+int bpm_sync_error(bpm_handle h, int32_t* err) {
+  if (!h || !err) return fail("null argument");
+  *err = 0;
+  if (!h->sync_err) return 0;
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  CU_TRY(cudaMemcpy(err, h->sync_err, sizeof(int32_t), cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -106,6 +106,34 @@ def _default_comm():
     return _SingleComm()
 
 
+def _resolve_comm(mpi_comm):
+    """The communicator the sampler shards over.  Collectives run on torch.distributed (NCCL / gloo);
+    an mpi4py communicator is accepted for signature compatibility (demc.py:15) but it must describe the
+    SAME world: same size and rank as the initialised torch.distributed group, else the ranks would be
+    mis-sharded silently or fail deep inside init_chains."""
+    if mpi_comm is None or not hasattr(mpi_comm, "rank"):
+        return _default_comm()
+    if isinstance(mpi_comm, (_SingleComm, _TorchComm)):
+        return mpi_comm
+    size = int(mpi_comm.Get_size()) if hasattr(mpi_comm, "Get_size") else int(getattr(mpi_comm, "size", 1))
+    rank = int(mpi_comm.Get_rank()) if hasattr(mpi_comm, "Get_rank") else int(mpi_comm.rank)
+    if size == 1:
+        return mpi_comm
+    try:
+        import torch.distributed as dist
+        ok = dist.is_available() and dist.is_initialized()
+    except Exception:
+        ok = False
+    if not ok:
+        raise RuntimeError("mpi_comm has %d ranks but torch.distributed is not initialised: bipymc_b200 runs its "
+                           "collectives on torch.distributed (one process per GPU, e.g. under torchrun); call "
+                           "torch.distributed.init_process_group first" % size)
+    if dist.get_world_size() != size or dist.get_rank() != rank:
+        raise RuntimeError("mpi_comm (rank %d of %d) and the torch.distributed group (rank %d of %d) disagree"
+                           % (rank, size, dist.get_rank(), dist.get_world_size()))
+    return _TorchComm(dist)
+
+
 class GaussianProposalStub(object):
     """The reference instantiates a GaussianProposal in every sampler ctor
     (samplers.py:27) but never calls it on the DE-MC / DREAM path; keep the attribute."""
@@ -278,7 +306,12 @@ class DeMcMpi(object):
         varepsilon = np.asarray(varepsilon)
         assert n_chains >= 4                                   # samplers.py:249
         self.n_chains = n_chains
-        self.comm = mpi_comm if (mpi_comm is not None and hasattr(mpi_comm, "rank")) else _default_comm()
+        self.comm = _resolve_comm(mpi_comm)
+        if n_chains % self.comm.size != 0:
+            # the reference counts j per rank (demc.py:79,103-109): ranks with fewer chains run more
+            # generations and its fixed-count Allgather (demc.py:93) mismatches -- it hangs.  Say so.
+            raise ValueError("n_chains (%d) must be divisible by the number of ranks (%d)"
+                             % (n_chains, self.comm.size))
         self.local_n_accepted = 0
         self.local_n_rejected = 1                               # demc.py:19-20
         if theta_0 is not None:
@@ -319,6 +352,9 @@ class DeMcMpi(object):
         # A different sampler than the reference's single population, hence opt-in and stated.
         self.subpop_k = int(kwargs.get("subpop_k", 0))
         self._peer_ptrs, self._own_X_ptr = [], None
+        self._sync_peer_ptrs, self._own_sync_ptr, self._sync_on = [], None, False
+        # peer_sync=False keeps the round-1 protocol (NCCL all-reduce as the barrier between half-phases)
+        self._peer_sync_wanted = bool(kwargs.get("peer_sync", True))
         self.outlier_gen = int(kwargs.get("outlier_gen", 0))
         self.n_outlier_resets = 0
         self._setup_device()
@@ -442,6 +478,15 @@ class DeMcMpi(object):
         for q in getattr(self, "_peer_ptrs", []):
             lib.bpm_ipc_close(self._device_index, C.c_void_p(q))
         self._peer_ptrs = []
+        if getattr(self, "_handle", None) is not None and getattr(self, "_sync_on", False):
+            lib.bpm_set_sync(self._handle, None, 0, 0)
+        self._sync_on = False
+        for q in getattr(self, "_sync_peer_ptrs", []):
+            lib.bpm_ipc_close(self._device_index, C.c_void_p(q))
+        self._sync_peer_ptrs = []
+        if getattr(self, "_own_sync_ptr", None):
+            lib.bpm_dev_free(self._device_index, C.c_void_p(self._own_sync_ptr))
+            self._own_sync_ptr = None
         if getattr(self, "_own_X_ptr", None):
             self._X = None
             lib.bpm_dev_free(self._device_index, C.c_void_p(self._own_X_ptr))
@@ -490,7 +535,43 @@ class DeMcMpi(object):
         arr = (C.c_void_p * len(self._peer_ptrs))(*self._peer_ptrs)
         _lib.check(lib.bpm_set_peers(self._handle, arr, len(self._peer_ptrs)))
         self._bar = torch.zeros((1,), dtype=torch.float32, device=self._device)
+        self._setup_peer_sync()
         return X
+
+    def _setup_peer_sync(self):
+        """Peer-memory barrier (bpm_set_sync): one small IPC-mapped block per rank; with it a sharded
+        generation is a plain sequence of kernels on one stream -- no NCCL call per half-phase."""
+        torch = _torch()
+        import torch.distributed as dist
+        lib = self._libh
+        nbytes = C.c_uint64()
+        _lib.check(lib.bpm_sync_bytes(C.byref(nbytes)))
+        ptr = C.c_void_p()
+        _lib.check(lib.bpm_dev_alloc(self._device_index, nbytes.value, C.byref(ptr)))
+        self._own_sync_ptr = ptr.value
+        self._wrap_device(ptr.value, (nbytes.value // 8,)).zero_()
+        torch.cuda.synchronize(self._device)
+        hbuf = C.create_string_buffer(64)
+        _lib.check(lib.bpm_ipc_export(self._device_index, ptr, hbuf))
+        handles = [None] * self.comm.size
+        dist.all_gather_object(handles, bytes(hbuf.raw))
+        blocks, ok = [], 1
+        for r, hb in enumerate(handles):
+            if r == self.comm.rank:
+                blocks.append(ptr.value)
+                continue
+            q = C.c_void_p()
+            if lib.bpm_ipc_open(self._device_index, C.create_string_buffer(hb, 64), C.byref(q)) != 0:
+                ok = 0
+                break
+            self._sync_peer_ptrs.append(q.value)
+            blocks.append(q.value)
+        flag = torch.tensor([ok], dtype=torch.int32, device=self._device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # also: every block is zeroed before anyone signals
+        self._sync_on = bool(int(flag.item())) and self._peer_sync_wanted
+        if self._sync_on:
+            arr = (C.c_void_p * len(blocks))(*blocks)
+            _lib.check(lib.bpm_set_sync(self._handle, arr, self.comm.rank, self.comm.size))
 
     def _phase_exchange(self, last):
         """Make this half-phase's updates visible on every rank before the next one reads them.
@@ -500,6 +581,9 @@ class DeMcMpi(object):
             return
         if self._exchange == "p2p":
             if last and self._algo == _lib.BPM_ALGO_DREAM:
+                return
+            if self._sync_on:
+                _lib.check(self._libh.bpm_peer_barrier(self._handle, self._stream()))
                 return
             import torch.distributed as dist
             dist.all_reduce(self._bar)
@@ -815,7 +899,8 @@ class DeMcMpi(object):
             if replay is not None:
                 self._replay_generation(st, replay[k_gen], k_gen + k_off, trace)
                 done = 1
-            elif mode == "device" and not self._sharded:
+            elif mode == "device" and (not self._sharded or (self._sync_on and self._n_phases == 2)):
+                # whole generations inside the library; sharded: barriers / CR exchange over peer memory
                 done = avail
                 if self._subpop:
                     done = min(done, self.subpop_k - (self._gens_since_deal % self.subpop_k))
@@ -837,6 +922,11 @@ class DeMcMpi(object):
             if self.checkpoint > 0 and k_gen % self.checkpoint == 0:        # demc.py:138-140
                 self.save_state(self.h5_file)
         torch.cuda.synchronize(self._device)
+        if self._sync_on:
+            err = C.c_int32()
+            _lib.check(self._libh.bpm_sync_error(self._handle, C.byref(err)))
+            if err.value:
+                raise RuntimeError("peer barrier timed out: a rank did not arrive (bpm_sync_error)")
         self._collect_counters()
         self.comm.Barrier()
 

@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .demc import DeMcMpi, GaussianProposalStub, _SingleComm, _default_comm, _torch
+from .demc import DeMcMpi, GaussianProposalStub, _SingleComm, _default_comm, _resolve_comm, _torch
 from .util import var_ball_batch
 
 
@@ -26,8 +26,9 @@ class DeMc(DeMcMpi):
     def __init__(self, log_like_fn, n_chains=8, ln_kwargs={}, **proposal_kwargs):
         assert n_chains >= 4                                        # samplers.py:249
         self.n_chains = n_chains
-        comm = proposal_kwargs.get("mpi_comm", None)
-        self.comm = comm if (comm is not None and hasattr(comm, "rank")) else _default_comm()
+        self.comm = _resolve_comm(proposal_kwargs.get("mpi_comm", None))
+        if n_chains % self.comm.size != 0:
+            raise ValueError("n_chains (%d) must be divisible by the number of ranks (%d)" % (n_chains, self.comm.size))
         self.am_chains = []                                         # samplers.py:23
         self.log_like_fn = log_like_fn
         self._ln_kwargs = dict(ln_kwargs)
@@ -45,9 +46,16 @@ class DeMc(DeMcMpi):
         self._fused = False                                         # the sweep uses the split launches
         self._chunk_bytes = int(proposal_kwargs.get("history_chunk_bytes", 1 << 30))
         self._reserve_rows = int(proposal_kwargs.get("history_reserve", 0))
-        self._exchange = proposal_kwargs.get("exchange", "p2p")
+        # A sweep is ONE phase in which every chain reads all other chains of the frozen population, so
+        # accepted rows must not reach another rank's replica while that rank is still proposing: the
+        # in-kernel peer stores of exchange="p2p" would race.  Several ranks therefore always refresh the
+        # replicas with an all-gather AFTER the sweep (a collective nobody completes before everyone has
+        # finished reading), whatever `exchange` asks for.
+        self._exchange = proposal_kwargs.get("exchange", "p2p") if self.comm.size == 1 else "allgather"
         self.subpop_k = 0
         self._peer_ptrs, self._own_X_ptr = [], None
+        self._sync_peer_ptrs, self._own_sync_ptr, self._sync_on = [], None, False
+        self._peer_sync_wanted = False
         self.outlier_gen, self.n_outlier_resets = 0, 0
         self._setup_device()
 

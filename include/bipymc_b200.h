@@ -219,6 +219,21 @@ int bpm_ipc_open(int32_t device, const unsigned char handle64[64], void** dev_pt
 int bpm_ipc_close(int32_t device, void* dev_ptr);
 int bpm_set_peers(bpm_handle h, double* const* peer_X, int32_t n_peers);
 
+/* Peer-memory barrier: the comm.Barrier() of demc.py:135 and the synchronisation implied by the two
+ * Allgathers (demc.py:93,116) without a collective library on the path.  Every rank allocates one sync
+ * block of bpm_sync_bytes() zeroed bytes with bpm_dev_alloc, exchanges its IPC handle, maps the others
+ * and registers all of them, indexed by rank (blocks[rank] = its own).  With a sync set,
+ * bpm_step_generations works on SHARDED handles: it puts a barrier kernel (a few microseconds on the
+ * same stream) after each half-phase and folds the all-reduce of the 2 n_cr CR statistics into the one
+ * that closes a DREAM generation (sums added in rank order: identical bits on every rank).  All ranks
+ * must make the same sequence of calls.  bpm_peer_barrier: one barrier on `stream` (e.g. after the host
+ * refreshed the replicas by other means).  A peer that does not arrive within ~4 s raises a sticky flag
+ * instead of hanging the device: bpm_sync_error.  world = 0 switches the sync off. */
+int bpm_sync_bytes(uint64_t* bytes);
+int bpm_set_sync(bpm_handle h, void* const* blocks, int32_t rank, int32_t world);
+int bpm_peer_barrier(bpm_handle h, bpm_stream stream);
+int bpm_sync_error(bpm_handle h, int32_t* err);
+
 /* Host-buffer entry (the end-to-end path): X_host / lnl_host are HOST arrays (pinned
  * for full speed); copies them to the device, runs n_gen native generations without
  * history, copies the result back.  Synchronous. */
@@ -266,7 +281,8 @@ int bpm_rhat(bpm_handle h, const bpm_state* st, int64_t t0, double* rhat_host, b
 /* Per-kernel timing for the benchmark's roofline line: while on, every launch is
  * bracketed by CUDA events on the caller's stream.  bpm_profile_read synchronises and
  * returns total milliseconds and launch counts for 8 kinds: 0 split/shuffle, 1 propose,
- * 2 likelihood, 3 accept, 4 fused half-phase, 5 CR reduction; then clears the records. */
+ * 2 likelihood, 3 accept, 4 fused half-phase, 5 CR reduction, 6 peer barrier / CR exchange; then clears
+ * the records. */
 int bpm_profile(bpm_handle h, int32_t on);
 int bpm_profile_read(bpm_handle h, double* ms_by_kind8, int64_t* launches_by_kind8);
 
