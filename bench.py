@@ -33,14 +33,30 @@ METRIC = "DREAM chain-steps/s, 100-D Gaussian"
 UNIT = "chain-steps/s"
 
 
+def csrc_hash():
+    """sha256 (first 16 hex digits) over the CUDA sources the library is built from: ties a committed ncu
+    capture to the kernels that were actually timed."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "bipymc_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic(history, adapt):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the
-    committed ncu --set full capture of this same workload (profiles/r1_traffic.json); None for
-    configurations that were not captured."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
+    ncu --set full capture of this same workload (profiles/traffic.json, written by tools/ncu_summary.py
+    traffic).  The file records the hash of csrc/ it was captured with; any other build gets None -- a stale
+    capture must not pass for a measurement of the kernel that was timed."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(p):
         return None
     j = json.load(open(p))
+    if j.get("csrc_sha16") != csrc_hash():
+        return None
     return j.get("history=%s,adapt=%s" % (history, "on" if adapt else "off"))
 
 
@@ -104,42 +120,93 @@ def cpu_port_spec(n_chains):
                 seed=42, varepsilon=1e-6, ctor_kwargs=dict(n_cr_gen=50, burnin_gen=2000))
 
 
+def cpu_arm(n_chains, procs, gens, gens_warm):
+    """Time the reference's DREAM on `procs` host processes: the UNMODIFIED reference from baseline/_ref
+    (oracle/ref_runner.py: shared-memory stand-in for mpirun) when it travelled with the tree, else the
+    oracle port (oracle/mp_port.py).  Returns (seconds, chain_steps, kind)."""
+    from oracle import ref_runner
+    if ref_runner.reference_dir() is not None:
+        spec = dict(n_chains=n_chains, dim=DIM, algo="dream", seed=42, varepsilon=1e-6,
+                    ctor_kwargs=dict(n_cr_gen=50, burnin_gen=2000))
+        dt, steps = ref_runner.time_reference(spec, procs, gens=gens, gens_warm=gens_warm)
+        return dt, steps, "reference"
+    from oracle.mp_port import time_port
+    dt, steps = time_port(cpu_port_spec(n_chains), procs, gens=gens, gens_warm=gens_warm)
+    return dt, steps, "port"
+
+
 def run_reference(args):
-    """The reference's algorithm on the host cores (oracle/mp_port.py: the oracle port of
-    DreamMpi with the mpi4py collectives replaced by shared memory)."""
+    """The reference's own CPU implementation of the path on the host cores: wgurecky/bipymc DreamMpi,
+    unmodified (baseline/_ref), one rank per core over a shared-memory communicator."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.mp_port import time_port
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
     n_chains = 200 * procs
     # a step = one generation of the sample population; warm-up generations are untimed
-    dt, steps = time_port(cpu_port_spec(n_chains), procs, gens=args.steps, gens_warm=max(args.warmup, 1))
+    dt, steps, kind = cpu_arm(n_chains, procs, gens=args.steps, gens_warm=max(args.warmup, 1))
     v = steps / dt
-    sample = "DREAM 100-D Gaussian, %d chains (200 per process), %d timed generations, %.1f s" % (
-        n_chains, args.steps, dt)
+    what = "unmodified reference DreamMpi (baseline/_ref)" if kind == "reference" else "oracle port of DreamMpi"
+    sample = "%s, %d ranks, 100-D Gaussian, %d chains (200 per rank), %d timed generations, %.1f s" % (
+        what, procs, n_chains, args.steps, dt)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "gpu_launches": 0,
             "config": {"workload": "configs[1]: DREAM, Gauss_100D(rho=0.5), CPU sample of %d chains" % n_chains,
                        "del_pairs": 3, "n_cr": 3, "n_cr_gen": 50, "burnin_gen": 2000},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 def cpu_baseline_leg():
-    from oracle.mp_port import time_port
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
     n_chains = 40 * procs
-    gens = 400            # ~10-20 s of host work: the port's np.std over the growing history is O(T)
-    dt, steps = time_port(cpu_port_spec(n_chains), procs, gens=gens, gens_warm=2)
-    return {"value": steps / dt, "unit": UNIT, "cores": procs, "kind": "port",
-            "sample": "oracle port of DreamMpi (shared-memory ranks), 100-D Gaussian, %d chains, "
-                      "%d generations, %.1f s" % (n_chains, gens, dt)}
+    gens = 400            # ~10-20 s of host work: np.std over the growing history is O(T) per step (dream.py:128)
+    dt, steps, kind = cpu_arm(n_chains, procs, gens=gens, gens_warm=2)
+    what = "unmodified reference DreamMpi (baseline/_ref), shared-memory ranks" if kind == "reference" else \
+        "oracle port of DreamMpi (shared-memory ranks)"
+    out = {"value": steps / dt, "unit": UNIT, "cores": procs, "kind": kind,
+           "sample": "%s, 100-D Gaussian, %d chains, %d generations, %.1f s" % (what, n_chains, gens, dt)}
+    if kind == "reference":
+        # BASELINE.md section 5 item 1: the same reference on ONE core (its bit-reproducible configuration)
+        dt1, steps1, _ = cpu_arm(40, 1, gens=100, gens_warm=2)
+        out["one_core"] = {"value": steps1 / dt1, "unit": UNIT, "cores": 1,
+                           "sample": "40 chains, 100 generations, %.1f s" % dt1}
+    return out
+
+
+def selfcheck_sharded(world, rank, local_rank):
+    """N > 1 only (the driver's scaling run has no other multi-GPU correctness test): a small sharded DREAM
+    run through the same entry points as the timed one must reproduce, bit for bit, rank 0's single-GPU
+    run of the same seed (every draw is a function of (seed, generation, chain), never of the rank;
+    adaptation off so no cross-rank sum rounds differently)."""
+    from bipymc_b200 import DreamMpi, targets
+    from bipymc_b200.demc import _SingleComm
+    N, G = 1024 * world, 4
+    tgt = targets.Gauss_100D(rho=0.5, dim=DIM)
+    np.random.seed(7)
+    s = DreamMpi(tgt.ln_like, np.zeros(DIM), n_chains=N, varepsilon=1.0, seed=11, burnin_gen=0, device=local_rank)
+    s.run_mcmc(N * (G + 1))
+    full = s.super_chain_mpi(0)
+    acc = s.n_accepted
+    out = None
+    if rank == 0:
+        np.random.seed(7)
+        one = DreamMpi(tgt.ln_like, np.zeros(DIM), n_chains=N, varepsilon=1.0, seed=11, burnin_gen=0,
+                       device=local_rank, mpi_comm=_SingleComm())
+        one.run_mcmc(N * (G + 1))
+        ref = one.super_chain
+        same = bool(full.shape == ref.shape and np.array_equal(full, ref) and acc == one.n_accepted)
+        out = {"ok": same, "chains": N, "generations": G, "rows_compared": int(ref.shape[0]),
+               "accepted": int(acc), "exchange": s._exchange,
+               "barrier": "peer-memory flags" if s._sync_on else "nccl all-reduce"}
+        one.close()
+    s.close()
+    return out
 
 
 def run_ours(args):
@@ -282,9 +349,11 @@ def run_ours(args):
         nb = N * s._ld * 8 + N * 8
         e2e = {"value": N * ke / dt, "unit": UNIT, "h2d_bytes_per_step": nb, "d2h_bytes_per_step": d2h / ke,
                "steps": ke, "ms_per_step": 1e3 * dt / ke,
-               "note": "bpm_generations_host: pinned host population -> H2D (all chains) -> one generation -> "
-                       "the device stores the rows of the chains that moved (and their lnL) back into the "
-                       "pinned host arrays, every step; the host arrays hold the full updated population"}
+               "note": "bpm_generations_host: pinned host population -> H2D (all chains) -> one generation "
+                       "(crossover adaptation ON: the entry keeps the chains' running moments on the device "
+                       "between calls; the chain history is the caller's) -> the device stores the rows of the "
+                       "chains that moved (and their lnL) back into the pinned host arrays, every step; the "
+                       "host arrays hold the full updated population"}
 
     if world > 1 and not args.no_e2e and args.subpop_k == 0:
         # sharded end-to-end step: every rank copies ITS shard (states + cached likelihoods) in from
@@ -324,6 +393,49 @@ def run_ours(args):
                "note": "per rank: pinned host shard -> H2D, NCCL all-gather of the replicas, one sharded "
                        "generation, shard -> D2H; bytes are summed over ranks"}
 
+    # ---- second point: the same engine on a population AT STATIONARITY (chains drawn from the target) ---
+    # acceptance-dependent traffic (accepted-row stores, peer stores, changed-rows write-back) is then
+    # quoted at the sampler's real acceptance rate, not that of generations 65-85 of the burn-in
+    stationary = None
+    if not args.no_stationary and args.subpop_k == 0:
+        Ks = max(10, min(K, 50))
+        np.random.seed(43)
+        s2 = DreamMpi(tgt.ln_like, np.zeros(DIM), n_chains=N, varepsilon=0.0, seed=43, n_cr_gen=50,
+                      burnin_gen=args.burnin_gen, device=local_rank, history=args.history,
+                      history_reserve=Ks + 16, fused=args.fused, exchange=args.exchange)
+        lo2, hi2 = s2._local_range()
+        g = torch.Generator(device=dev)
+        g.manual_seed(1234)            # same draw on every rank: the replicas must agree
+        z = torch.randn((N, DIM), generator=g, device=dev, dtype=torch.float64)
+        Lc = torch.linalg.cholesky(torch.from_numpy(tgt.cov).to(dev))
+        s2._X[:, :DIM] = z @ Lc.T
+        s2._mean_t.copy_(s2._X[lo2:hi2]); s2._hist.set_initial(s2._X[lo2:hi2]); s2._lnl_valid = False
+        del z
+        k2 = 0
+
+        def gens2(n):
+            nonlocal k2
+            s2.run_mcmc(N * (n + 1), _k_gen0=k2)
+            k2 += n
+        gens2(W + 2)
+        sync_all()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        gens2(Ks)
+        q1.record()
+        sync_all()
+        ms2 = q0.elapsed_time(q1)
+        if world > 1:
+            t = torch.tensor([ms2], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms2 = float(t.item())
+        stationary = {"value": N * Ks / (ms2 * 1e-3), "unit": UNIT, "steps": Ks, "ms_per_step": ms2 / Ks,
+                      "acceptance_fraction": s2.acceptance_fraction,
+                      "init": "chains drawn from the target N(0, Sigma); %d untimed generations" % (W + 2)}
+        s2.close()
+        del s2
+
+    check = selfcheck_sharded(world, rank, local_rank) if world > 1 else None
     cpu = cpu_baseline_leg() if (rank == 0 and world == 1 and not args.no_cpu) else None
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -352,7 +464,8 @@ def run_ours(args):
                 "proposals_and_lnl_evals_per_s": value,
                 "acceptance_fraction": acc_frac, "gpu_launches": launches,
                 "kernel_ms": dict(zip(kinds, ms_k)), "kernel_launches": dict(zip(kinds, n_k)),
-                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": ck}
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": ck,
+                "stationary": stationary, "selfcheck": check}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -373,6 +486,7 @@ def main():
                     help="sub-population mode: islands re-dealt every K generations (0 = one population, the default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
+    ap.add_argument("--no-stationary", action="store_true", help="skip the second (stationary-population) point")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

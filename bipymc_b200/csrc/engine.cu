@@ -99,6 +99,10 @@ struct bpm_engine {
   // host-entry buffers
   double* hX = nullptr;
   double* hL = nullptr;
+  double* hMean = nullptr;       // host entry: per-chain running moments kept on the device across calls
+  double* hM2 = nullptr;         // (derived state: the reference recomputes np.std(chain.chain), dream.py:128)
+  int64_t h_mom_len = 0;         // rows they cover; 0 = restart at the next call
+  int64_t h_pending = 0;
   int32_t* h_accept = nullptr;   // host entry: accept flags of a generation / rows that moved in this call
   int32_t* h_changed = nullptr;
   unsigned long long* h_nrows = nullptr;
@@ -147,7 +151,7 @@ struct bpm_engine {
     cudaFree(inv); cudaFree(loc_list); cudaFree(loc_cnt); cudaFree(phase_cnt); cudaFree(cmp_blk); cudaFree(cr_ticket);
     cudaFree(perm); cudaFree(flip); cudaFree(prop); cudaFree(lnl_prop); cudaFree(cr_delta);
     cudaFree(cr_pick); cudaFree(p_cr); cudaFree(cr_dm); cudaFree(cr_cnt); cudaFree(cr_part); cudaFree(cr_block);
-    cudaFree(counters); cudaFree(nan_flag); cudaFree(tparams); cudaFree(hX); cudaFree(hL);
+    cudaFree(counters); cudaFree(nan_flag); cudaFree(tparams); cudaFree(hX); cudaFree(hL); cudaFree(hMean); cudaFree(hM2);
     cudaFree(h_accept); cudaFree(h_changed); cudaFree(h_nrows);
     cudaFree(omega_sum); cudaFree(omega_buf); cudaFree(diag_out); cudaFree(diag_i); cudaFree(sort_tmp);
     cudaFree(rh_mean); cudaFree(rh_m2); cudaFree(rh_out); cudaFree(sync_err);
@@ -243,6 +247,23 @@ struct bpm_engine {
     if (rp) a.rp = *rp;
     if (tr) a.tr = *tr;
     return a;
+  }
+
+  // bpm_generations_host: state block over the device copies of the caller's host arrays.  DREAM keeps
+  // the chains' running moments here between calls, so crossover adaptation (dream.py:92,119-140) runs
+  // end to end exactly as in a device-resident run; they restart when the entry is (re)started.
+  int host_entry_state(bpm_state* st, int64_t g_abs0, size_t nx, cudaStream_t s) {
+    memset(st, 0, sizeof(*st));
+    st->X = hX; st->lnl = hL; st->hist_len = g_abs0;
+    if (hMean) {
+      if (h_mom_len == 0) {          // first call: the moments cover the one row the caller handed in
+        CU_TRY(cudaMemcpyAsync(hMean, hX, nx, cudaMemcpyDeviceToDevice, s));
+        CU_TRY(cudaMemsetAsync(hM2, 0, nx, s));
+        h_mom_len = 1; h_pending = 0;
+      }
+      st->mean = hMean; st->m2 = hM2; st->mom_len = h_mom_len; st->pending = h_pending;
+    }
+    return 0;
   }
 
   // Does phase() run the lazy-protocol kernel for this handle?  (kernels_fused.cuh: fused_plan_is_v3)
@@ -827,6 +848,11 @@ int bpm_generations_host(bpm_handle h, double* X_host, double* lnl_host, int64_t
     CU_TRY(cudaMalloc(&h->h_accept, sizeof(int32_t) * N));
     CU_TRY(cudaMalloc(&h->h_changed, sizeof(int32_t) * N));
     CU_TRY(cudaMalloc(&h->h_nrows, sizeof(unsigned long long)));
+    if (h->cfg.algo == BPM_ALGO_DREAM) {
+      CU_TRY(cudaMalloc(&h->hMean, nx));
+      CU_TRY(cudaMalloc(&h->hM2, nx));
+    }
+    h->h_mom_len = 0;
   }
   // pinned (mapped) host buffers can be written by the device directly: only rows that moved go back
   double *X_map = nullptr, *L_map = nullptr;
@@ -855,13 +881,13 @@ int bpm_generations_host(bpm_handle h, double* X_host, double* lnl_host, int64_t
     CU_TRY(cudaMemcpyAsync(h->hX, X_host, nx, cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemcpyAsync(h->hL, lnl_host, nl, cudaMemcpyHostToDevice, s));
     bpm_state st;
-    memset(&st, 0, sizeof(st));
-    st.X = h->hX; st.lnl = h->hL; st.hist_len = g_abs0;
+    BPM_TRY(h->host_entry_state(&st, g_abs0, nx, s));
     h->peers[h->n_peers++] = X_map;
     int rc = 0;
     for (int g = 0; g < n_gen && rc == 0; ++g) rc = h->generation<false>(&st, k_gen0 + g, nullptr, nullptr, s);
     h->peers[--h->n_peers] = nullptr;
     if (rc) return rc;
+    h->h_mom_len = st.mom_len; h->h_pending = st.pending;
     CU_TRY(cudaMemcpyAsync(lnl_host, h->hL, nl, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaMemcpyAsync(&acc1, h->counters, sizeof(acc1), cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
@@ -871,8 +897,7 @@ int bpm_generations_host(bpm_handle h, double* X_host, double* lnl_host, int64_t
   CU_TRY(cudaMemcpyAsync(h->hX, X_host, nx, cudaMemcpyHostToDevice, s));
   CU_TRY(cudaMemcpyAsync(h->hL, lnl_host, nl, cudaMemcpyHostToDevice, s));
   bpm_state st;
-  memset(&st, 0, sizeof(st));
-  st.X = h->hX; st.lnl = h->hL; st.hist_len = g_abs0;
+  BPM_TRY(h->host_entry_state(&st, g_abs0, nx, s));
   bpm_trace_out tr;
   memset(&tr, 0, sizeof(tr));
   tr.accept = h->h_accept;
@@ -884,6 +909,7 @@ int bpm_generations_host(bpm_handle h, double* X_host, double* lnl_host, int64_t
     BPM_TRY(h->generation<false>(&st, k_gen0 + g, nullptr, X_map ? &tr : nullptr, s));
     if (X_map) bpm::or_flags_kernel<<<cdiv(N, 256), 256, 0, s>>>(h->h_changed, h->h_accept, N);
   }
+  h->h_mom_len = st.mom_len; h->h_pending = st.pending;
   if (X_map) {
     bpm::scatter_changed_rows_kernel<<<cdiv((int64_t)N * 32, 256), 256, 0, s>>>(h->hX, h->hL, h->h_changed, X_map,
                                                                                L_map, N, h->cfg.ld, h->h_nrows);
@@ -898,6 +924,12 @@ int bpm_generations_host(bpm_handle h, double* X_host, double* lnl_host, int64_t
     CU_TRY(cudaStreamSynchronize(s));
     h->last_d2h_bytes = nx + nl;
   }
+  return 0;
+}
+
+int bpm_host_entry_restart(bpm_handle h) {
+  if (!h) return fail("null handle");
+  h->h_mom_len = 0; h->h_pending = 0;
   return 0;
 }
 

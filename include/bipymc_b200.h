@@ -235,10 +235,17 @@ int bpm_peer_barrier(bpm_handle h, bpm_stream stream);
 int bpm_sync_error(bpm_handle h, int32_t* err);
 
 /* Host-buffer entry (the end-to-end path): X_host / lnl_host are HOST arrays (pinned
- * for full speed); copies them to the device, runs n_gen native generations without
- * history, copies the result back.  Synchronous. */
+ * for full speed); copies them to the device, runs n_gen native generations, copies the
+ * result back.  Synchronous.  The chain HISTORY stays with the caller (the host arrays are
+ * McmcChain.current_pos of every chain; appending them is the caller's np.vstack, chain.py:51-54).
+ * What DREAM derives from the history -- the per-chain running mean / M2 behind np.std(chain.chain)
+ * (dream.py:128) -- is kept on the device by the handle between calls, so crossover adaptation runs
+ * exactly as in bpm_step_generations: the moments start with the population of the first call
+ * (g_abs0 = the chains' length then) and see every population handed in afterwards.
+ * bpm_host_entry_restart forgets them (a new sampling run through the same handle). */
 int bpm_generations_host(bpm_handle h, double* X_host, double* lnl_host, int64_t k_gen0,
                          int64_t g_abs0, int32_t n_gen);
+int bpm_host_entry_restart(bpm_handle h);
 /* When both host arrays are pinned (device-mapped) memory, bpm_generations_host writes back only
  * the rows of chains that moved (the device stores them straight into the host arrays; rows of
  * chains that did not move are already correct there).  Bytes the last call moved device->host. */

@@ -391,26 +391,32 @@ def test_large_d_quadratic_form_matches_numpy(dim, n, shift):
     np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-10)
 
 
+@pytest.mark.parametrize("adapt", [False, True], ids=["noadapt", "adapt"])
 @pytest.mark.parametrize("pinned", [True, False])
-def test_host_buffer_entry_equals_device_resident_generations(pinned):
+def test_host_buffer_entry_equals_device_resident_generations(pinned, adapt):
     """bpm_generations_host (the end-to-end entry: HOST population in, HOST population out) must
     leave exactly the population a device-resident run produces -- both with pinned buffers (only
-    the rows that moved are written back by the device) and with pageable ones (full copy)."""
+    the rows that moved are written back by the device) and with pageable ones (full copy) -- and,
+    with crossover adaptation on, the same p_cr: the entry keeps the chains' running moments on the
+    device between calls (dream.py:119-140 needs np.std of every chain's history)."""
     import ctypes as C
+    import os
     import torch
     from bipymc_b200 import DreamMpi, targets, _lib
-    N, d, G = 4096, 100, 5
+    N, d, G = 4096, 100, 7
     tgt = targets.Gauss_100D()
+    kw = dict(burnin_gen=1000, n_cr_gen=2) if adapt else dict(burnin_gen=0)
     np.random.seed(1)
-    a = DreamMpi(tgt.ln_like, np.zeros(d), n_chains=N, seed=8, varepsilon=1.0, history="none", burnin_gen=0)
+    a = DreamMpi(tgt.ln_like, np.zeros(d), n_chains=N, seed=8, varepsilon=1.0, history="none", **kw)
     np.random.seed(1)
-    b = DreamMpi(tgt.ln_like, np.zeros(d), n_chains=N, seed=8, varepsilon=1.0, history="none", burnin_gen=0)
+    b = DreamMpi(tgt.ln_like, np.zeros(d), n_chains=N, seed=8, varepsilon=1.0, history="none", **kw)
     b.run_mcmc(N)                                   # sets run parameters, evaluates the initial likelihoods
     Xh = torch.empty((N, b._ld), dtype=torch.float64)
     Lh = torch.empty((N,), dtype=torch.float64)
     if pinned:
         Xh, Lh = Xh.pin_memory(), Lh.pin_memory()
     Xh.copy_(b._X.cpu()); Lh.copy_(b._lnl.cpu())
+    host_peer = pinned and os.environ.get("BIPYMC_B200_HOST_PEER", "") == "1"
     moved = 0
     for g in range(G):
         before = Xh.clone()
@@ -419,10 +425,15 @@ def test_host_buffer_entry_equals_device_resident_generations(pinned):
         _lib.check(b._libh.bpm_last_d2h_bytes(b._handle, C.byref(nb)))
         rows = int((before != Xh).any(dim=1).sum())
         moved += rows
-        if pinned:
+        if host_peer:       # accepted rows stored from inside the kernels + one copy of the cached likelihoods
+            assert nb.value == rows * b._ld * 8 + N * 8 + 16
+        elif pinned:
             assert nb.value == rows * (b._ld + 1) * 8 + 8
         else:
             assert nb.value == N * (b._ld + 1) * 8
     a.run_mcmc(N * (G + 1))
     assert torch.equal(a._X.cpu(), Xh) and torch.equal(a._lnl.cpu(), Lh)
     assert moved == a.n_accepted
+    if adapt:
+        assert a.n_cr_updates.sum() > 0
+        assert np.array_equal(a.p_cr, b.p_cr) and np.array_equal(a.delta_m, b.delta_m)

@@ -4,6 +4,7 @@
   python tools/ncu_summary.py launches  <launches.csv>          per-kernel count / mean duration / share of the step
   python tools/ncu_summary.py kernel    <report.ncu-rep>        headline metrics + warp-stall samples by reason
   python tools/ncu_summary.py regions   <report.ncu-rep> name:lo:hi ...   stall samples of SASS index ranges
+  python tools/ncu_summary.py traffic   <report.ncu-rep> "history=full,adapt=on" [csrc_sha16]   -> profiles/traffic.json
 """
 import csv
 import io
@@ -75,11 +76,40 @@ def regions(rep, specs):
               ", ".join("%s %.1f%%" % (n, 100.0 * c / tot) for c, n in agg if c)))
 
 
+def traffic(rep, key, sha=None):
+    """profiles/traffic.json: DRAM bytes (read + write) of the captured launch, keyed by the bench
+    configuration, together with the hash of csrc/ the capture was taken with (bench.py: roofline.traffic
+    is null for any other build).  `sha`: hash of the tree the capture ran on, when it differs from HEAD."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    rows = ncu_csv(rep, "raw")
+    h, units, v = rows[0], rows[1], rows[2]
+
+    def val(m):
+        x = float(v[h.index(m)].replace(",", ""))
+        return x * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[h.index(m)]]
+    tot = int(val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
+    path = os.path.join(root, "profiles", "traffic.json")
+    sha = sha or bench.csrc_hash()
+    j = json.load(open(path)) if os.path.exists(path) else {}
+    if j.get("csrc_sha16") != sha:
+        j = {"csrc_sha16": sha}
+    j[key] = tot
+    j["source"] = os.path.basename(rep)
+    json.dump(j, open(path, "w"), indent=1)
+    print(path, j)
+
+
 if __name__ == "__main__":
     mode = sys.argv[1]
     if mode == "launches":
         launches(sys.argv[2])
     elif mode == "kernel":
         kernel(sys.argv[2])
+    elif mode == "traffic":
+        traffic(*sys.argv[2:5])
     else:
         regions(sys.argv[2], sys.argv[3:])
