@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libbipymc_b200.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["rng.cuh", "step.cuh", "targets.cuh", "kernels_generic.cuh", "kernels_fused.cuh", "diagnostics.cuh", "gauss_dmma.cuh", "sync.cuh",
+HEADERS = ["rng.cuh", "step.cuh", "targets.cuh", "kernels_generic.cuh", "kernels_fused.cuh", "kernels_fused_v4.cuh", "diagnostics.cuh", "gauss_dmma.cuh", "sync.cuh",
            os.path.join("..", "..", "include", "bipymc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]

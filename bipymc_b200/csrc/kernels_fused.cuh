@@ -1369,7 +1369,11 @@ __global__ void __launch_bounds__(128) fused_small_kernel(const PhaseArgs a, con
   }
 }
 
-// Will try_fused_phase run the lazy-protocol kernel (fused_gauss_v3_kernel) for this configuration?
+}  // namespace bpm
+#include "kernels_fused_v4.cuh"     // fused_gauss_v4_kernel: v3 with TMA-staged partner gathers (uses the helpers above)
+namespace bpm {
+
+// Will try_fused_phase run a lazy-protocol kernel (fused_gauss_v4_kernel / _v3_kernel) for this configuration?
 // The engine asks BEFORE building the phase arguments, because that kernel leaves the generation's new
 // history row / moment sample pending (PhaseArgs::lazy) and the others do not.
 inline bool fused_plan_is_v3(int target, int d, int ld, int r, int variant) {
@@ -1429,8 +1433,23 @@ inline int try_fused_phase(const TargetView& tv, const PhaseArgs& a, cudaStream_
       if (!a.lazy) return 1;       // the engine must have planned the lazy protocol (fused_plan_is_v3)
       const int grid = n_tiles > 148 ? 148 : (n_tiles < 1 ? 1 : n_tiles);
       const bool d3 = a.algo == BPM_ALGO_DREAM && a.del_pairs == 3;
-      const size_t sm = fused_v3_smem(a.d);
+      const int npair = a.algo == BPM_ALGO_DREAM ? a.del_pairs : 1;
       int rc;
+      // default: TMA-staged gathers (v4) whenever its shared-memory layout fits; variant 5 = v3 (register gathers)
+      if (variant != 5 && fused_v4_fits(a.d, a.ld, tv.r, npair)) {
+        const size_t sm4 = v4_layout(a.d, tv.r, npair).total;
+        if (tv.mu_is_zero)
+          rc = d3 ? launch_fused_v4<REPLAY, false, 3>(a, g, grid, sm4, s)
+                  : launch_fused_v4<REPLAY, false, 0>(a, g, grid, sm4, s);
+        else
+          rc = d3 ? launch_fused_v4<REPLAY, true, 3>(a, g, grid, sm4, s)
+                  : launch_fused_v4<REPLAY, true, 0>(a, g, grid, sm4, s);
+        if (rc) return 1;
+        if (cudaGetLastError() != cudaSuccess) return 1;
+        *done = 1;
+        return 0;
+      }
+      const size_t sm = fused_v3_smem(a.d);
       if (tv.mu_is_zero)
         rc = d3 ? launch_fused_v3<REPLAY, false, 3>(a, g, grid, sm, s)
                 : launch_fused_v3<REPLAY, false, 0>(a, g, grid, sm, s);

@@ -47,7 +47,7 @@ def test_native_dream_gauss_with_nonzero_mean(dim):
 
 
 # ---- RNG-replay parity against the second batch of golden vectors (oracle/cases.py: EXTRA_CASES) --------
-@pytest.mark.parametrize("fused", [1, 0, 2, 3], ids=["fused", "split", "fused-halves", "fused-ws12"])
+@pytest.mark.parametrize("fused", [1, 0, 2, 3, 5], ids=["fused", "split", "fused-halves", "fused-ws12", "fused-v3"])
 @pytest.mark.parametrize("name", sorted(__import__("oracle.cases", fromlist=["EXTRA_CASES"]).EXTRA_CASES))
 def test_replay_extra_golden_cases(name, fused):
     """Includes gauss100_dream_tiles: 136 chains at d = 100, i.e. one full 64-chain tile plus a partial tile per
