@@ -179,6 +179,31 @@ def cpu_baseline_leg():
     return out
 
 
+def bind_to_gpu_numa(local_rank):
+    """Best effort: run this rank (and first-touch its pinned host buffers) on the NUMA node its GPU hangs
+    off, so eight ranks' host copies do not all cross one socket link.  Returns the node or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(hnd).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def selfcheck_sharded(world, rank, local_rank):
     """N > 1 only (the driver's scaling run has no other multi-GPU correctness test): a small sharded DREAM
     run through the same entry points as the timed one must reproduce, bit for bit, rank 0's single-GPU
@@ -355,43 +380,46 @@ def run_ours(args):
                        "chains that moved (and their lnL) back into the pinned host arrays, every step; the "
                        "host arrays hold the full updated population"}
 
-    if world > 1 and not args.no_e2e and args.subpop_k == 0:
-        # sharded end-to-end step: every rank copies ITS shard (states + cached likelihoods) in from
-        # pinned host memory, the replicas are completed by an all-gather, one generation runs
-        # through the same C-ABI calls run_mcmc makes, and the shard is copied back out
+    if world > 1 and not args.no_e2e and args.subpop_k == 0 and s._sync_on:
+        # sharded end-to-end step through the C-ABI (bpm_generations_host_sharded): every rank hands in ITS
+        # shard (states + cached likelihoods) in pinned host memory; one kernel streams it over PCIe into
+        # every replica (host copy + all-gather fused), a generation runs, accepted rows are stored back into
+        # the host shard by the phase kernels, the cached likelihoods return with one copy.
+        numa = bind_to_gpu_numa(local_rank)
         lo, hi = int(s.rank_chain_ids[0]), int(s.rank_chain_ids[-1]) + 1
         Xh = torch.empty((hi - lo, s._ld), dtype=torch.float64).pin_memory()
         Lh = torch.empty((hi - lo,), dtype=torch.float64).pin_memory()
+        s._flush()
         Xh.copy_(s._X[lo:hi]); Lh.copy_(s._lnl[lo:hi])
-        g0 = s._hist.length
         ke = max(3, min(K, 20))
+        st = s._state(None)
+        stream = s._stream()
+        d2h, b = 0, C.c_uint64()
 
         def e2e_step(i):
-            s._X[lo:hi].copy_(Xh, non_blocking=True)
-            s._lnl[lo:hi].copy_(Lh, non_blocking=True)
-            s._allgather_population()
-            st = s._state(None)
-            st.hist_len = g0 + i
-            st.mom_len = s._mom_len + i
-            s._split_generation(st, k_done + i)
-            Xh.copy_(s._X[lo:hi], non_blocking=True)
-            Lh.copy_(s._lnl[lo:hi], non_blocking=True)
-            torch.cuda.synchronize(dev)
+            _lib.check(lib.bpm_generations_host_sharded(h, C.byref(st), Xh.data_ptr(), Lh.data_ptr(), k_done + i, 1,
+                                                        stream))
         for i in range(2):
             e2e_step(i)
         sync_all()
         t0 = time.perf_counter()
         for i in range(ke):
             e2e_step(2 + i)
+            lib.bpm_last_d2h_bytes(h, C.byref(b))
+            d2h += b.value
         sync_all()
-        dt_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
-        dt = float(dt_t.item())
+        dt_t = torch.tensor([time.perf_counter() - t0, d2h / ke], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt_t[0:1], op=dist.ReduceOp.MAX)
+        dist.all_reduce(dt_t[1:2], op=dist.ReduceOp.SUM)
+        dt, d2h_all = float(dt_t[0].item()), float(dt_t[1].item())
+        s._pending, s._mom_len = int(st.pending), int(st.mom_len)
         nb = (N * s._ld * 8 + N * 8)
-        e2e = {"value": N * ke / dt, "unit": UNIT, "h2d_bytes_per_step": nb, "d2h_bytes_per_step": nb,
-               "steps": ke, "ms_per_step": 1e3 * dt / ke,
-               "note": "per rank: pinned host shard -> H2D, NCCL all-gather of the replicas, one sharded "
-                       "generation, shard -> D2H; bytes are summed over ranks"}
+        e2e = {"value": N * ke / dt, "unit": UNIT, "h2d_bytes_per_step": nb, "d2h_bytes_per_step": d2h_all,
+               "steps": ke, "ms_per_step": 1e3 * dt / ke, "host_numa_node": numa,
+               "note": "bpm_generations_host_sharded, per rank: pinned host shard -> ONE kernel streams it over PCIe "
+                       "into all %d replicas (host copy + all-gather fused, NVLink stores under the PCIe read) -> peer "
+                       "barrier -> one sharded generation (adaptation ON) whose phase kernels store accepted rows back "
+                       "into the host shard -> cached likelihoods D2H; bytes are summed over ranks" % world}
 
     # ---- second point: the same engine on a population AT STATIONARITY (chains drawn from the target) ---
     # acceptance-dependent traffic (accepted-row stores, peer stores, changed-rows write-back) is then

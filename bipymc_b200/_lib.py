@@ -89,6 +89,8 @@ SIGNATURES = {
     "bpm_generations_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                        C.c_int32]),
     "bpm_host_entry_restart": (C.c_int, [C.c_void_p]),
+    "bpm_generations_host_sharded": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p, C.c_void_p, C.c_int64,
+                                               C.c_int32, C.c_void_p]),
     "bpm_dev_alloc": (C.c_int, [C.c_int32, C.c_uint64, C.POINTER(C.c_void_p)]),
     "bpm_dev_free": (C.c_int, [C.c_int32, C.c_void_p]),
     "bpm_ipc_export": (C.c_int, [C.c_int32, C.c_void_p, C.c_char_p]),

@@ -927,6 +927,58 @@ int bpm_generations_host(bpm_handle h, double* X_host, double* lnl_host, int64_t
   return 0;
 }
 
+int bpm_generations_host_sharded(bpm_handle h, bpm_state* st, double* X_host, double* lnl_host, int64_t k_gen0,
+                                 int32_t n_gen, bpm_stream stream) {
+  if (!h || !st || !st->X || !st->lnl || !X_host || !lnl_host) return fail("null argument");
+  if (!h->sharded()) return fail("bpm_generations_host_sharded: the handle owns every chain; use bpm_generations_host");
+  if (!h->sync_on || h->n_peers != h->sync.world - 1)
+    return fail("bpm_generations_host_sharded needs the peer replicas (bpm_set_peers) and the peer barrier (bpm_set_sync)");
+  if (h->serial()) return fail("serial DE-MC is not offered on the sharded host entry");
+  if (h->n_peers >= BPM_MAX_PEERS) return fail("no peer slot left for the host array");
+  if (h->target == BPM_TARGET_EXTERNAL && !h->user_fn) return fail("needs a built-in target or a batched callback");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int lo = h->cfg.chain_lo, nloc = h->cfg.chain_hi - lo, ld = h->cfg.ld;
+  if (((size_t)ld * sizeof(double)) % 16 != 0) return fail("rows must be multiples of 16 bytes");
+  double *X_map = nullptr;
+  {
+    cudaPointerAttributes ax;
+    if (cudaPointerGetAttributes(&ax, X_host) != cudaSuccess || ax.type != cudaMemoryTypeHost || !ax.devicePointer) {
+      cudaGetLastError();
+      return fail("bpm_generations_host_sharded: X_host must be pinned (device-mapped) host memory");
+    }
+    X_map = (double*)ax.devicePointer;
+  }
+  const size_t off = (size_t)lo * ld;
+  bpm::ShardInArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.src = reinterpret_cast<const double2*>(X_map);
+  sa.dst[0] = reinterpret_cast<double2*>(st->X + off);
+  for (int p = 0; p < h->n_peers; ++p) sa.dst[1 + p] = reinterpret_cast<double2*>(h->peers[p] + off);
+  sa.n_dst = 1 + h->n_peers;
+  sa.n2 = (int64_t)nloc * ld / 2;
+  unsigned long long acc0 = 0, acc1 = 0;
+  CU_TRY(cudaMemcpyAsync(&acc0, h->counters, sizeof(acc0), cudaMemcpyDeviceToHost, s));
+  h->prof_begin(7, s);
+  bpm::shard_in_kernel<<<296, 512, 0, s>>>(sa);
+  CU_TRY(cudaGetLastError());
+  h->prof_end(s);
+  CU_TRY(cudaMemcpyAsync(st->lnl + lo, lnl_host, sizeof(double) * nloc, cudaMemcpyHostToDevice, s));
+  BPM_TRY(h->peer_barrier(s));                  // every replica holds every shard
+  // the caller's host array is one more "replica": accepted rows are stored into it from inside the phase
+  // kernels (indexed by global chain id, hence the offset base; only this rank's rows are ever written)
+  h->peers[h->n_peers++] = X_map - off;
+  int rc = 0;
+  for (int g = 0; g < n_gen && rc == 0; ++g) rc = h->generation<false>(st, k_gen0 + g, nullptr, nullptr, s);
+  h->peers[--h->n_peers] = nullptr;
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(lnl_host, st->lnl + lo, sizeof(double) * nloc, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaMemcpyAsync(&acc1, h->counters, sizeof(acc1), cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  h->last_d2h_bytes = (acc1 - acc0) * (sizeof(double) * ld) + sizeof(double) * nloc + 2 * sizeof(acc0);
+  return 0;
+}
+
 int bpm_host_entry_restart(bpm_handle h) {
   if (!h) return fail("null handle");
   h->h_mom_len = 0; h->h_pending = 0;

@@ -13,8 +13,9 @@
 //   * the chain's own row and M2 row (sequential, streamed) are prefetched into 16 registers at the same
 //     moment -- registers the landing area no longer needs; the mean row is loaded once S is done;
 //   * the landing slots (16 x 4.8 KB at d = 100) take the shared memory of v3's second proposal tile:
-//     there is ONE 64-row proposal tile, handed over per 8-row m-tile (mbarriers FULLm / DONEm[8]); a
-//     producer writes its row of m-tile cw only after consumer cw released the previous tile's;
+//     there is ONE 64-row proposal tile, handed over per 8-row m-tile (named barrier per m-tile towards
+//     the consumer -- a blocking hardware wait, no polling -- and mbarrier DONEm[8] back); a producer
+//     writes its row of m-tile cw only after consumer cw released the previous tile's;
 //   * consumers are v3's: 8 warps, one m-tile each on the FP64 tensor pipe (mma.sync.m8n8k4.f64, W in
 //     DMMA fragment order in shared memory), Metropolis decision in registers, accepted rows stored from
 //     the tile (and into the peer replicas) by the deciding warp.
@@ -62,6 +63,9 @@ inline bool fused_v4_fits(int d, int ld, int r, int npair) {
          v4_layout(d, r, npair).total <= kMaxDynSmem;
 }
 
+constexpr int kV4BarFull0 = 3;                       // named barriers 3 .. 10 (0 = __syncthreads, 2 = BAR_CONS)
+constexpr int kV4FullCount = 32 * (8 + 1);           // 8 producing warps + the consumer warp
+
 // rows of the own chain prefetched one chain ahead
 struct V4Pre {
   double2 u0, u1, w0, w1;
@@ -88,13 +92,14 @@ fused_gauss_v4_kernel(const PhaseArgs a, const GaussArgs g) {
   int* row_c = reinterpret_cast<int*>(smem4 + L4.cid);             // chain id of every tile row, -1 = empty
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem4 + L4.bars);
   uint64_t* LAND = bars;                               // [16] partner rows of the warp's chain have landed
-  uint64_t* FULLm = bars + kV3ProdWarps;               // [8]  all 8 rows of m-tile cw are in the tile
-  uint64_t* DONEm = FULLm + kV3ConsWarps;              // [8]  consumer cw is done with its m-tile
+  uint64_t* DONEm = bars + kV3ProdWarps;               // [8]  consumer cw is done with its m-tile
+  // "all 8 rows of m-tile cw are in the tile" is named barrier kV4BarFull0 + cw: 8 producing warps arrive,
+  // the consumer warp syncs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   fill_tables_v3(a, g, tb, threadIdx.x, kV3Threads);
   if (threadIdx.x == 0) {
     for (int w = 0; w < kV3ProdWarps; ++w) mbar_init(LAND + w, 1);
-    for (int w = 0; w < kV3ConsWarps; ++w) { mbar_init(FULLm + w, 8); mbar_init(DONEm + w, 1); }
+    for (int w = 0; w < kV3ConsWarps; ++w) mbar_init(DONEm + w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -114,7 +119,7 @@ fused_gauss_v4_kernel(const PhaseArgs a, const GaussArgs g) {
     const bool decider = (lane & 3) == 0;
     const int my_row = 8 * warp + (lane >> 2);
     for (int i = 0; i < n_my; ++i) {
-      mbar_wait(FULLm + warp, i & 1);
+      nbar_sync(kV4BarFull0 + warp, kV4FullCount);      // blocks until the 8 producing warps arrived
       const double maha = gauss_tile_maha_dmma8<CENTER>(P, pld, tb.Ws, tb.mus, d, NT, warp, lane);
       const int c = decider ? row_c[my_row] : -1;
       int acc = 0;
@@ -156,7 +161,10 @@ fused_gauss_v4_kernel(const PhaseArgs a, const GaussArgs g) {
     return *reinterpret_cast<TileScratch*>(smem4 + L4.scratch + (size_t)(tile & 1) * t_stride);
   };
   double* land = reinterpret_cast<double*>(smem4 + L4.land) + (size_t)pw * L4.land_rows * d;
+  // Lanes past the row (4 lane >= d; 7 of 32 at d = 100) do the work of the last real lane on the same
+  // addresses and simply never store: no divergence, no zero-filled stand-in values.
   const bool act = 4 * lane < d;
+  const int lc = act ? lane : (d >> 2) - 1;
   const bool adapt = dream && a.adapt;
   const bool welford_var = adapt && !(REPLAY && a.hist_base != nullptr);
   const bool fold = a.pending && a.mean != nullptr;
@@ -171,8 +179,6 @@ fused_gauss_v4_kernel(const PhaseArgs a, const GaussArgs g) {
     const int row = pw + kV3ProdWarps * (n & 3);
     const int c = T.cid[row];
     pre.c = c;
-    const double2 z = make_double2(0.0, 0.0);
-    pre.u0 = z; pre.u1 = z; pre.w0 = z; pre.w1 = z;
     if (c < 0) return;
     if (lane == 0) mbar_expect_tx(LAND + pw, land_bytes);
     __syncwarp();
@@ -181,16 +187,32 @@ fused_gauss_v4_kernel(const PhaseArgs a, const GaussArgs g) {
       const int id = (lane & 1) ? T.pb[row][p] : T.pa[row][p];
       bulk_g2s(land + (size_t)lane * d, a.X + (size_t)id * a.ld, (uint32_t)(d * 8), LAND + pw);
     }
-    if (act) {
-      const double* xc = a.X + (size_t)c * a.ld + 4 * lane;
-      pre.u0 = ldg2(xc); pre.u1 = ldg2(xc + 2);
-      const size_t o = (size_t)(c - a.chain_lo) * a.ld + 4 * lane;
-      if (need_m2) { pre.w0 = ld_stream2(a.m2 + o); pre.w1 = ld_stream2(a.m2 + o + 2); }
+    const double* xc = a.X + (size_t)c * a.ld + 4 * lc;
+    pre.u0 = ldg2(xc); pre.u1 = ldg2(xc + 2);
+    if (need_m2) {
+      const double* mp = a.m2 + (size_t)(c - a.chain_lo) * a.ld + 4 * lc;
+      pre.w0 = ld_stream2(mp); pre.w1 = ld_stream2(mp + 2);
     }
+  };
+  // row `row` of the tile is complete: all 32 lanes arrive on the m-tile's named barrier (the consumer
+  // blocks in bar.sync there -- a hardware wait that costs no issue slots, unlike an mbarrier poll)
+  auto hand_over = [&](int i, int row, int cw, int c, double u, const double* prv) {
+    if (i >= 1) mbar_wait(DONEm + cw, (i - 1) & 1);     // consumer cw released tile i-1's m-tile
+    if (act) {
+      double* prow = P + row * pld + 4 * lane;
+      *reinterpret_cast<double2*>(prow) = make_double2(prv[0], prv[1]);
+      *reinterpret_cast<double2*>(prow + 2) = make_double2(prv[2], prv[3]);
+    }
+    if (lane == 0) {
+      row_c[row] = c;
+      row_u[row] = u;
+    }
+    nbar_arrive(kV4BarFull0 + cw, kV4FullCount);
   };
 
   warp_stage_draws<REPLAY>(a, L, tb, scratch(0), g_lo, g_hi, pw, lane);
   V4Pre pre;
+  pre.u0 = pre.u1 = pre.w0 = pre.w1 = make_double2(0.0, 0.0);
   start_chain(0, pre);
 #pragma unroll 1
   for (int n = 0; n < n_total; ++n) {
@@ -200,156 +222,142 @@ fused_gauss_v4_kernel(const PhaseArgs a, const GaussArgs g) {
       warp_stage_draws<REPLAY>(a, L, tb, scratch(i + 1), g_lo + (i + 1) * kTileRows, g_hi, pw, lane);
     const TileScratch& T = scratch(i);
     const int c = pre.c;
+    if (c < 0) {                     // past the end of this CTA's range (last tile only): an empty row
+      const double zero[4] = {0.0, 0.0, 0.0, 0.0};
+      if (n + 1 < n_total) start_chain(n + 1, pre);
+      hand_over(i, row, cw, -1, 0.0, zero);
+      continue;
+    }
     double cur[4] = {pre.u0.x, pre.u0.y, pre.u1.x, pre.u1.y};
     double var[4] = {pre.w0.x, pre.w0.y, pre.w1.x, pre.w1.y};
-    double2 mn0 = make_double2(0.0, 0.0), mn1 = mn0;
-    double S[4] = {0, 0, 0, 0};
-    if (c >= 0) {
-      mbar_wait(LAND + pw, land_phase & 1);
-      land_phase += 1;
-      if (act) {
-        const double* lp = land + 4 * lane;
-        if constexpr (NPAIR == 3) {
-          double2 va[3][2], vb[3][2];
+    double S[4];
+    mbar_wait(LAND + pw, land_phase & 1);
+    land_phase += 1;
+    {
+      const double* lp = land + 4 * lc;
+      if constexpr (NPAIR == 3) {
+        double2 va[3][2], vb[3][2];
 #pragma unroll
-          for (int p = 0; p < 3; ++p) {
-            va[p][0] = *reinterpret_cast<const double2*>(lp + (2 * p) * d);
-            va[p][1] = *reinterpret_cast<const double2*>(lp + (2 * p) * d + 2);
-            vb[p][0] = *reinterpret_cast<const double2*>(lp + (2 * p + 1) * d);
-            vb[p][1] = *reinterpret_cast<const double2*>(lp + (2 * p + 1) * d + 2);
-          }
+        for (int p = 0; p < 3; ++p) {
+          va[p][0] = *reinterpret_cast<const double2*>(lp + (2 * p) * d);
+          va[p][1] = *reinterpret_cast<const double2*>(lp + (2 * p) * d + 2);
+          vb[p][0] = *reinterpret_cast<const double2*>(lp + (2 * p + 1) * d);
+          vb[p][1] = *reinterpret_cast<const double2*>(lp + (2 * p + 1) * d + 2);
+        }
+        S[0] = __dsub_rn(va[0][0].x, vb[0][0].x); S[1] = __dsub_rn(va[0][0].y, vb[0][0].y);
+        S[2] = __dsub_rn(va[0][1].x, vb[0][1].x); S[3] = __dsub_rn(va[0][1].y, vb[0][1].y);
 #pragma unroll
-          for (int p = 0; p < 3; ++p) {
-            const double df0 = __dsub_rn(va[p][0].x, vb[p][0].x), df1 = __dsub_rn(va[p][0].y, vb[p][0].y);
-            const double df2 = __dsub_rn(va[p][1].x, vb[p][1].x), df3 = __dsub_rn(va[p][1].y, vb[p][1].y);
-            S[0] = p == 0 ? df0 : __dadd_rn(S[0], df0);
-            S[1] = p == 0 ? df1 : __dadd_rn(S[1], df1);
-            S[2] = p == 0 ? df2 : __dadd_rn(S[2], df2);
-            S[3] = p == 0 ? df3 : __dadd_rn(S[3], df3);
-          }
-        } else {
-          for (int p = 0; p < npair; ++p) {
-            const double2 s0 = *reinterpret_cast<const double2*>(lp + (2 * p) * d);
-            const double2 s1 = *reinterpret_cast<const double2*>(lp + (2 * p) * d + 2);
-            const double2 t0 = *reinterpret_cast<const double2*>(lp + (2 * p + 1) * d);
-            const double2 t1 = *reinterpret_cast<const double2*>(lp + (2 * p + 1) * d + 2);
-            const double df0 = __dsub_rn(s0.x, t0.x), df1 = __dsub_rn(s0.y, t0.y);
-            const double df2 = __dsub_rn(s1.x, t1.x), df3 = __dsub_rn(s1.y, t1.y);
-            S[0] = p == 0 ? df0 : __dadd_rn(S[0], df0);
-            S[1] = p == 0 ? df1 : __dadd_rn(S[1], df1);
-            S[2] = p == 0 ? df2 : __dadd_rn(S[2], df2);
-            S[3] = p == 0 ? df3 : __dadd_rn(S[3], df3);
-          }
+        for (int p = 1; p < 3; ++p) {
+          S[0] = __dadd_rn(S[0], __dsub_rn(va[p][0].x, vb[p][0].x));
+          S[1] = __dadd_rn(S[1], __dsub_rn(va[p][0].y, vb[p][0].y));
+          S[2] = __dadd_rn(S[2], __dsub_rn(va[p][1].x, vb[p][1].x));
+          S[3] = __dadd_rn(S[3], __dsub_rn(va[p][1].y, vb[p][1].y));
+        }
+      } else {
+        S[0] = S[1] = S[2] = S[3] = 0.0;
+        for (int p = 0; p < npair; ++p) {
+          const double2 s0 = *reinterpret_cast<const double2*>(lp + (2 * p) * d);
+          const double2 s1 = *reinterpret_cast<const double2*>(lp + (2 * p) * d + 2);
+          const double2 t0 = *reinterpret_cast<const double2*>(lp + (2 * p + 1) * d);
+          const double2 t1 = *reinterpret_cast<const double2*>(lp + (2 * p + 1) * d + 2);
+          const double df0 = __dsub_rn(s0.x, t0.x), df1 = __dsub_rn(s0.y, t0.y);
+          const double df2 = __dsub_rn(s1.x, t1.x), df3 = __dsub_rn(s1.y, t1.y);
+          S[0] = p == 0 ? df0 : __dadd_rn(S[0], df0);
+          S[1] = p == 0 ? df1 : __dadd_rn(S[1], df1);
+          S[2] = p == 0 ? df2 : __dadd_rn(S[2], df2);
+          S[3] = p == 0 ? df3 : __dadd_rn(S[3], df3);
         }
       }
-      __syncwarp();                                                       // every lane has read the slot ...
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // ... before the async proxy refills it
     }
+    __syncwarp();                                                       // every lane has read the slot ...
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // ... before the async proxy refills it
     // the next chain's gather runs under the rest of this chain
     if (n + 1 < n_total) start_chain(n + 1, pre);
 
-    double prv[4] = {0.0, 0.0, 0.0, 0.0};
-    if (c >= 0) {
-      if (act && a.pending) {
-        // the mean row's latency hides behind the draws below; the pending history row leaves from registers
-        const size_t o = (size_t)(c - a.chain_lo) * a.ld + 4 * lane;
-        if (fold) { mn0 = ld_stream2(a.mean + o); mn1 = ld_stream2(a.mean + o + 2); }
-        if (a.hist_cur) {
-          st_stream2(a.hist_cur + o, cur[0], cur[1]);
-          st_stream2(a.hist_cur + o + 2, cur[2], cur[3]);
-        }
+    const size_t o = (size_t)(c - a.chain_lo) * a.ld + 4 * lc;
+    double2 mn0 = make_double2(0.0, 0.0), mn1 = mn0;
+    if (a.pending) {
+      // the mean row's latency hides behind the draws below; the pending history row leaves from registers
+      if (fold) { mn0 = ld_stream2(a.mean + o); mn1 = ld_stream2(a.mean + o + 2); }
+      if (a.hist_cur && act) {
+        st_stream2(a.hist_cur + o, cur[0], cur[1]);
+        st_stream2(a.hist_cur + o + 2, cur[2], cur[3]);
       }
-      uint32_t mbits = 0xFu;
-      double gamma;
-      const double gu = T.gamma_u[row];
-      if (dream) {
-        mbits = 0u;
-        const int m = T.cr_idx[row];
-        if (act) {
-          if (REPLAY) {
-            const double cr = tb.crv[m];
-            double z[4];
-            z4<REPLAY>(a, c, lane, z);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (z[q] <= cr) mbits |= 1u << q;
-          } else {
-            const uint32_t th = tb.thr[m];
-            const Philox4 q = draw4(a.rng, (uint32_t)c, RNG_Z, (uint32_t)lane);
-            mbits = (q.x <= th ? 1u : 0u) | (q.y <= th ? 2u : 0u) | (q.z <= th ? 4u : 0u) | (q.w <= th ? 8u : 0u);
-          }
-        }
-        int d_prime = __reduce_add_sync(0xFFFFFFFFu, __popc(mbits));
-        if (d_prime == 0) {
-          const int fb = T.fallback[row] < 0 ? 0 : T.fallback[row];
-          if ((fb >> 2) == lane) mbits |= 1u << (fb & 3);
-          d_prime = 1;
-        }
-        gamma = tb.gam[d_prime];
-        if (a.gamma_jump) gamma = gu < a.gamma_p0 ? gamma : 1.0;
+    }
+    uint32_t mbits = 0xFu;
+    double gamma;
+    const double gu = T.gamma_u[row];
+    if (dream) {
+      const int m = T.cr_idx[row];
+      if (REPLAY) {
+        const double cr = tb.crv[m];
+        double z[4];
+        z4<REPLAY>(a, c, lc, z);
+        mbits = (z[0] <= cr ? 1u : 0u) | (z[1] <= cr ? 2u : 0u) | (z[2] <= cr ? 4u : 0u) | (z[3] <= cr ? 8u : 0u);
       } else {
-        gamma = demc_gamma(a, gu);
+        const uint32_t th = tb.thr[m];
+        const Philox4 q = draw4(a.rng, (uint32_t)c, RNG_Z, (uint32_t)lc);
+        mbits = (q.x <= th ? 1u : 0u) | (q.y <= th ? 2u : 0u) | (q.z <= th ? 4u : 0u) | (q.w <= th ? 8u : 0u);
       }
-      double delta = 0.0;
-      if (act) {
-        double e[4], nn[4];
-        en4<REPLAY>(a, c, lane, e, nn);
-        if (fold) {
-          welford_update(cur[0], a.inv_mom, mn0.x, var[0]);
-          welford_update(cur[1], a.inv_mom, mn0.y, var[1]);
-          welford_update(cur[2], a.inv_mom, mn1.x, var[2]);
-          welford_update(cur[3], a.inv_mom, mn1.y, var[3]);
-          const size_t o = (size_t)(c - a.chain_lo) * a.ld + 4 * lane;
+      int d_prime = __reduce_add_sync(0xFFFFFFFFu, act ? __popc(mbits) : 0);
+      if (d_prime == 0) {
+        const int fb = T.fallback[row] < 0 ? 0 : T.fallback[row];
+        if ((fb >> 2) == lane) mbits |= 1u << (fb & 3);
+        d_prime = 1;
+      }
+      gamma = tb.gam[d_prime];
+      if (a.gamma_jump) gamma = gu < a.gamma_p0 ? gamma : 1.0;
+    } else {
+      gamma = demc_gamma(a, gu);
+    }
+    double delta = 0.0, prv[4];
+    {
+      double e[4], nn[4];
+      en4<REPLAY>(a, c, lc, e, nn);
+      if (fold) {
+        welford_update(cur[0], a.inv_mom, mn0.x, var[0]);
+        welford_update(cur[1], a.inv_mom, mn0.y, var[1]);
+        welford_update(cur[2], a.inv_mom, mn1.x, var[2]);
+        welford_update(cur[3], a.inv_mom, mn1.y, var[3]);
+        if (act) {
           st_stream2(a.mean + o, mn0.x, mn0.y); st_stream2(a.mean + o + 2, mn1.x, mn1.y);
           st_stream2(a.m2 + o, var[0], var[1]); st_stream2(a.m2 + o + 2, var[2], var[3]);
         }
+      }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          double pr;
-          if (dream) {
-            pr = dream_prop(cur[q], S[q], e[q], nn[q], gamma, (mbits >> q) & 1u ? 1.0 : 0.0);
-            if (adapt) {
-              double v;
-              if (welford_var) {
-                v = __dmul_rn(var[q], a.inv_mom);
-                if (!(v > 0.0)) v = 1e-12 * 1e-12;
-              } else {
-                v = cr_variance<REPLAY>(a, c, 4 * lane + q);
-              }
-              delta += cr_term(cur[q], pr, v);
+      for (int q = 0; q < 4; ++q) {
+        double pr;
+        if (dream) {
+          pr = dream_prop(cur[q], S[q], e[q], nn[q], gamma, (mbits >> q) & 1u ? 1.0 : 0.0);
+          if (adapt) {
+            double v;
+            if (welford_var) {
+              v = __dmul_rn(var[q], a.inv_mom);
+              if (!(v > 0.0)) v = 1e-12 * 1e-12;
+            } else {
+              v = cr_variance<REPLAY>(a, c, 4 * lc + q);
             }
-          } else {
-            pr = demc_prop(cur[q], S[q], nn[q], gamma);
+            delta += cr_term(cur[q], pr, v);
           }
-          prv[q] = pr;
+        } else {
+          pr = demc_prop(cur[q], S[q], nn[q], gamma);
         }
-        if (REPLAY && a.tr.prop) {
-          double* tp = a.tr.prop + (size_t)c * d + 4 * lane;
+        prv[q] = pr;
+      }
+      if (REPLAY && a.tr.prop && act) {
+        double* tp = a.tr.prop + (size_t)c * d + 4 * lane;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) tp[q] = prv[q];
-        }
-      }
-      if (dream) {
-        delta = group_sum_d<32>(delta);
-        if (lane == 0) {
-          a.cr_pick[c] = adapt ? T.cr_idx[row] : -1;
-          a.cr_delta[c] = delta;
-        }
+        for (int q = 0; q < 4; ++q) tp[q] = prv[q];
       }
     }
-    // hand the row over: m-tile cw of the single proposal tile, free once consumer cw released tile i-1's
-    if (i >= 1) mbar_wait(DONEm + cw, (i - 1) & 1);
-    if (act) {
-      double* prow = P + row * pld + 4 * lane;
-      *reinterpret_cast<double2*>(prow) = make_double2(prv[0], prv[1]);
-      *reinterpret_cast<double2*>(prow + 2) = make_double2(prv[2], prv[3]);
+    if (dream) {
+      delta = group_sum_d<32>(act ? delta : 0.0);
+      if (lane == 0) {
+        a.cr_pick[c] = adapt ? T.cr_idx[row] : -1;
+        a.cr_delta[c] = delta;
+      }
     }
-    if (lane == 0) {
-      row_c[row] = c;
-      row_u[row] = c >= 0 ? T.accept_u[row] : 0.0;
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(FULLm + cw);
+    hand_over(i, row, cw, c, T.accept_u[row], prv);
   }
 }
 

@@ -99,4 +99,32 @@ __global__ void __launch_bounds__(64) peer_cr_exchange_kernel(const SyncArgs a, 
   if (threadIdx.x == 0) cr_apply(red, n_cr, dm, cnt, p_cr);
 }
 
+// Sharded end-to-end entry: fused "host -> device copy + all-gather".  Every rank streams ITS shard of
+// the population out of the caller's pinned (mapped) host array -- 16-byte zero-copy reads over PCIe,
+// many in flight per thread -- and stores each chunk into its own replica and into every peer replica
+// (NVLink stores), so the replicas are complete when the PCIe read ends; the reference's
+// comm.Allgather of demc.py:93 rides under the host copy instead of following it.
+struct ShardInArgs {
+  const double2* src;             // mapped host shard [n2] double2
+  double2* dst[kSyncRanks];       // the shard's rows in every replica (own first)
+  int32_t n_dst;
+  int64_t n2;
+};
+__global__ void __launch_bounds__(512) shard_in_kernel(const ShardInArgs a) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < a.n2; i += 4 * stride) {
+    double2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = a.src[i + u * stride];
+    for (int p = 0; p < a.n_dst; ++p)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a.dst[p][i + u * stride] = v[u];
+  }
+  for (; i < a.n2; i += stride) {
+    const double2 v = a.src[i];
+    for (int p = 0; p < a.n_dst; ++p) a.dst[p][i] = v;
+  }
+}
+
 }  // namespace bpm

@@ -246,6 +246,16 @@ int bpm_sync_error(bpm_handle h, int32_t* err);
 int bpm_generations_host(bpm_handle h, double* X_host, double* lnl_host, int64_t k_gen0,
                          int64_t g_abs0, int32_t n_gen);
 int bpm_host_entry_restart(bpm_handle h);
+/* The same end-to-end step for a SHARDED population (one process per GPU; needs bpm_set_peers and
+ * bpm_set_sync).  X_host [n_local][ld] / lnl_host [n_local] are THIS rank's chains in pinned
+ * (device-mapped) host memory; st is the rank's device state (st->X = its full replica).  One kernel
+ * streams the shard out of host memory into every replica (host->device copy and the reference's
+ * Allgather, demc.py:93, fused: the NVLink stores ride under the PCIe read), a peer barrier follows,
+ * n_gen generations run with the host array registered as one more replica -- so accepted rows are
+ * written back by the phase kernels themselves -- and the cached likelihoods come back with one copy.
+ * Collective: every rank calls it with the same k_gen0 / n_gen.  Synchronous. */
+int bpm_generations_host_sharded(bpm_handle h, bpm_state* st, double* X_host, double* lnl_host,
+                                 int64_t k_gen0, int32_t n_gen, bpm_stream stream);
 /* When both host arrays are pinned (device-mapped) memory, bpm_generations_host writes back only
  * the rows of chains that moved (the device stores them straight into the host arrays; rows of
  * chains that did not move are already correct there).  Bytes the last call moved device->host. */
@@ -288,8 +298,8 @@ int bpm_rhat(bpm_handle h, const bpm_state* st, int64_t t0, double* rhat_host, b
 /* Per-kernel timing for the benchmark's roofline line: while on, every launch is
  * bracketed by CUDA events on the caller's stream.  bpm_profile_read synchronises and
  * returns total milliseconds and launch counts for 8 kinds: 0 split/shuffle, 1 propose,
- * 2 likelihood, 3 accept, 4 fused half-phase, 5 CR reduction, 6 peer barrier / CR exchange; then clears
- * the records. */
+ * 2 likelihood, 3 accept, 4 fused half-phase, 5 CR reduction, 6 peer barrier / CR exchange, 7 host shard
+ * copy-in + all-gather; then clears the records. */
 int bpm_profile(bpm_handle h, int32_t on);
 int bpm_profile_read(bpm_handle h, double* ms_by_kind8, int64_t* launches_by_kind8);
 
