@@ -233,8 +233,12 @@ __device__ __forceinline__ void fill_tables(const PhaseArgs& a, const GaussArgs&
       t.cdf[m] = __ddiv_rn(acc, tot);
       t.crv[m] = __ddiv_rn((double)(m + 1), (double)a.n_cr);
       // u32d(w) = (w + 0.5) 2^-32 <= cr  <=>  w <= floor(cr 2^32 - 0.5)   (all steps exact)
+#if BPM_ZEN_ONE
+      t.thr[m] = zen_threshold(t.crv[m]);
+#else
       const double lim = floor(t.crv[m] * 4294967296.0 - 0.5);
       t.thr[m] = lim >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)lim;
+#endif
     }
   }
 }
@@ -946,8 +950,12 @@ __device__ __forceinline__ void tile_stage_propose_v3(const PhaseArgs& a, const 
             if (z[q] <= cr) mbits |= 1u << q;
         } else {
           const uint32_t th = tb.thr[m];
+#if BPM_ZEN_ONE
+          mbits = zen_mask4(draw4(a.rng, (uint32_t)c, RNG_ZEN, (uint32_t)lane), th);
+#else
           const Philox4 q = draw4(a.rng, (uint32_t)c, RNG_Z, (uint32_t)lane);
           mbits = (q.x <= th ? 1u : 0u) | (q.y <= th ? 2u : 0u) | (q.z <= th ? 4u : 0u) | (q.w <= th ? 8u : 0u);
+#endif
         }
       }
       int d_prime = __reduce_add_sync(0xFFFFFFFFu, __popc(mbits));
@@ -1153,8 +1161,12 @@ __device__ __forceinline__ void fill_tables_v3(const PhaseArgs& a, const GaussAr
       acc = __dadd_rn(acc, a.p_cr[m]);
       t.cdf[m] = __ddiv_rn(acc, tot);
       t.crv[m] = __ddiv_rn((double)(m + 1), (double)a.n_cr);
+#if BPM_ZEN_ONE
+      t.thr[m] = zen_threshold(t.crv[m]);
+#else
       const double lim = floor(t.crv[m] * 4294967296.0 - 0.5);
       t.thr[m] = lim >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)lim;
+#endif
     }
   }
 }

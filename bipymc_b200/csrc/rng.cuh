@@ -44,6 +44,7 @@ enum : uint32_t {
   RNG_SCALAR = 0,  // slot 0: cr_u | accept_u ; slot 1: gamma_u | fallback ; slot 2+p: pair p
   RNG_Z = 1,       // slot = dim/4: four mask uniforms
   RNG_EN = 2,      // slot = dim/4: four box-jitter uniforms (16 bit) + four jitter normals
+  RNG_ZEN = 3,     // (BPM_ZEN_ONE) slot = dim/4: mask uniform, box jitter and jitter normal of four dims in ONE call
   RNG_GEN = 4,     // chain = 0xFFFFFFFF: slot 0 flip_u + Feistel keys, slot 1 more keys
   RNG_INIT = 5     // device-side chain initialisation jitter
 };
@@ -103,6 +104,16 @@ __device__ __forceinline__ void normal2(uint32_t a, uint32_t b, float& n0, float
 __device__ __forceinline__ void normal2_16(uint32_t w, float& n0, float& n1) {
   float u1 = ((float)(w & 0xFFFFu) + 1.0f) * (1.0f / 65536.0f);  // (0,1]
   float u2 = (float)(w >> 16) * (1.0f / 65536.0f);               // [0,1)
+  float r = sqrtf(-2.0f * __logf(u1));
+  float s, c;
+  __sincosf(6.283185307179586f * u2, &s, &c);
+  n0 = r * c;
+  n1 = r * s;
+}
+// Same from 12 + 12 bits.
+__device__ __forceinline__ void normal2_12(uint32_t b1, uint32_t b2, float& n0, float& n1) {
+  float u1 = ((float)b1 + 1.0f) * (1.0f / 4096.0f);   // (0,1]
+  float u2 = (float)b2 * (1.0f / 4096.0f);            // [0,1)
   float r = sqrtf(-2.0f * __logf(u1));
   float s, c;
   __sincosf(6.283185307179586f * u2, &s, &c);

@@ -218,6 +218,47 @@ __device__ __forceinline__ double accept_uniform(const PhaseArgs& a, int c) {
   return slot0_accept_u(draw4(a.rng, (uint32_t)c, RNG_SCALAR, 0));
 }
 
+// BPM_ZEN_ONE = 1: the three per-dimension draws of a 4-dim block -- crossover-mask uniform z (dream.py:52),
+// box jitter e (dream.py:83) and jitter normal n (dream.py:84) -- come from ONE Philox call instead of two.
+// Word k of the call belongs to dim 4b + k:  bits 0-11 z on a 4096-point grid, bits 12-19 e on a 256-point
+// grid, bits 20-31 twelve bits towards a Box-Muller pair (words 0,1 -> n0,n1; words 2,3 -> n2,n3).
+// The mask compares z with CR in {1/n_cr ..}: a 2^-12 grid moves each crossover probability by < 2.5e-4;
+// e only randomises gamma by +-1 %; n has sd epsilon ~ 1e-12.  A chain-step of the fused kernel is bound by
+// its instruction count, and a Philox call is ~70 of ~850 (profiles/r2c_*).
+#ifndef BPM_ZEN_ONE
+#define BPM_ZEN_ONE 0
+#endif
+__device__ __forceinline__ uint32_t zen_mask4(const Philox4& q, uint32_t th12) {
+  return ((q.x & 0xFFFu) <= th12 ? 1u : 0u) | ((q.y & 0xFFFu) <= th12 ? 2u : 0u) |
+         ((q.z & 0xFFFu) <= th12 ? 4u : 0u) | ((q.w & 0xFFFu) <= th12 ? 8u : 0u);
+}
+// u = (z12 + 0.5) / 4096 <= cr  <=>  z12 <= floor(cr * 4096 - 0.5)
+__device__ __forceinline__ uint32_t zen_threshold(double cr) {
+  const double lim = floor(cr * 4096.0 - 0.5);
+  return lim >= 4095.0 ? 0xFFFu : (lim < 0.0 ? 0xFFFFFFFFu : (uint32_t)lim);   // lim < 0: nothing passes (wraps: never <=)
+}
+__device__ __forceinline__ void zen_en4(const PhaseArgs& a, const Philox4& q, double e[4], double n[4]) {
+  e[0] = e[1] = e[2] = e[3] = 0.0;
+  n[0] = n[1] = n[2] = n[3] = 0.0;
+  if (a.u_eps > 0.0) {
+    const double lo = -a.u_eps, w = __dsub_rn(a.u_eps, lo);
+    const double w9 = w * (1.0 / 512.0);           // (h + 0.5) / 256 = (2h + 1) / 512
+    e[0] = __dadd_rn(lo, __dmul_rn(w9, (double)(int)(2u * ((q.x >> 12) & 0xFFu) + 1u)));
+    e[1] = __dadd_rn(lo, __dmul_rn(w9, (double)(int)(2u * ((q.y >> 12) & 0xFFu) + 1u)));
+    e[2] = __dadd_rn(lo, __dmul_rn(w9, (double)(int)(2u * ((q.z >> 12) & 0xFFu) + 1u)));
+    e[3] = __dadd_rn(lo, __dmul_rn(w9, (double)(int)(2u * ((q.w >> 12) & 0xFFu) + 1u)));
+  }
+  if (a.eps > 0.0) {
+    float f0, f1, f2, f3;
+    normal2_12(q.x >> 20, q.y >> 20, f0, f1);
+    normal2_12(q.z >> 20, q.w >> 20, f2, f3);
+    n[0] = __dmul_rn(a.eps, (double)f0);
+    n[1] = __dmul_rn(a.eps, (double)f1);
+    n[2] = __dmul_rn(a.eps, (double)f2);
+    n[3] = __dmul_rn(a.eps, (double)f3);
+  }
+}
+
 // Four per-dimension draws for dims 4b .. 4b+3 of chain c.
 template <bool REPLAY>
 __device__ __forceinline__ void z4(const PhaseArgs& a, int c, int b, double z[4]) {
@@ -228,8 +269,14 @@ __device__ __forceinline__ void z4(const PhaseArgs& a, int c, int b, double z[4]
       z[t] = i < a.d ? a.rp.z[(size_t)c * a.d + i] : 2.0;
     }
   } else {
+#if BPM_ZEN_ONE
+    Philox4 q = draw4(a.rng, (uint32_t)c, RNG_ZEN, (uint32_t)b);
+    z[0] = ((double)(q.x & 0xFFFu) + 0.5) * (1.0 / 4096.0); z[1] = ((double)(q.y & 0xFFFu) + 0.5) * (1.0 / 4096.0);
+    z[2] = ((double)(q.z & 0xFFFu) + 0.5) * (1.0 / 4096.0); z[3] = ((double)(q.w & 0xFFFu) + 0.5) * (1.0 / 4096.0);
+#else
     Philox4 q = draw4(a.rng, (uint32_t)c, RNG_Z, (uint32_t)b);
     z[0] = u32d(q.x); z[1] = u32d(q.y); z[2] = u32d(q.z); z[3] = u32d(q.w);
+#endif
   }
 }
 // Box jitter e (dream.py:83, var_box) and Gaussian jitter n (demc.py:182 / dream.py:84,
@@ -248,6 +295,10 @@ __device__ __forceinline__ void en4(const PhaseArgs& a, int c, int b, double e[4
   } else {
     e[0] = e[1] = e[2] = e[3] = 0.0;  // var_box returns 0. and draws nothing (util.py:24-28)
     n[0] = n[1] = n[2] = n[3] = 0.0;  // var_ball returns 0. and draws nothing (util.py:11-16)
+#if BPM_ZEN_ONE
+    if (a.u_eps > 0.0 || a.eps > 0.0) zen_en4(a, draw4(a.rng, (uint32_t)c, RNG_ZEN, (uint32_t)b), e, n);
+    return;
+#endif
     if (a.u_eps > 0.0 || a.eps > 0.0) {
       const Philox4 q = draw4(a.rng, (uint32_t)c, RNG_EN, (uint32_t)b);
       if (a.u_eps > 0.0) {
