@@ -108,6 +108,8 @@ SIGNATURES = {
     "bpm_omega": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "bpm_outlier_reset": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_void_p, C.c_void_p,
                                     C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_void_p]),
+    "bpm_cov_track": (C.c_int, [C.c_void_p, C.c_int32]),
+    "bpm_cov_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "bpm_rhat": (C.c_int, [C.c_void_p, C.POINTER(State), C.c_int64, C.c_void_p, C.c_void_p]),
 }
 

@@ -166,4 +166,24 @@ __global__ void __launch_bounds__(256) rhat_kernel(const double* __restrict__ me
   }
 }
 
+// Streaming cross moments of the population (posterior COVARIANCE without a stored history: north_star's
+// "posterior mean and covariance ... within Monte-Carlo standard error"): after every generation
+//   sum[i] += sum_c X[c][i],   cross[i][j] += sum_c X[c][i] X[c][j]   over this rank's chains.
+// O(n_local d^2) per generation -- a diagnostic for populations of 10^2 .. 10^4 chains, off by default.
+// One block per row i of the d x d matrix; thread j walks the chains (X[c][i] is a broadcast, X[c][j] coalesced).
+__global__ void __launch_bounds__(128) cross_moment_kernel(const double* __restrict__ X, int lo, int hi, int d, int ld,
+                                                           double* __restrict__ sum, double* __restrict__ cross) {
+  const int i = blockIdx.x;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    double acc = 0.0, s1 = 0.0;
+    for (int c = lo; c < hi; ++c) {
+      const double xi = X[(size_t)c * ld + i], xj = X[(size_t)c * ld + j];
+      acc = fma(xi, xj, acc);
+      s1 += xj;
+    }
+    cross[(size_t)i * d + j] += acc;
+    if (i == 0) sum[j] += s1;
+  }
+}
+
 }  // namespace bpm

@@ -127,6 +127,9 @@ struct bpm_engine {
   double* rh_out = nullptr;      // [dim]
   bool omega_on = false;
   int64_t omega_cnt = 0;
+  double* cov_acc = nullptr;     // [d + d*d] streaming sum / cross moments (bpm_cov_track)
+  bool cov_on = false;
+  int64_t cov_rows = 0;          // chain states accumulated (per local chain: generations)
   // optional per-kernel timing (bpm_profile): CUDA events around every launch, by kind
   struct Rec { int kind; cudaEvent_t a, b; };
   bool prof_on = false;
@@ -154,7 +157,7 @@ struct bpm_engine {
     cudaFree(counters); cudaFree(nan_flag); cudaFree(tparams); cudaFree(hX); cudaFree(hL); cudaFree(hMean); cudaFree(hM2);
     cudaFree(h_accept); cudaFree(h_changed); cudaFree(h_nrows);
     cudaFree(omega_sum); cudaFree(omega_buf); cudaFree(diag_out); cudaFree(diag_i); cudaFree(sort_tmp);
-    cudaFree(rh_mean); cudaFree(rh_m2); cudaFree(rh_out); cudaFree(sync_err);
+    cudaFree(rh_mean); cudaFree(rh_m2); cudaFree(rh_out); cudaFree(sync_err); cudaFree(cov_acc);
     for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ev_pool) cudaEventDestroy(e);
   }
@@ -392,6 +395,12 @@ struct bpm_engine {
   }
 
   int track_omega(const bpm_state* st, cudaStream_t s) {
+    if (cov_on) {
+      bpm::cross_moment_kernel<<<cfg.dim, 128, 0, s>>>(st->X, cfg.chain_lo, cfg.chain_hi, cfg.dim, cfg.ld, cov_acc,
+                                                       cov_acc + cfg.dim);
+      CU_TRY(cudaGetLastError());
+      cov_rows += 1;
+    }
     if (!omega_on) return 0;
     const int nloc = cfg.chain_hi - cfg.chain_lo;
     bpm::omega_accum_kernel<<<cdiv(nloc, 256), 256, 0, s>>>(st->lnl, omega_sum, cfg.chain_lo, cfg.chain_hi);
@@ -1141,6 +1150,31 @@ int bpm_omega_track(bpm_handle h, int32_t on) {
     h->omega_cnt = 0;
   }
   h->omega_on = on != 0;
+  return 0;
+}
+
+int bpm_cov_track(bpm_handle h, int32_t on) {
+  if (!h) return fail("null handle");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  const size_t n = (size_t)h->cfg.dim * (h->cfg.dim + 1);
+  if (on) {
+    if (!h->cov_acc) CU_TRY(cudaMalloc(&h->cov_acc, sizeof(double) * n));
+    CU_TRY(cudaMemset(h->cov_acc, 0, sizeof(double) * n));
+    h->cov_rows = 0;
+  }
+  h->cov_on = on != 0;
+  return 0;
+}
+
+int bpm_cov_read(bpm_handle h, double* sum_host, double* cross_host, int64_t* generations) {
+  if (!h || !sum_host || !cross_host || !generations) return fail("null argument");
+  if (!h->cov_acc) return fail("bpm_cov_read: nothing tracked (bpm_cov_track)");
+  CU_TRY(cudaSetDevice(h->cfg.device));
+  CU_TRY(cudaDeviceSynchronize());
+  const int d = h->cfg.dim;
+  CU_TRY(cudaMemcpy(sum_host, h->cov_acc, sizeof(double) * d, cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(cross_host, h->cov_acc + d, sizeof(double) * d * d, cudaMemcpyDeviceToHost));
+  *generations = h->cov_rows;
   return 0;
 }
 

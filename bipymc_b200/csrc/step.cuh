@@ -225,8 +225,10 @@ __device__ __forceinline__ double accept_uniform(const PhaseArgs& a, int c) {
 // The mask compares z with CR in {1/n_cr ..}: a 2^-12 grid moves each crossover probability by < 2.5e-4;
 // e only randomises gamma by +-1 %; n has sd epsilon ~ 1e-12.  A chain-step of the fused kernel is bound by
 // its instruction count, and a Philox call is ~70 of ~850 (profiles/r2c_*).
+// Measured (profiles/r2d_*): 125.7 -> 118.0 us per launch of the fused 100-D kernel; default on.  BPM_ZEN_ONE = 0
+// restores round 1's two calls (32-bit z, 16-bit e, 16 + 16-bit Box-Muller).
 #ifndef BPM_ZEN_ONE
-#define BPM_ZEN_ONE 0
+#define BPM_ZEN_ONE 1
 #endif
 __device__ __forceinline__ uint32_t zen_mask4(const Philox4& q, uint32_t th12) {
   return ((q.x & 0xFFFu) <= th12 ? 1u : 0u) | ((q.y & 0xFFFu) <= th12 ? 2u : 0u) |

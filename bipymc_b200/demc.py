@@ -602,6 +602,20 @@ class DeMcMpi(object):
         self.dim = len(theta_0)
         assert np.all(np.asarray(varepsilon) >= 0.0)
         N, d = self.n_chains, self.dim
+        if kwargs.get("device_init", False):
+            # populations too large to draw on the host (BASELINE config 5: 10^7 x 1000 doubles = 80 GB):
+            # theta_0 + sqrt(varepsilon) * randn on the device, seeded from the sampler's seed.  NOT numpy's
+            # stream, so such a run does not start from the reference's initial states -- opt-in, stated.
+            if self._handle is None:
+                self._create_handle()
+            g = torch.Generator(device=self._device)
+            g.manual_seed((int(self._seed) * 2654435761 + (self.comm.rank + 1 if self._subpop else 0)) % (1 << 62))
+            n_here = len(self.rank_chain_ids) if self._subpop else N
+            sd = torch.from_numpy(np.sqrt(np.broadcast_to(np.asarray(varepsilon, dtype=float), (d,))).copy()).to(self._device)
+            th = torch.from_numpy(theta_0).to(self._device)
+            self._set_population(None, x0_dev=(n_here, lambda out: out.copy_(
+                torch.randn(out.shape, generator=g, device=self._device, dtype=torch.float64) * sd + th)))
+            return
         # every rank draws the jitter of ALL chains so the replicas agree (demc.py seeds
         # every rank identically as well, tests/test_banana.py:17).  This is the FIRST use
         # of numpy's global stream, exactly as in the reference's constructor.
@@ -615,16 +629,27 @@ class DeMcMpi(object):
             x0 = x0t.cpu().numpy()
         self._set_population(x0)
 
-    def _set_population(self, x0, history=None):
+    def _set_population(self, x0, history=None, x0_dev=None):
         torch = _torch()
         N, d, ld = self._n_engine, self.dim, self._ld
         lo, hi = self._local_range()
         nl = hi - lo
-        if self._subpop:          # x0 covers every chain of the job: keep this island's block
-            g0, g1 = int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
-            x0 = np.asarray(x0)[g0:g1]
         self._X = self._alloc_population(N, ld)
-        self._X[:, :d] = torch.from_numpy(np.ascontiguousarray(x0)).to(self._device)
+        if x0_dev is not None:    # (rows, fill): the initial states are produced on the device, in place
+            rows, fill = x0_dev
+            assert rows == N
+            if ld == d:
+                fill(self._X)
+            else:
+                tmp = torch.empty((N, d), dtype=torch.float64, device=self._device)
+                fill(tmp)
+                self._X[:, :d] = tmp
+                del tmp
+        else:
+            if self._subpop:          # x0 covers every chain of the job: keep this island's block
+                g0, g1 = int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
+                x0 = np.asarray(x0)[g0:g1]
+            self._X[:, :d] = torch.from_numpy(np.ascontiguousarray(x0)).to(self._device)
         if self.comm.size > 1:
             import torch.distributed as dist
             torch.cuda.synchronize(self._device)
@@ -745,9 +770,19 @@ class DeMcMpi(object):
             st = self._state(None)
             _lib.check(self._libh.bpm_rhat(self._handle, C.byref(st), -1, out.ctypes.data, self._stream()))
             return out
-        mean, m2 = self._gathered_moments()
-        W = (m2 / (T - 1.0)).mean(dim=0)
-        B_over_T = mean.var(dim=0, unbiased=True)
+        # sharded: three all-reduced sums per dimension instead of gathering N x d moments (80 GB at config 5)
+        import torch.distributed as dist
+        mean, m2 = self._mean[:, :self.dim], self._m2[:, :self.dim]
+        n_all = float(self.n_chains)
+        # shift by a common origin (rank 0's first chain mean) so that sum(mean^2) - N gm^2 does not cancel
+        origin = mean[0].clone()
+        dist.broadcast(origin, src=0)
+        dm = mean - origin[None]
+        sums = torch.stack([dm.sum(dim=0), (dm * dm).sum(dim=0), m2.sum(dim=0)])
+        dist.all_reduce(sums)
+        gm = sums[0] / n_all
+        B_over_T = (sums[1] - n_all * gm * gm) / (n_all - 1.0)
+        W = sums[2] / (n_all * (T - 1.0))
         return torch.sqrt(((T - 1.0) / T * W + B_over_T) / W).cpu().numpy()
 
     def rhat_history(self, t0=None):
@@ -816,6 +851,30 @@ class DeMcMpi(object):
         gm = mean.mean(dim=0)
         var = (m2.sum(dim=0) + T * ((mean - gm[None]) ** 2).sum(dim=0)) / (T * mean.shape[0])
         return gm.cpu().numpy(), torch.sqrt(var).cpu().numpy()
+
+    def track_covariance(self, on=True):
+        """Start (and zero) / stop the device-side accumulation of the population's cross moments
+        (bpm_cov_track): the posterior covariance without a stored history."""
+        _lib.check(self._libh.bpm_cov_track(self._handle, 1 if on else 0))
+
+    def covariance_estimate(self):
+        """(mean [d], covariance [d, d]) pooled over every chain and every generation since
+        track_covariance(); sharded runs add the ranks' sums."""
+        d = self.dim
+        s1, s2, g = np.zeros(d), np.zeros((d, d)), C.c_int64()
+        _lib.check(self._libh.bpm_cov_read(self._handle, _lib.dptr(s1), _lib.dptr(s2), C.byref(g)))
+        n = float(g.value) * len(self.rank_chain_ids)
+        if self.comm.size > 1:
+            torch = _torch()
+            import torch.distributed as dist
+            t = torch.from_numpy(np.concatenate([s1, s2.ravel(), [n]])).to(self._device)
+            dist.all_reduce(t)
+            t = t.cpu().numpy()
+            s1, s2, n = t[:d], t[d:d + d * d].reshape(d, d), float(t[-1])
+        if n < 2:
+            raise RuntimeError("covariance_estimate(): nothing accumulated (track_covariance() first)")
+        m = s1 / n
+        return m, s2 / n - np.outer(m, m)
 
     def _mode(self):
         if self._target is not None:

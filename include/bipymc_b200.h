@@ -290,6 +290,16 @@ int bpm_omega_track(bpm_handle h, int32_t on);
 int bpm_omega(bpm_handle h, double** sum_dev, int64_t* count);
 int bpm_outlier_reset(bpm_handle h, bpm_state* st, const double* omega, int32_t* flags_dev,
                       int32_t* n_reset, double* stats_host, bpm_stream stream);
+/* Streaming posterior covariance (north_star: "posterior mean and covariance ... within Monte-Carlo
+ * standard error"; the reference gets it from the stored super chain, demc.py:235-248).  While on, every
+ * generation adds this rank's chain states to sum[d] and cross[d][d] (= sum x x^T) on the device;
+ * O(n_local d^2) per generation, meant for diagnostic runs.  bpm_cov_track(h, 1) zeroes and starts,
+ * (h, 0) stops; bpm_cov_read copies the sums and the number of generations accumulated to the host
+ * (covariance = cross / n - mean mean^T with n = generations * n_local; a sharded host adds the ranks'
+ * sums first).  Synchronises the device. */
+int bpm_cov_track(bpm_handle h, int32_t on);
+int bpm_cov_read(bpm_handle h, double* sum_host, double* cross_host, int64_t* generations);
+
 /* Gelman-Rubin R-hat per dimension over this handle's local chains: from history rows
  * [t0, hist_len) when t0 >= 0, from the running moments (mean, m2 over mom_len rows) when
  * t0 < 0.  rhat_host: dim doubles.  Synchronises the stream. */

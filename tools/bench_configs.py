@@ -109,7 +109,86 @@ def c5multi():
     dist.destroy_process_group()
 
 
+def c5full():
+    """BASELINE configs[4] AT SCALE (launch under torchrun, one rank per GPU): DREAM on the 1000-D correlated
+    Gaussian (direct log-density: the reference's log(pdf) underflows at d = 1000) with
+    C5_PER_GPU chains per GPU (default 1.25e6: 10^7 on 8 GPUs), in the stated sub-population mode -- every GPU
+    steps its chains as one island (pairs from the local opposite half, no replica of the 80 GB population),
+    islands re-dealt with one all-to-all every k generations (default 10).  History off, running moments and CR
+    adaptation on.  Reports chain-steps/s (device events, max over ranks, re-deal included), the FP64-roof
+    fraction of the quadratic-form kernel (2 d^2 flop per chain-step against the measured 36.5 TFLOP/s,
+    profiles/r1_fp64_probe_b200.txt), acceptance and the R-hat trend from the streaming moments."""
+    import ctypes as C
+    import torch.distributed as dist
+    from bipymc_b200 import DreamMpi, targets, _lib
+    rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    world = dist.get_world_size()
+    per = int(float(os.environ.get("C5_PER_GPU", "1250000")))
+    k = int(os.environ.get("C5_K", "10"))
+    gens = int(os.environ.get("C5_GENS", "10"))
+    N, d, warm = per * world, 1000, 3
+    t = targets.Gauss_100D(dim=d)
+    np.random.seed(1)
+    s = DreamMpi(t.ln_like, np.zeros(d), n_chains=N, seed=3, varepsilon=np.arange(d) + 1.0, history="none",
+                 burnin_gen=10 ** 6, n_cr_gen=2, device=local, subpop_k=k, device_init=True)
+    done = 0
+    trend = []
+
+    def gens_run(n):
+        nonlocal done
+        s.run_mcmc(N * (n + 1), _k_gen0=done)
+        done += n
+
+    def note():
+        rh = s.rhat()
+        trend.append({"generation": done, "rhat_max": float(np.max(rh)), "rhat_median": float(np.median(rh))})
+
+    gens_run(warm)
+    note()
+    _lib.check(s._libh.bpm_profile(s._handle, 1))
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    gens_run(gens)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_k, n_k = (C.c_double * 8)(), (C.c_int64 * 8)()
+    _lib.check(s._libh.bpm_profile_read(s._handle, ms_k, n_k))
+    _lib.check(s._libh.bpm_profile(s._handle, 0))
+    acc = s.acceptance_fraction
+    note()
+    gens_run(gens)
+    note()
+    mem = torch.cuda.max_memory_allocated() / 2 ** 30
+    if rank == 0:
+        kinds = ["split", "propose", "likelihood", "accept", "fused_phase", "cr_reduce"]
+        kms = dict((kinds[i], ms_k[i] / max(1, n_k[i])) for i in range(6) if n_k[i])
+        chains_per_launch = per / 2.0
+        out = {"config": "C5: DREAM Gauss_1000D, %d GPUs x %d chains, sub-population mode k=%d" % (world, per, k),
+               "n_chains": N, "dim": d, "generations_timed": gens,
+               "chain_steps_per_s": N * gens / (float(ms.item()) * 1e-3), "ms_per_generation": float(ms.item()) / gens,
+               "acceptance_fraction": acc, "rhat_trend": trend, "avg_launch_ms_by_kernel": kms,
+               "torch_peak_alloc_GiB_per_gpu": mem}
+        if "likelihood" in kms:
+            tf = 2.0 * d * d * chains_per_launch / (kms["likelihood"] * 1e-3) / 1e12
+            out["quadratic_form_fp64_tflops"] = tf
+            out["frac_of_fp64_peak_36.5"] = tf / 36.5
+            tot = sum(ms_k[i] for i in range(6))
+            out["quadratic_form_share_of_kernel_time"] = ms_k[2] / tot
+        print(json.dumps(out), flush=True)
+    s.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["c5full"]:
+        c5full()
+        sys.exit(0)
     if sys.argv[1:] == ["c5multi"]:
         c5multi()
         sys.exit(0)
