@@ -376,9 +376,9 @@ def run_ours(args):
                "steps": ke, "ms_per_step": 1e3 * dt / ke,
                "note": "bpm_generations_host: pinned host population -> H2D (all chains) -> one generation "
                        "(crossover adaptation ON: the entry keeps the chains' running moments on the device "
-                       "between calls; the chain history is the caller's) -> the device stores the rows of the "
-                       "chains that moved (and their lnL) back into the pinned host arrays, every step; the "
-                       "host arrays hold the full updated population"}
+                       "between calls; the chain history is the caller's), the phase kernels storing every accepted "
+                       "row straight into the pinned host array -> cached likelihoods D2H (8 N bytes), every step; "
+                       "the host arrays hold the full updated population"}
 
     if world > 1 and not args.no_e2e and args.subpop_k == 0 and s._sync_on:
         # sharded end-to-end step through the C-ABI (bpm_generations_host_sharded): every rank hands in ITS

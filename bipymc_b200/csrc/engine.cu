@@ -494,6 +494,54 @@ struct bpm_engine {
     return &tv;
   }
 
+  // d <= 4, native RNG, unsharded: every generation of the call in ONE persistent cooperative launch
+  // (kernels_fused.cuh: small_generations_kernel).  Returns done = 0 when the configuration is not covered.
+  int coop_blocks = 0;           // co-resident 256-thread blocks of small_generations_kernel (0 = not asked yet)
+  int try_small_generations(bpm_state* st, int64_t k_gen0, int n_gen, cudaStream_t s, int* done) {
+    *done = 0;
+    if (fused_ok != 1 || serial() || sharded() || cfg.dim > 4 || cov_on || n_peers > 0) return 0;
+    if (!(target == BPM_TARGET_BANANA || target == BPM_TARGET_BIMODAL || target == BPM_TARGET_LINEFIT)) return 0;
+    if (st->pending) BPM_TRY(flush(st, s));
+    const size_t sm = target == BPM_TARGET_LINEFIT ? sizeof(double) * 3 * linefit_M : 0;
+    void* fn = target == BPM_TARGET_BANANA ? (void*)bpm::small_generations_kernel<BPM_TARGET_BANANA>
+             : target == BPM_TARGET_BIMODAL ? (void*)bpm::small_generations_kernel<BPM_TARGET_BIMODAL>
+                                            : (void*)bpm::small_generations_kernel<BPM_TARGET_LINEFIT>;
+    if (coop_blocks == 0) {
+      int coop = 0, per_sm = 0, sms = 0;
+      CU_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg.device));
+      CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device));
+      CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, sm));
+      coop_blocks = coop ? sms * (per_sm < 4 ? per_sm : 4) : -1;
+    }
+    if (coop_blocks <= 0) return 0;
+    bpm::PhaseArgs a = make_args(st, k_gen0, 0, nullptr, nullptr);
+    a.loc_list = nullptr; a.loc_cnt = nullptr;        // chains are walked in order; no packed lists
+    bpm::SmallGens q;
+    memset(&q, 0, sizeof(q));
+    q.k_gen0 = k_gen0; q.n_gen = n_gen; q.burnin_gen = cfg.burnin_gen; q.n_cr_gen = cfg.n_cr_gen;
+    q.jump_mod = cfg.algo == BPM_ALGO_DREAM ? 5 : 10;
+    q.shuffle = cfg.shuffle; q.flip_p = cfg.flip; q.seed = cfg.seed;
+    q.hist0 = st->history; q.omega_sum = omega_on ? omega_sum : nullptr;
+    q.cr_block = cr_block; q.cr_part = cr_part; q.cr_dm = cr_dm; q.cr_cnt = cr_cnt; q.p_cr = p_cr;
+    int nb = cdiv(cfg.n_chains, 2048);
+    if (nb > bpm::kCrBlocks) nb = bpm::kCrBlocks;
+    int grid = cdiv(cfg.n_chains, 256);
+    if (grid > coop_blocks) grid = coop_blocks;
+    if (grid < nb) nb = grid;                           // (the partial sums stay in block order either way)
+    q.cr_blocks = nb;
+    const bpm::TargetView* tvp = this_target();
+    void* args[] = {(void*)&a, (void*)tvp, (void*)&q};
+    prof_begin(4, s);
+    CU_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), args, sm, s));
+    prof_end(s);
+    st->hist_len += n_gen;
+    if (st->mom_len > 0) st->mom_len += n_gen;
+    if (omega_on) omega_cnt += n_gen;
+    st->pending = 0;
+    *done = 1;
+    return 0;
+  }
+
   template <bool REPLAY>
   int generation(bpm_state* st, int64_t k_gen, const bpm_replay* rp, const bpm_trace_out* tr,
                  cudaStream_t s) {
@@ -722,6 +770,11 @@ int bpm_step_generations(bpm_handle h, bpm_state* st, int64_t k_gen0, int32_t n_
     return fail("serial DE-MC steps every chain against the frozen population: sharded handles must use the "
                 "split API with an all-gather after the sweep");
   CU_TRY(cudaSetDevice(h->cfg.device));
+  if (n_gen > 0) {
+    int done = 0;
+    BPM_TRY(h->try_small_generations(st, k_gen0, n_gen, (cudaStream_t)stream, &done));
+    if (done) return 0;
+  }
   for (int g = 0; g < n_gen; ++g)
     BPM_TRY(h->generation<false>(st, k_gen0 + g, nullptr, nullptr, (cudaStream_t)stream));
   return 0;
@@ -876,13 +929,13 @@ int bpm_generations_host(bpm_handle h, double* X_host, double* lnl_host, int64_t
     }
   }
   cudaStream_t s = 0;
-  // Opt-in (BIPYMC_B200_HOST_PEER=1, not yet measured -- DESIGN.md section 9): the mapped host population is
+  // Default (BIPYMC_B200_HOST_PEER=0 selects the older changed-rows pass below): the mapped host population is
   // handed to the phase kernels as one more peer replica, so every accepted row is stored to the host from
-  // inside the write-back (overlapped with compute) and no changed-rows pass follows the generation; the
+  // inside the kernels (overlapped with compute) and no changed-rows pass follows the generation; the
   // cached likelihoods (8 N bytes) come back with one plain copy.
   static const bool host_peer_opt = [] {
-    const char* e = getenv("BIPYMC_B200_HOST_PEER");
-    return e && e[0] == '1';
+    const char* e = getenv("BIPYMC_B200_HOST_PEER");     // default on; "0" = the changed-rows pass after the generation
+    return !(e && e[0] == '0');
   }();
   if (X_map && host_peer_opt && h->n_peers < BPM_MAX_PEERS) {
     unsigned long long acc0 = 0, acc1 = 0;

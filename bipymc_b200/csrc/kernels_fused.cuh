@@ -1266,6 +1266,108 @@ inline int launch_fused_v3(const PhaseArgs& a, const GaussArgs& g, int grid, siz
 }
 
 // ---- d <= 4 analytic targets: one thread per chain ------------------------------------
+// One chain-step of a d <= 4 target, start to finish (draws, proposal, likelihood, Metropolis decision,
+// state / moments / history update).  pool_id(r) maps a pool position to a global chain id: a lookup in the
+// materialised shuffle for the per-phase kernel, the Feistel permutation evaluated on the fly for the
+// persistent multi-generation kernel.  Returns 1 when the proposal was accepted.
+template <bool REPLAY, int TARGET, typename PoolFn>
+__device__ __forceinline__ int small_chain_step(const PhaseArgs& a, const TargetView& tv, const double* sdata,
+                                                int c, int n_pool, PoolFn pool_id) {
+  const int d = a.d;
+  const bool dream = a.algo == BPM_ALGO_DREAM;
+  const int npair = dream ? a.del_pairs : 1;
+  ChainDraws D;
+  chain_scalar_draws<REPLAY>(a, c, n_pool, D);
+  uint32_t mbits = 0xFu;
+  double gamma;
+  if (dream) {
+    mbits = 0u;
+    const double cr = __ddiv_rn((double)(D.cr_idx + 1), (double)a.n_cr);
+    double z[4];
+    z4<REPLAY>(a, c, 0, z);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q < d && z[q] <= cr) mbits |= 1u << q;
+    int d_prime = __popc(mbits);
+    if (d_prime == 0) {
+      mbits |= 1u << ((D.fallback < 0 ? 0 : D.fallback) & 3);
+      d_prime = 1;
+    }
+    gamma = dream_gamma(a, d_prime, D.gamma_u);
+  } else {
+    gamma = demc_gamma(a, D.gamma_u);
+  }
+  double* xc = a.X + (size_t)c * a.ld;
+  double cur[4] = {0, 0, 0, 0}, S[4] = {0, 0, 0, 0}, pr[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (q < d) cur[q] = xc[q];
+#pragma unroll
+  for (int p = 0; p < BPM_MAX_PAIRS; ++p)
+    if (p < npair) {
+      const double* pa = a.X + (size_t)pool_id(D.r1[p]) * a.ld;
+      const double* pb = a.X + (size_t)pool_id(D.r2[p]) * a.ld;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < d) {
+          const double df = __dsub_rn(pa[q], pb[q]);
+          S[q] = p == 0 ? df : __dadd_rn(S[q], df);
+        }
+    }
+  double e[4], nn[4];
+  en4<REPLAY>(a, c, 0, e, nn);
+  double delta = 0.0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (q < d) {
+      if (dream) {
+        pr[q] = dream_prop(cur[q], S[q], e[q], nn[q], gamma, (mbits >> q) & 1u ? 1.0 : 0.0);
+        if (a.adapt) delta += cr_term(cur[q], pr[q], cr_variance<REPLAY>(a, c, q));
+      } else {
+        pr[q] = demc_prop(cur[q], S[q], nn[q], gamma);
+      }
+    }
+  if (dream) {
+    a.cr_pick[c] = a.adapt ? D.cr_idx : -1;
+    a.cr_delta[c] = delta;
+  }
+  if (REPLAY && a.tr.prop)
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q < d) a.tr.prop[(size_t)c * d + q] = pr[q];
+  double lp;
+  if (TARGET == BPM_TARGET_BANANA) lp = banana_lnl(tv.banana, pr[0], pr[1]);
+  else if (TARGET == BPM_TARGET_BIMODAL) lp = bimodal_lnl(tv.bimodal, pr[0], pr[1]);
+  else lp = linefit_lnl(sdata, sdata + tv.linefit_M, sdata + 2 * tv.linefit_M, tv.linefit_M, pr[0],
+                        pr[1], pr[2]);
+  int acc = metropolis(a.lnl[c], lp, accept_uniform<REPLAY>(a, c));
+  if (acc < 0) {
+    *a.nan_flag = 1;
+    acc = 0;
+  }
+  const size_t o = (size_t)(c - a.chain_lo) * a.ld;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (q < d) {
+      const double s = acc ? pr[q] : cur[q];
+      if (acc) {
+        xc[q] = s;
+        store_peers1(a, (size_t)c * a.ld + q, s);
+      }
+      if (a.mean) {
+        double mu = a.mean[o + q], v = a.m2[o + q];
+        welford_update(s, a.inv_n1, mu, v);
+        a.mean[o + q] = mu;
+        a.m2[o + q] = v;
+      }
+      if (a.hist_row) a.hist_row[o + q] = s;
+    }
+  if (acc) a.lnl[c] = lp;
+  if (a.tr.accept) a.tr.accept[c] = acc;
+  if (a.tr.lnl_prop) a.tr.lnl_prop[c] = lp;
+  return acc;
+}
+
 template <bool REPLAY, int TARGET>
 __global__ void __launch_bounds__(128) fused_small_kernel(const PhaseArgs a, const TargetView tv) {
   extern __shared__ __align__(16) double sdata[];
@@ -1279,105 +1381,107 @@ __global__ void __launch_bounds__(128) fused_small_kernel(const PhaseArgs a, con
   const int c = valid ? L.self[gid] : 0;
   valid = valid && c >= a.chain_lo && c < a.chain_hi;
   int acc = 0;
-  if (valid) {
-    const int d = a.d;
-    const bool dream = a.algo == BPM_ALGO_DREAM;
-    const int npair = dream ? a.del_pairs : 1;
-    ChainDraws D;
-    chain_scalar_draws<REPLAY>(a, c, L.n_pool, D);
-    uint32_t mbits = 0xFu;
-    double gamma;
-    if (dream) {
-      mbits = 0u;
-      const double cr = __ddiv_rn((double)(D.cr_idx + 1), (double)a.n_cr);
-      double z[4];
-      z4<REPLAY>(a, c, 0, z);
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (q < d && z[q] <= cr) mbits |= 1u << q;
-      int d_prime = __popc(mbits);
-      if (d_prime == 0) {
-        mbits |= 1u << ((D.fallback < 0 ? 0 : D.fallback) & 3);
-        d_prime = 1;
-      }
-      gamma = dream_gamma(a, d_prime, D.gamma_u);
-    } else {
-      gamma = demc_gamma(a, D.gamma_u);
-    }
-    double* xc = a.X + (size_t)c * a.ld;
-    double cur[4] = {0, 0, 0, 0}, S[4] = {0, 0, 0, 0}, pr[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (q < d) cur[q] = xc[q];
-#pragma unroll
-    for (int p = 0; p < BPM_MAX_PAIRS; ++p)
-      if (p < npair) {
-        const double* pa = a.X + (size_t)L.pool[D.r1[p]] * a.ld;
-        const double* pb = a.X + (size_t)L.pool[D.r2[p]] * a.ld;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (q < d) {
-            const double df = __dsub_rn(pa[q], pb[q]);
-            S[q] = p == 0 ? df : __dadd_rn(S[q], df);
-          }
-      }
-    double e[4], nn[4];
-    en4<REPLAY>(a, c, 0, e, nn);
-    double delta = 0.0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (q < d) {
-        if (dream) {
-          pr[q] = dream_prop(cur[q], S[q], e[q], nn[q], gamma, (mbits >> q) & 1u ? 1.0 : 0.0);
-          if (a.adapt) delta += cr_term(cur[q], pr[q], cr_variance<REPLAY>(a, c, q));
-        } else {
-          pr[q] = demc_prop(cur[q], S[q], nn[q], gamma);
-        }
-      }
-    if (dream) {
-      a.cr_pick[c] = a.adapt ? D.cr_idx : -1;
-      a.cr_delta[c] = delta;
-    }
-    if (REPLAY && a.tr.prop)
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (q < d) a.tr.prop[(size_t)c * d + q] = pr[q];
-    double lp;
-    if (TARGET == BPM_TARGET_BANANA) lp = banana_lnl(tv.banana, pr[0], pr[1]);
-    else if (TARGET == BPM_TARGET_BIMODAL) lp = bimodal_lnl(tv.bimodal, pr[0], pr[1]);
-    else lp = linefit_lnl(sdata, sdata + tv.linefit_M, sdata + 2 * tv.linefit_M, tv.linefit_M, pr[0],
-                          pr[1], pr[2]);
-    acc = metropolis(a.lnl[c], lp, accept_uniform<REPLAY>(a, c));
-    if (acc < 0) {
-      *a.nan_flag = 1;
-      acc = 0;
-    }
-    const size_t o = (size_t)(c - a.chain_lo) * a.ld;
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (q < d) {
-        const double s = acc ? pr[q] : cur[q];
-        if (acc) {
-          xc[q] = s;
-          store_peers1(a, (size_t)c * a.ld + q, s);
-        }
-        if (a.mean) {
-          double mu = a.mean[o + q], v = a.m2[o + q];
-          welford_update(s, a.inv_n1, mu, v);
-          a.mean[o + q] = mu;
-          a.m2[o + q] = v;
-        }
-        if (a.hist_row) a.hist_row[o + q] = s;
-      }
-    if (acc) a.lnl[c] = lp;
-    if (a.tr.accept) a.tr.accept[c] = acc;
-    if (a.tr.lnl_prop) a.tr.lnl_prop[c] = lp;
-  }
+  if (valid) acc = small_chain_step<REPLAY, TARGET>(a, tv, sdata, c, L.n_pool, [&](int r) { return L.pool[r]; });
   const unsigned am = __ballot_sync(0xFFFFFFFFu, valid && acc);
   const unsigned rm = __ballot_sync(0xFFFFFFFFu, valid && !acc);
   if ((threadIdx.x & 31) == 0) {
     if (am) atomicAdd(a.n_acc, (unsigned long long)__popc(am));
     if (rm) atomicAdd(a.n_rej, (unsigned long long)__popc(rm));
+  }
+}
+
+// ---- d <= 4: a whole run of generations in ONE persistent cooperative launch -----------------------------
+// A generation of 10^5 three-parameter chains is ~10 us of work; launched as split + list packing + two
+// half-phases + CR reduction it costs 93 us (profiles/r1b_secondary_configs.txt: launch-bound).  Here one
+// cooperative grid keeps every generation of a bpm_step_generations call on the device (demc.py:79-135,
+// the whole while-loop):
+//   * no shuffle is materialised: a chain finds its half from the INVERSE Feistel permutation of its own id
+//     and its partners from the forward permutation of the pool positions it drew;
+//   * thread <-> chain is fixed (chain order: 16-byte rows share sectors, moments / history stream);
+//   * three grid-wide barriers per generation: after phase a (its updates are phase b's partner states),
+//     after phase b, after the CR reduction (block partials in the per-phase kernels' own order -- bit-identical
+//     p_cr -- then block 0 applies dream.py:132-140).
+// Native RNG, unsharded handles; draws are addressed by chain id, so the chains are those of the per-phase path.
+struct SmallGens {
+  int64_t k_gen0;
+  int32_t n_gen, burnin_gen, n_cr_gen, jump_mod, shuffle;
+  double flip_p;
+  uint64_t seed;
+  double* hist0;           // row 0 of the flat history (or nullptr)
+  double* omega_sum;       // per-chain running sum of ln_like (outlier tracking) or nullptr
+  double* cr_block;        // [<= kCrBlocks][2 BPM_MAX_CR]
+  double* cr_part;
+  double* cr_dm;
+  double* cr_cnt;
+  double* p_cr;
+  int32_t cr_blocks;
+};
+
+}  // namespace bpm
+#include <cooperative_groups.h>
+namespace bpm {
+
+template <int TARGET>
+__global__ void __launch_bounds__(256, 2) small_generations_kernel(const PhaseArgs a0, const TargetView tv, const SmallGens q) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) double sdata[];
+  __shared__ FeistelKey fkey;
+  __shared__ int flip_s;
+  if (TARGET == BPM_TARGET_LINEFIT) {
+    for (int i = threadIdx.x; i < 3 * tv.linefit_M; i += blockDim.x) sdata[i] = tv.linefit[i];
+  }
+  PhaseArgs a = a0;
+  const int N = a.N, nA = a.nA;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  const size_t hstride = (size_t)N * a.ld;
+  unsigned n_acc = 0, n_rej = 0;
+  for (int g = 0; g < q.n_gen; ++g) {
+    const int64_t k_gen = q.k_gen0 + g, hist_len = a0.hist_len + g, mom_len = a0.mom_len + g;
+    a.gamma_jump = (k_gen % q.jump_mod) == 0;                       // dream.py:77 / demc.py:174
+    a.adapt = a.algo == BPM_ALGO_DREAM && q.burnin_gen > k_gen && hist_len > q.n_cr_gen && a.m2 != nullptr;
+    a.hist_len = hist_len; a.mom_len = mom_len;
+    a.inv_mom = 1.0 / (double)mom_len;
+    a.inv_n1 = 1.0 / (double)(mom_len + 1);
+    a.rng = make_rng(q.seed, (uint64_t)hist_len);
+    a.hist_row = q.hist0 ? q.hist0 + (size_t)hist_len * hstride : nullptr;
+    if (threadIdx.x == 0) {                                          // demc.py:81-86, keyed by (seed, generation) only
+      const Philox4 f = draw4(a.rng, 0xFFFFFFFFu, RNG_GEN, 0);
+      const double thr = __ddiv_rn(q.flip_p, __dadd_rn(q.flip_p, __dsub_rn(1.0, q.flip_p)));
+      flip_s = u53(f.x, f.y) < thr ? 1 : 0;
+      if (q.shuffle) fkey = make_feistel(a.rng, (uint32_t)N);
+    }
+    __syncthreads();
+    const int flip = flip_s;
+    for (int ph = 0; ph < 2; ++ph) {
+      const bool self_first = (ph ^ flip) == 0;                      // this phase updates perm[0 : nA)
+      const int n_pool = self_first ? N - nA : nA, off = self_first ? nA : 0;
+      for (int c = gtid; c < N; c += nthreads) {
+        const int pos = q.shuffle ? (int)feistel_inv(fkey, (uint32_t)c) : c;
+        if ((pos < nA) != self_first) continue;
+        const int acc = small_chain_step<false, TARGET>(a, tv, sdata, c, n_pool, [&](int r) {
+          return q.shuffle ? (int)feistel_perm(fkey, (uint32_t)(off + r)) : off + r;
+        });
+        n_acc += acc; n_rej += 1 - acc;
+      }
+      grid.sync();
+    }
+    if (q.omega_sum)
+      for (int c = gtid; c < N; c += nthreads) q.omega_sum[c] += a.lnl[c];
+    if (a.algo == BPM_ALGO_DREAM) {
+      if ((int)blockIdx.x < q.cr_blocks)
+        cr_block_partials(a.cr_delta, a.cr_pick, 0, N, a.n_cr, (int)blockIdx.x, q.cr_blocks, q.cr_block);
+      grid.sync();
+      if (blockIdx.x == 0) cr_finish(q.cr_block, q.cr_blocks, a.n_cr, q.cr_part, 1, q.cr_dm, q.cr_cnt, q.p_cr);
+      grid.sync();                                                   // the next generation draws CR from the new p_cr
+    }
+  }
+  // accept / reject tallies: one atomic pair per warp
+  n_acc = __reduce_add_sync(0xFFFFFFFFu, n_acc);
+  n_rej = __reduce_add_sync(0xFFFFFFFFu, n_rej);
+  if ((threadIdx.x & 31) == 0) {
+    if (n_acc) atomicAdd(a.n_acc, (unsigned long long)n_acc);
+    if (n_rej) atomicAdd(a.n_rej, (unsigned long long)n_rej);
   }
 }
 

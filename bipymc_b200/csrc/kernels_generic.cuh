@@ -437,18 +437,14 @@ __device__ __forceinline__ void cr_apply(const double* __restrict__ part, int n_
   for (int m = 0; m < n_cr; ++m) p_cr[m] /= tot;
 }
 
-__global__ void __launch_bounds__(256) cr_update_kernel(const double* __restrict__ cr_delta,
-                                                        const int32_t* __restrict__ cr_pick, int lo, int hi,
-                                                        int n_cr, double* __restrict__ block_part,
-                                                        unsigned int* __restrict__ ticket,
-                                                        double* __restrict__ part, int apply,
-                                                        double* __restrict__ dm, double* __restrict__ cnt,
-                                                        double* __restrict__ p_cr) {
+// first half: block `bid` of `nb` sums the chains of its contiguous segment (256 threads)
+__device__ __forceinline__ void cr_block_partials(const double* __restrict__ cr_delta,
+                                                  const int32_t* __restrict__ cr_pick, int lo, int hi, int n_cr,
+                                                  int bid, int nb, double* __restrict__ block_part) {
   __shared__ double sm[8][2 * 4];
-  __shared__ bool last;
   const int n = hi - lo;
-  const int per = (n + gridDim.x - 1) / gridDim.x;
-  const int c0 = lo + blockIdx.x * per;
+  const int per = (n + nb - 1) / nb;
+  const int c0 = lo + bid * per;
   const int c1 = min(hi, c0 + per);
   if (n_cr <= 4) {
     // one pass over the block's chains, the (at most four) CR classes in registers
@@ -487,8 +483,9 @@ __global__ void __launch_bounds__(256) cr_update_kernel(const double* __restrict
       const int q = threadIdx.x & 3, pass = threadIdx.x >> 2;
       double w = 0.0;
       for (int i = 0; i < 8; ++i) w += sm[i][threadIdx.x];
-      if (q < n_cr) block_part[(size_t)blockIdx.x * 2 * BPM_MAX_CR + pass * n_cr + q] = w;
+      if (q < n_cr) block_part[(size_t)bid * 2 * BPM_MAX_CR + pass * n_cr + q] = w;
     }
+    __syncthreads();
   } else {
     for (int m = 0; m < n_cr; ++m) {
       double s = 0.0, k = 0.0;
@@ -503,12 +500,47 @@ __global__ void __launch_bounds__(256) cr_update_kernel(const double* __restrict
         if (threadIdx.x == 0) {
           double w = 0.0;
           for (int i = 0; i < 8; ++i) w += sm[i][0];
-          block_part[(size_t)blockIdx.x * 2 * BPM_MAX_CR + pass * n_cr + m] = w;
+          block_part[(size_t)bid * 2 * BPM_MAX_CR + pass * n_cr + m] = w;
         }
         __syncthreads();
       }
     }
   }
+}
+// second half, one block: all block partials land in shared memory with independent loads, then each of
+// the 2 n_cr outputs is added up in block order
+__device__ __forceinline__ void cr_finish(const double* __restrict__ block_part, int nb, int n_cr,
+                                          double* __restrict__ part, int apply, double* __restrict__ dm,
+                                          double* __restrict__ cnt, double* __restrict__ p_cr) {
+  __shared__ double stage[kCrBlocks * 2 * BPM_MAX_CR / 4];    // nb <= 148 blocks x 2 n_cr <= 8 values (n_cr <= 4) or fewer blocks
+  const int nv = 2 * n_cr;
+  const int fit = (int)(sizeof(stage) / sizeof(double)) / nv;      // blocks that fit in the stage
+  double w = 0.0;
+  for (int b0 = 0; b0 < nb; b0 += fit) {
+    const int nb_here = min(nb - b0, fit);
+    for (int idx = threadIdx.x; idx < nb_here * nv; idx += blockDim.x) {
+      const int b = idx / nv, i = idx - b * nv;
+      stage[idx] = __ldcg(&block_part[(size_t)(b0 + b) * 2 * BPM_MAX_CR + i]);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nv)
+      for (int b = 0; b < nb_here; ++b) w += stage[b * nv + threadIdx.x];
+    __syncthreads();
+  }
+  if ((int)threadIdx.x < nv) part[threadIdx.x] = w;
+  __syncthreads();
+  if (threadIdx.x == 0 && apply) cr_apply(part, n_cr, dm, cnt, p_cr);
+}
+
+__global__ void __launch_bounds__(256) cr_update_kernel(const double* __restrict__ cr_delta,
+                                                        const int32_t* __restrict__ cr_pick, int lo, int hi,
+                                                        int n_cr, double* __restrict__ block_part,
+                                                        unsigned int* __restrict__ ticket,
+                                                        double* __restrict__ part, int apply,
+                                                        double* __restrict__ dm, double* __restrict__ cnt,
+                                                        double* __restrict__ p_cr) {
+  __shared__ bool last;
+  cr_block_partials(cr_delta, cr_pick, lo, hi, n_cr, (int)blockIdx.x, (int)gridDim.x, block_part);
   __threadfence();        // every writer publishes its block partials before the ticket is taken
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -518,29 +550,8 @@ __global__ void __launch_bounds__(256) cr_update_kernel(const double* __restrict
   __syncthreads();
   if (!last) return;
   __threadfence();
-  // all block partials land in shared memory with independent loads, then each of the 2 n_cr
-  // outputs is added up in block order
-  __shared__ double stage[kCrBlocks * 2 * BPM_MAX_CR / 4];    // gridDim.x <= 148 blocks x 2 n_cr <= 8 values (n_cr <= 4) or fewer blocks
-  const int nv = 2 * n_cr;
-  const int fit = (int)(sizeof(stage) / sizeof(double)) / nv;      // blocks that fit in the stage
-  double w = 0.0;
-  for (unsigned b0 = 0; b0 < gridDim.x; b0 += fit) {
-    const int nb_here = min((int)(gridDim.x - b0), fit);
-    for (int idx = threadIdx.x; idx < nb_here * nv; idx += blockDim.x) {
-      const int b = idx / nv, i = idx - b * nv;
-      stage[idx] = __ldcg(&block_part[(size_t)(b0 + b) * 2 * BPM_MAX_CR + i]);
-    }
-    __syncthreads();
-    if (threadIdx.x < nv)
-      for (int b = 0; b < nb_here; ++b) w += stage[b * nv + threadIdx.x];
-    __syncthreads();
-  }
-  if (threadIdx.x < nv) part[threadIdx.x] = w;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    *ticket = 0u;                        // ready for the next generation
-    if (apply) cr_apply(part, n_cr, dm, cnt, p_cr);
-  }
+  if (threadIdx.x == 0) *ticket = 0u;      // ready for the next generation
+  cr_finish(block_part, (int)gridDim.x, n_cr, part, apply, dm, cnt, p_cr);
 }
 
 __global__ void cr_apply_kernel(const double* __restrict__ part, int n_cr, double* __restrict__ dm,

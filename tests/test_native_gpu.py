@@ -440,7 +440,7 @@ def test_host_buffer_entry_equals_device_resident_generations(pinned, adapt):
     if pinned:
         Xh, Lh = Xh.pin_memory(), Lh.pin_memory()
     Xh.copy_(b._X.cpu()); Lh.copy_(b._lnl.cpu())
-    host_peer = pinned and os.environ.get("BIPYMC_B200_HOST_PEER", "") == "1"
+    host_peer = pinned and os.environ.get("BIPYMC_B200_HOST_PEER", "1") != "0"
     moved = 0
     for g in range(G):
         before = Xh.clone()

@@ -54,3 +54,42 @@ def test_replay_extra_golden_cases(name, fused):
     half-phase of the fused kernel (the other 100-D goldens hold 8-12 chains)."""
     from test_replay_parity_gpu import replay_and_check
     replay_and_check(name, fused)
+
+
+# ---- d <= 4: the persistent cooperative multi-generation kernel against the per-phase launches ------------
+@pytest.mark.parametrize("target,n_chains,algo", [("banana", 1000, "dream"), ("dblgauss", 4099, "dream"),
+                                                   ("linefit", 2500, "dream"), ("banana", 777, "demc")])
+def test_small_d_persistent_kernel_equals_per_phase_path(target, n_chains, algo):
+    """fused=1 runs every generation of a run_mcmc call in ONE cooperative launch (Feistel shuffle evaluated on
+    the fly, grid-wide barriers between half-phases); fused=0 launches split / propose / likelihood / accept /
+    CR reduction per generation.  Same seed: identical histories, cached likelihoods, counters, running
+    moments and -- the CR block partials are summed in the same order -- bit-identical p_cr."""
+    import ctypes as C
+    import torch
+    from bipymc_b200 import DreamMpi, DeMcMpi, targets, _lib
+    tgt = {"banana": targets.Banana_2D, "dblgauss": targets.BimodeGauss_2D, "linefit": targets.LineFit}[target]()
+    th0 = [-0.8, 4.5, 0.2] if target == "linefit" else [0.0, 0.0]
+    G = 37
+    runs = []
+    for fused in (1, 0):
+        np.random.seed(21)
+        if algo == "dream":
+            s = DreamMpi(tgt.ln_like, th0, n_chains=n_chains, seed=9, varepsilon=1e-2 if target == "linefit" else 0.3,
+                         n_cr_gen=3, burnin_gen=30, fused=fused)
+        else:
+            s = DeMcMpi(tgt.ln_like, th0, n_chains=n_chains, seed=9, varepsilon=0.3, fused=fused)
+        _lib.check(s._libh.bpm_profile(s._handle, 1))
+        s.run_mcmc(n_chains * (G + 1), flip=0.3)
+        ms, n = (C.c_double * 8)(), (C.c_int64 * 8)()
+        _lib.check(s._libh.bpm_profile_read(s._handle, ms, n))
+        runs.append((s, [int(v) for v in n]))
+    (a, ka), (b, kb) = runs
+    assert ka[4] == 1 and ka[1] == 0 and ka[0] == 0, ka          # one launch for the whole run
+    assert kb[4] == 0 and kb[1] == 2 * G, kb
+    assert torch.equal(a._hist.tensor(), b._hist.tensor())
+    assert torch.equal(a._lnl, b._lnl) and torch.equal(a._X, b._X)
+    assert torch.equal(a._mean, b._mean) and torch.equal(a._m2, b._m2)
+    assert (a.n_accepted, a.n_rejected) == (b.n_accepted, b.n_rejected)
+    if algo == "dream":
+        assert np.array_equal(a.p_cr, b.p_cr) and np.array_equal(a.delta_m, b.delta_m)
+        assert np.array_equal(a.n_cr_updates, b.n_cr_updates) and a.n_cr_updates.sum() > 0

@@ -185,7 +185,56 @@ def c5full():
     dist.destroy_process_group()
 
 
+def c4multi():
+    """BASELINE configs[3] (launch under torchrun, 1 / 2 / 4 ranks): DREAM on the examples/ex_para_fit.py line
+    fit (3 parameters, 50 data points, likelihood evaluated in-kernel), 10^5 chains in TOTAL sharded over the
+    GPUs (the config as stated: strong scaling) and 10^5 chains PER GPU (weak scaling).  One rank: every
+    generation of the call runs inside one persistent cooperative kernel; several ranks: per-phase kernels with
+    accepted rows stored into the peer replicas and the peer-memory barrier / CR exchange between them."""
+    import torch.distributed as dist
+    from bipymc_b200 import DreamMpi, targets
+    rank, local = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    t = targets.LineFit()
+    gens, warm = 200, 20
+    for label, N in (("1e5 chains in total", 100000 // world * world), ("1e5 chains per GPU", 100000 * world)):
+        np.random.seed(1)
+        s = DreamMpi(t.ln_like, [-0.8, 4.5, 0.2], n_chains=N, seed=3, varepsilon=1e-2, history="none",
+                     burnin_gen=10 ** 6, n_cr_gen=10, device=local)
+        s.run_mcmc(N * (warm + 1))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        s.run_mcmc(N * (gens + 1), _k_gen0=warm)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(json.dumps({"config": "C4 linefit DREAM, %d GPU(s), %s" % (world, label), "n_gpus": world,
+                              "n_chains": N, "chain_steps_per_s": N * gens / (float(ms.item()) * 1e-3),
+                              "us_per_generation": 1e3 * float(ms.item()) / gens,
+                              "acceptance_fraction": s.acceptance_fraction,
+                              "path": "persistent cooperative kernel" if world == 1 else
+                                      "per-phase kernels + peer-memory barrier (%s)" % ("on" if s._sync_on else "off")}),
+                  flush=True)
+        s.close()
+        if world > 1:
+            dist.barrier()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["c4multi"]:
+        c4multi()
+        sys.exit(0)
     if sys.argv[1:] == ["c5full"]:
         c5full()
         sys.exit(0)
