@@ -245,6 +245,13 @@ struct bpm_engine {
     a.prop = prop; a.lnl_prop = lnl_prop;
     for (int p = 0; p < n_peers; ++p) a.peers[p] = peers[p];
     a.n_peers = n_peers;
+    // MEASUREMENT ONLY (BIPYMC_B200_NO_PEER_STORES=1): drop the in-kernel peer stores of a sharded run to
+    // separate their cost from that of the larger replicated population; the replicas then diverge.
+    static const bool no_peer_stores = [] {
+      const char* e = getenv("BIPYMC_B200_NO_PEER_STORES");
+      return e && e[0] == '1';
+    }();
+    if (no_peer_stores) a.n_peers = 0;
     a.n_acc = counters; a.n_rej = counters + 1; a.nan_flag = nan_flag;
     a.rng = bpm::make_rng(cfg.seed, (uint64_t)st->hist_len);
     if (rp) a.rp = *rp;
@@ -514,6 +521,9 @@ struct bpm_engine {
       coop_blocks = coop ? sms * (per_sm < 4 ? per_sm : 4) : -1;
     }
     if (coop_blocks <= 0) return 0;
+    // one resident thread per chain or not at all: a thread that has to walk several chains serialises their
+    // (latency-bound) likelihoods, and the per-phase launches win (measured: 10^6 bimodal chains 370 vs 197 us)
+    if ((int64_t)cfg.n_chains > (int64_t)coop_blocks * 256) return 0;
     bpm::PhaseArgs a = make_args(st, k_gen0, 0, nullptr, nullptr);
     a.loc_list = nullptr; a.loc_cnt = nullptr;        // chains are walked in order; no packed lists
     bpm::SmallGens q;

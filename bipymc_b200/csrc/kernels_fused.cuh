@@ -1397,7 +1397,11 @@ __global__ void __launch_bounds__(128) fused_small_kernel(const PhaseArgs a, con
 // the whole while-loop):
 //   * no shuffle is materialised: a chain finds its half from the INVERSE Feistel permutation of its own id
 //     and its partners from the forward permutation of the pool positions it drew;
-//   * thread <-> chain is fixed (chain order: 16-byte rows share sectors, moments / history stream);
+//   * thread <-> chain is fixed, ONE chain per thread (chain order: 16-byte rows share sectors, moments /
+//     history stream).  A chain-step is a long dependent instruction sequence (the 50-point line-fit
+//     likelihood is ~25 us of latency), so the kernel only pays while every chain has its own resident thread:
+//     the engine uses it up to 148 x 3 x 256 chains and keeps the per-phase launches (which are throughput-bound
+//     there: C3, 10^6 chains) beyond;
 //   * three grid-wide barriers per generation: after phase a (its updates are phase b's partner states),
 //     after phase b, after the CR reduction (block partials in the per-phase kernels' own order -- bit-identical
 //     p_cr -- then block 0 applies dream.py:132-140).
@@ -1422,7 +1426,7 @@ struct SmallGens {
 namespace bpm {
 
 template <int TARGET>
-__global__ void __launch_bounds__(256, 2) small_generations_kernel(const PhaseArgs a0, const TargetView tv, const SmallGens q) {
+__global__ void __launch_bounds__(256, 3) small_generations_kernel(const PhaseArgs a0, const TargetView tv, const SmallGens q) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) double sdata[];

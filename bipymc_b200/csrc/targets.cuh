@@ -66,6 +66,9 @@ __device__ __forceinline__ double linefit_lnl(const double* x, const double* y, 
   if (!(-5.0 < m && m < 0.5 && 0.0 < b && b < 10.0 && -10.0 < lnf && lnf < 1.0)) return -INFINITY;
   const double e2 = exp(__dmul_rn(2.0, lnf));
   double s = 0.0;
+  // the M terms are independent up to the (ordered) accumulation: unrolled so that five divisions / logarithms
+  // are in flight per thread -- the sequential form is ~25 us of pure latency per chain at M = 50
+#pragma unroll 5
   for (int i = 0; i < M; ++i) {
     double model = __dadd_rn(__dmul_rn(m, x[i]), b);
     double inv = __ddiv_rn(1.0, __dadd_rn(__dmul_rn(yerr[i], yerr[i]),

@@ -67,6 +67,37 @@ def main():
             print("case", name, exchange, "->", s._exchange, "ok", flush=True)
         dist.barrier()
         del s
+    # ---- sharded end-to-end entry (bpm_generations_host_sharded): host shards in / out every generation ==
+    #      the device-resident sharded run of the same seed (adaptation on: moments live in the sampler state)
+    import ctypes as C
+    from bipymc_b200 import _lib
+    N, d, G = 2048 * world, 100, 6
+    tgt = targets.Gauss_100D()
+    kw = dict(n_chains=N, seed=5, varepsilon=1.0, device=local, history="none", burnin_gen=1000, n_cr_gen=2)
+    np.random.seed(3)
+    ref = DreamMpi(tgt.ln_like, np.zeros(d), **kw)
+    ref.run_mcmc(N * (G + 1))
+    np.random.seed(3)
+    s = DreamMpi(tgt.ln_like, np.zeros(d), **kw)
+    assert s._sync_on, "peer-memory barrier not available"
+    s.run_mcmc(N)                                   # run parameters + initial likelihoods, no generation
+    lo, hi = int(s.rank_chain_ids[0]), int(s.rank_chain_ids[-1]) + 1
+    Xh = torch.empty((hi - lo, s._ld), dtype=torch.float64).pin_memory()
+    Lh = torch.empty((hi - lo,), dtype=torch.float64).pin_memory()
+    Xh.copy_(s._X[lo:hi]); Lh.copy_(s._lnl[lo:hi])
+    st = s._state(None)
+    for g in range(G):
+        _lib.check(s._libh.bpm_generations_host_sharded(s._handle, C.byref(st), Xh.data_ptr(), Lh.data_ptr(), g, 1,
+                                                        s._stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(Xh, ref._X[lo:hi].cpu()), "host shard differs from the device-resident sharded run"
+    assert torch.equal(Lh, ref._lnl[lo:hi].cpu())
+    assert torch.equal(s._X, ref._X), "replicas (all shards) differ"
+    assert np.array_equal(s.p_cr, ref.p_cr)
+    dist.barrier()
+    if rank == 0:
+        print("case host-sharded entry ok", flush=True)
+    s.close(); ref.close()
     # ---- sub-population (island) mode: no replica, chains re-dealt every k generations
     N, k = 1024 * world, 5
     np.random.seed(3)
