@@ -76,6 +76,8 @@ struct bpm_engine {
   double* cr_part = nullptr;
   double* cr_block = nullptr;
   unsigned int* cr_ticket = nullptr;
+  double* cr_fold_part = nullptr;          // [2][148][2 BPM_MAX_CR] per-CTA CR partials of the fused v4 launches
+  unsigned int* cr_fold_ticket = nullptr;
   unsigned long long* counters = nullptr;  // [0] accepted, [1] rejected
   int32_t* nan_flag = nullptr;
   // target
@@ -152,6 +154,7 @@ struct bpm_engine {
 
   ~bpm_engine() {
     cudaFree(inv); cudaFree(loc_list); cudaFree(loc_cnt); cudaFree(phase_cnt); cudaFree(cmp_blk); cudaFree(cr_ticket);
+    cudaFree(cr_fold_part); cudaFree(cr_fold_ticket);
     cudaFree(perm); cudaFree(flip); cudaFree(prop); cudaFree(lnl_prop); cudaFree(cr_delta);
     cudaFree(cr_pick); cudaFree(p_cr); cudaFree(cr_dm); cudaFree(cr_cnt); cudaFree(cr_part); cudaFree(cr_block);
     cudaFree(counters); cudaFree(nan_flag); cudaFree(tparams); cudaFree(hX); cudaFree(hL); cudaFree(hMean); cudaFree(hM2);
@@ -187,6 +190,10 @@ struct bpm_engine {
     CU_TRY(cudaMalloc(&cr_block, sizeof(double) * 2 * BPM_MAX_CR * bpm::kCrBlocks));
     CU_TRY(cudaMalloc(&cr_ticket, sizeof(unsigned int)));
     CU_TRY(cudaMemset(cr_ticket, 0, sizeof(unsigned int)));
+    CU_TRY(cudaMalloc(&cr_fold_part, sizeof(double) * 2 * 148 * 2 * BPM_MAX_CR));
+    CU_TRY(cudaMemset(cr_fold_part, 0, sizeof(double) * 2 * 148 * 2 * BPM_MAX_CR));
+    CU_TRY(cudaMalloc(&cr_fold_ticket, sizeof(unsigned int)));
+    CU_TRY(cudaMemset(cr_fold_ticket, 0, sizeof(unsigned int)));
     CU_TRY(cudaMalloc(&counters, sizeof(unsigned long long) * 2));
     CU_TRY(cudaMalloc(&nan_flag, sizeof(int32_t)));
     CU_TRY(cudaMemset(flip, 0, sizeof(int32_t)));
@@ -204,7 +211,7 @@ struct bpm_engine {
 
   // Parameter block of one half-phase of generation k_gen.
   bpm::PhaseArgs make_args(const bpm_state* st, int64_t k_gen, int phase, const bpm_replay* rp,
-                           const bpm_trace_out* tr, bool lazy = false) const {
+                           const bpm_trace_out* tr, bool lazy = false, bool fly = false) const {
     bpm::PhaseArgs a;
     memset(&a, 0, sizeof(a));
     a.X = st->X; a.lnl = st->lnl; a.mean = st->mean; a.m2 = st->m2;
@@ -254,6 +261,12 @@ struct bpm_engine {
     if (no_peer_stores) a.n_peers = 0;
     a.n_acc = counters; a.n_rej = counters + 1; a.nan_flag = nan_flag;
     a.rng = bpm::make_rng(cfg.seed, (uint64_t)st->hist_len);
+    if (fly && !rp && !serial()) fill_fly(a);
+    if (lazy && cr_fold_plan()) {
+      a.cr_fold_part = cr_fold_part; a.cr_fold_ticket = cr_fold_ticket; a.cr_fold_out = cr_part;
+      a.cr_fold_dm = cr_dm; a.cr_fold_cnt = cr_cnt; a.cr_fold_pcr = p_cr;
+      a.cr_fold_apply = sharded() ? 0 : 1;
+    }
     if (rp) a.rp = *rp;
     if (tr) a.tr = *tr;
     return a;
@@ -280,6 +293,18 @@ struct bpm_engine {
   bool lazy_plan() const {
     return fused_ok && !serial() && bpm::fused_plan_is_v3(target, cfg.dim, cfg.ld, gauss_r, fused_ok);
   }
+  // DREAM on the v4 kernel: the CR statistics are reduced in the kernels' tails, no cr_update launch
+  bool cr_fold_plan() const {
+    return cfg.algo == BPM_ALGO_DREAM && lazy_plan() && fused_ok != 5 &&
+           bpm::fused_v4_fits(cfg.dim, cfg.ld, gauss_r, cfg.del_pairs);
+  }
+  // Native-RNG generations that never materialise the shuffle ("fly" mode, step.cuh): the lazy-protocol Gaussian
+  // kernels (sharded or not) and the d <= 4 fused kernel on a handle that owns every chain.
+  bool fly_plan() const {
+    if (lazy_plan()) return true;
+    return fused_ok == 1 && !serial() && !sharded() && cfg.dim <= 4 &&
+           (target == BPM_TARGET_BANANA || target == BPM_TARGET_BIMODAL || target == BPM_TARGET_LINEFIT);
+  }
   // bpm_flush: history row hist_len - 1 and its moment sample, left pending by a lazy generation
   int flush(bpm_state* st, cudaStream_t s) {
     if (!st->pending) return 0;
@@ -296,8 +321,40 @@ struct bpm_engine {
     return 0;
   }
 
-  int begin(const bpm_state* st, const bpm_replay* rp, cudaStream_t s) {
+  // fly mode: the generation's flip and permutation key, evaluated on the host (demc.py:81-86; the same
+  // Philox calls and the same IEEE arithmetic split_native_kernel makes on the device)
+  void fill_fly(bpm::PhaseArgs& a) const {
+    a.fly = 1;
+    const bpm::Philox4 q = bpm::draw4(a.rng, 0xFFFFFFFFu, bpm::RNG_GEN, 0);
+    const double thr = cfg.flip / (cfg.flip + (1.0 - cfg.flip));
+    a.flip_val = bpm::u53(q.x, q.y) < thr ? 1 : 0;
+    a.fly_shuffle = cfg.shuffle ? 1 : 0;
+    if (cfg.shuffle) a.fk = bpm::make_feistel(a.rng, (uint32_t)cfg.n_chains);
+  }
+
+  int begin(const bpm_state* st, const bpm_replay* rp, cudaStream_t s, bool fly = false) {
     const int N = cfg.n_chains;
+    if (fly && !rp && !serial()) {
+      // nothing to materialise; sharded ranks still pack their local chains of both halves, reading list
+      // positions from the inverse permutation evaluated on the fly (O(n_local), not O(N))
+      if (sharded()) {
+        prof_begin(0, s);
+        bpm::PhaseArgs t;
+        memset(&t, 0, sizeof(t));
+        t.rng = bpm::make_rng(cfg.seed, (uint64_t)st->hist_len);
+        fill_fly(t);
+        bpm::ListPos pos;
+        pos.inv = nullptr; pos.fly = 1; pos.shuffle = t.fly_shuffle; pos.fk = t.fk;
+        const int nblk = cdiv(cfg.chain_hi - cfg.chain_lo, bpm::kCompactBlock);
+        bpm::compact_count_kernel<<<nblk, bpm::kCompactThreads, 0, s>>>(pos, nA, cfg.chain_lo, cfg.chain_hi, cmp_blk);
+        bpm::compact_scan_kernel<<<1, 1024, 0, s>>>(cmp_blk, nblk, cmp_blk + 2 * nblk, loc_cnt);
+        bpm::compact_write_kernel<<<nblk, bpm::kCompactThreads, 0, s>>>(pos, nA, cfg.chain_lo, cfg.chain_hi,
+                                                                       cmp_blk + 2 * nblk, loc_list);
+        prof_end(s);
+        CU_TRY(cudaGetLastError());
+      }
+      return 0;
+    }
     prof_begin(0, s);
     if (serial()) {
       bpm::identity_split_kernel<<<cdiv(N, 256), 256, 0, s>>>(perm, inv, flip, N);
@@ -311,9 +368,12 @@ struct bpm_engine {
     }
     if (packed()) {
       const int nblk = cdiv(cfg.chain_hi - cfg.chain_lo, bpm::kCompactBlock);
-      bpm::compact_count_kernel<<<nblk, bpm::kCompactThreads, 0, s>>>(inv, nA, cfg.chain_lo, cfg.chain_hi, cmp_blk);
+      bpm::ListPos pos;
+      memset(&pos, 0, sizeof(pos));
+      pos.inv = inv;
+      bpm::compact_count_kernel<<<nblk, bpm::kCompactThreads, 0, s>>>(pos, nA, cfg.chain_lo, cfg.chain_hi, cmp_blk);
       bpm::compact_scan_kernel<<<1, 1024, 0, s>>>(cmp_blk, nblk, cmp_blk + 2 * nblk, loc_cnt);
-      bpm::compact_write_kernel<<<nblk, bpm::kCompactThreads, 0, s>>>(inv, nA, cfg.chain_lo, cfg.chain_hi,
+      bpm::compact_write_kernel<<<nblk, bpm::kCompactThreads, 0, s>>>(pos, nA, cfg.chain_lo, cfg.chain_hi,
                                                                      cmp_blk + 2 * nblk, loc_list);
     }
     prof_end(s);
@@ -416,8 +476,8 @@ struct bpm_engine {
     return 0;
   }
 
-  int end(cudaStream_t s) {
-    if (cfg.algo != BPM_ALGO_DREAM) return 0;
+  int end(cudaStream_t s, bool folded = false) {
+    if (cfg.algo != BPM_ALGO_DREAM || folded) return 0;
     prof_begin(5, s);
     const int nloc = cfg.chain_hi - cfg.chain_lo;
     int nb = cdiv(nloc, 2048);
@@ -450,8 +510,9 @@ struct bpm_engine {
 
   template <bool REPLAY>
   int phase(const bpm_state* st, int64_t k_gen, int ph, const bpm_replay* rp, const bpm_trace_out* tr,
-            cudaStream_t s, bool lazy) {
-    bpm::PhaseArgs a = make_args(st, k_gen, ph, rp, tr, lazy);
+            cudaStream_t s, bool lazy, bool fly) {
+    bpm::PhaseArgs a = make_args(st, k_gen, ph, rp, tr, lazy, fly);
+    if (a.fly && !sharded()) { a.loc_list = nullptr; a.loc_cnt = nullptr; }   // nothing was packed
     if (fused_ok && !serial()) {
       int done = 0;
       prof_begin(4, s);
@@ -460,7 +521,7 @@ struct bpm_engine {
       if (done) { prof_end(s); return 0; }
       if (prof_on) { ev_pool.push_back(recs.back().a); ev_pool.push_back(recs.back().b); recs.pop_back(); }
     }
-    if (lazy) return fail("internal: lazy protocol planned but the fused kernel did not launch");
+    if (lazy || a.fly) return fail("internal: lazy / fly mode planned but the fused kernel did not launch");
     prof_begin(1, s);
     BPM_TRY(launch_propose<REPLAY>(a, s));
     prof_end(s);
@@ -506,7 +567,7 @@ struct bpm_engine {
   int coop_blocks = 0;           // co-resident 256-thread blocks of small_generations_kernel (0 = not asked yet)
   int try_small_generations(bpm_state* st, int64_t k_gen0, int n_gen, cudaStream_t s, int* done) {
     *done = 0;
-    if (fused_ok != 1 || serial() || sharded() || cfg.dim > 4 || cov_on || n_peers > 0) return 0;
+    if (fused_ok != 6 || serial() || sharded() || cfg.dim > 4 || cov_on || n_peers > 0) return 0;   // experimental
     if (!(target == BPM_TARGET_BANANA || target == BPM_TARGET_BIMODAL || target == BPM_TARGET_LINEFIT)) return 0;
     if (st->pending) BPM_TRY(flush(st, s));
     const size_t sm = target == BPM_TARGET_LINEFIT ? sizeof(double) * 3 * linefit_M : 0;
@@ -559,14 +620,15 @@ struct bpm_engine {
     // pending; every other path (and a replay step, whose exact np.std walks the stored history) needs
     // the row materialised first
     const bool lazy = lazy_plan();
+    const bool fly = !REPLAY && fly_plan();
     if (st->pending && (!lazy || REPLAY)) BPM_TRY(flush(st, s));
-    BPM_TRY(begin(st, rp, s));
-    BPM_TRY(phase<REPLAY>(st, k_gen, 0, rp, tr, s, lazy));
+    BPM_TRY(begin(st, rp, s, fly));
+    BPM_TRY(phase<REPLAY>(st, k_gen, 0, rp, tr, s, lazy, fly));
     if (!serial()) {
       if (sync_on) BPM_TRY(peer_barrier(s));          // every rank's phase-a rows are in every replica
-      BPM_TRY(phase<REPLAY>(st, k_gen, 1, rp, tr, s, lazy));
+      BPM_TRY(phase<REPLAY>(st, k_gen, 1, rp, tr, s, lazy, fly));
     }
-    BPM_TRY(end(s));
+    BPM_TRY(end(s, lazy && cr_fold_plan()));
     if (sync_on) {
       if (cfg.algo == BPM_ALGO_DREAM) BPM_TRY(peer_cr_exchange(s));
       else BPM_TRY(peer_barrier(s));
@@ -825,7 +887,7 @@ int bpm_begin_generation(bpm_handle h, bpm_state* st, int64_t k_gen, const bpm_r
   h->cur_lazy = h->lazy_plan() && !(h->target == BPM_TARGET_EXTERNAL);
   h->cur_phases_run = 0;
   if (st->pending && (!h->cur_lazy || rp)) BPM_TRY(h->flush(st, (cudaStream_t)stream));
-  BPM_TRY(h->begin(st, rp, (cudaStream_t)stream));
+  BPM_TRY(h->begin(st, rp, (cudaStream_t)stream, h->cur_lazy && !rp));
   h->cur = h->make_args(st, k_gen, 0, rp, nullptr);
   h->cur_replay = rp != nullptr;
   h->cur_k_gen = k_gen;
@@ -842,6 +904,8 @@ int bpm_propose(bpm_handle h, bpm_state* st, int32_t phase, double** prop, int32
     if (h->cur_phases_run) return fail("bpm_propose after bpm_phase in the same generation");
     BPM_TRY(h->flush(st, (cudaStream_t)stream));
     h->cur_lazy = false;
+    // bpm_begin_generation planned fly mode and materialised no shuffle: do it now
+    BPM_TRY(h->begin(st, h->cur_replay ? &h->cur.rp : nullptr, (cudaStream_t)stream, false));
     h->cur = h->make_args(st, h->cur_k_gen, 0, h->cur_replay ? &h->cur.rp : nullptr, nullptr);
   }
   h->cur.phase = phase;
@@ -888,15 +952,15 @@ int bpm_phase(bpm_handle h, bpm_state* st, int32_t phase, bpm_stream stream) {
   const bpm_replay* rp = h->cur_replay ? &h->cur.rp : nullptr;
   const int64_t k_gen = h->cur_k_gen;
   h->cur_phases_run += 1;
-  if (h->cur_replay) return h->phase<true>(st, k_gen, phase, rp, nullptr, (cudaStream_t)stream, h->cur_lazy);
-  return h->phase<false>(st, k_gen, phase, nullptr, nullptr, (cudaStream_t)stream, h->cur_lazy);
+  if (h->cur_replay) return h->phase<true>(st, k_gen, phase, rp, nullptr, (cudaStream_t)stream, h->cur_lazy, false);
+  return h->phase<false>(st, k_gen, phase, nullptr, nullptr, (cudaStream_t)stream, h->cur_lazy, h->cur_lazy);
 }
 
 int bpm_end_generation(bpm_handle h, bpm_state* st, bpm_stream stream) {
   if (!h || !st) return fail("null argument");
   if (!h->in_generation) return fail("bpm_end_generation without bpm_begin_generation");
   CU_TRY(cudaSetDevice(h->cfg.device));
-  BPM_TRY(h->end((cudaStream_t)stream));
+  BPM_TRY(h->end((cudaStream_t)stream, h->cur_lazy && h->cur_phases_run == 2 && h->cr_fold_plan()));
   BPM_TRY(h->track_omega(st, (cudaStream_t)stream));
   st->hist_len += 1;
   if (st->mom_len > 0) st->mom_len += 1;

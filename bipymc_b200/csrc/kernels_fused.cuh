@@ -1068,7 +1068,7 @@ __device__ __forceinline__ void warp_stage_draws(const PhaseArgs& a, const Phase
     const int row = pw + kV3ProdWarps * j;
     const int gid = gid0 + row;
     bool valid = gid < gid_end;
-    const int c = valid ? L.self[gid] : 0;
+    const int c = valid ? lself(a, L, gid) : 0;
     valid = valid && c >= a.chain_lo && c < a.chain_hi;
     if (slot == 0) T.cid[row] = valid ? c : -1;
     if (!valid) continue;
@@ -1088,8 +1088,8 @@ __device__ __forceinline__ void warp_stage_draws(const PhaseArgs& a, const Phase
         T.fallback[row] = dream ? a.rp.fallback_dim[c] : -1;
       } else {
         const int p = slot - 2;
-        T.pa[row][p] = L.pool[a.rp.pairs[((size_t)c * npair + p) * 2 + 0]];
-        T.pb[row][p] = L.pool[a.rp.pairs[((size_t)c * npair + p) * 2 + 1]];
+        T.pa[row][p] = lpool(a, L, a.rp.pairs[((size_t)c * npair + p) * 2 + 0]);
+        T.pb[row][p] = lpool(a, L, a.rp.pairs[((size_t)c * npair + p) * 2 + 1]);
         v3_prefetch_x(a.X + (size_t)T.pa[row][p] * a.ld, row_bytes);
         v3_prefetch_x(a.X + (size_t)T.pb[row][p] * a.ld, row_bytes);
       }
@@ -1111,7 +1111,7 @@ __device__ __forceinline__ void warp_stage_draws(const PhaseArgs& a, const Phase
       } else {
         int r1, r2;
         slot_pair(q, L.n_pool, r1, r2);
-        const int ga = L.pool[r1], gb = L.pool[r2];
+        const int ga = lpool(a, L, r1), gb = lpool(a, L, r2);
         T.pa[row][slot - 2] = ga;
         T.pb[row][slot - 2] = gb;
         v3_prefetch_x(a.X + (size_t)ga * a.ld, row_bytes);
@@ -1390,7 +1390,42 @@ __global__ void __launch_bounds__(128) fused_small_kernel(const PhaseArgs a, con
   }
 }
 
+// d <= 4 in fly mode (unsharded, native RNG): thread = chain, in CHAIN order (16-byte rows share sectors, moments
+// and history stream) -- the chain finds its half from the inverse Feistel image of its own id, its partners from
+// the forward image of the pool positions it drew.  No split kernel, no list-packing kernels: a generation is two
+// of these launches plus the CR reduction (C4, 10^5 line-fit chains: 93 -> ~50 us per generation).
+template <int TARGET>
+__global__ void __launch_bounds__(128) fused_small_fly_kernel(const PhaseArgs a, const TargetView tv) {
+  extern __shared__ __align__(16) double sdata[];
+  if (TARGET == BPM_TARGET_LINEFIT) {
+    for (int i = threadIdx.x; i < 3 * tv.linefit_M; i += blockDim.x) sdata[i] = tv.linefit[i];
+    __syncthreads();
+  }
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool self_first = (a.phase ^ a.flip_val) == 0;                 // this phase updates list positions [0, nA)
+  bool valid = c < a.N;
+  if (valid) {
+    const int pos = a.fly_shuffle ? (int)feistel_inv(a.fk, (uint32_t)c) : c;
+    valid = (pos < a.nA) == self_first;
+  }
+  int acc = 0;
+  if (valid) {
+    const int n_pool = self_first ? a.N - a.nA : a.nA, off = self_first ? a.nA : 0;
+    acc = small_chain_step<false, TARGET>(a, tv, sdata, c, n_pool, [&](int r) {
+      return a.fly_shuffle ? (int)feistel_perm(a.fk, (uint32_t)(off + r)) : off + r;
+    });
+  }
+  const unsigned am = __ballot_sync(0xFFFFFFFFu, valid && acc);
+  const unsigned rm = __ballot_sync(0xFFFFFFFFu, valid && !acc);
+  if ((threadIdx.x & 31) == 0) {
+    if (am) atomicAdd(a.n_acc, (unsigned long long)__popc(am));
+    if (rm) atomicAdd(a.n_rej, (unsigned long long)__popc(rm));
+  }
+}
+
 // ---- d <= 4: a whole run of generations in ONE persistent cooperative launch -----------------------------
+// (EXPERIMENTAL, bpm_set_fused(h, 6): measured slower than the per-phase launches -- 152 vs 91 us per generation at
+// 10^5 line-fit chains; every warp runs the chain-step twice with half its lanes, at 80 registers with spills.)
 // A generation of 10^5 three-parameter chains is ~10 us of work; launched as split + list packing + two
 // half-phases + CR reduction it costs 93 us (profiles/r1b_secondary_configs.txt: launch-bound).  Here one
 // cooperative grid keeps every generation of a bpm_step_generations call on the device (demc.py:79-135,
@@ -1578,6 +1613,19 @@ inline int try_fused_phase(const TargetView& tv, const PhaseArgs& a, cudaStream_
                 : launch_fused_v3<REPLAY, true, 0>(a, g, grid, sm, s);
       if (rc) return 1;
     }
+    if (cudaGetLastError() != cudaSuccess) return 1;
+    *done = 1;
+    return 0;
+  }
+  if (a.d <= 4 && a.fly && !REPLAY && (tv.target == BPM_TARGET_BANANA || tv.target == BPM_TARGET_BIMODAL ||
+                                       tv.target == BPM_TARGET_LINEFIT)) {
+    const int grid = (a.N + 127) / 128;
+    if (tv.target == BPM_TARGET_BANANA)
+      fused_small_fly_kernel<BPM_TARGET_BANANA><<<grid, 128, 0, s>>>(a, tv);
+    else if (tv.target == BPM_TARGET_BIMODAL)
+      fused_small_fly_kernel<BPM_TARGET_BIMODAL><<<grid, 128, 0, s>>>(a, tv);
+    else
+      fused_small_fly_kernel<BPM_TARGET_LINEFIT><<<grid, 128, sizeof(double) * 3 * tv.linefit_M, s>>>(a, tv);
     if (cudaGetLastError() != cudaSuccess) return 1;
     *done = 1;
     return 0;

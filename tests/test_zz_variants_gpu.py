@@ -56,14 +56,16 @@ def test_replay_extra_golden_cases(name, fused):
     replay_and_check(name, fused)
 
 
-# ---- d <= 4: the persistent cooperative multi-generation kernel against the per-phase launches ------------
+# ---- d <= 4: the shuffle-free ("fly") fused kernel and the persistent cooperative kernel against the split path ---
+@pytest.mark.parametrize("fused", [1, 6], ids=["fly", "persistent"])
 @pytest.mark.parametrize("target,n_chains,algo", [("banana", 1000, "dream"), ("dblgauss", 4099, "dream"),
                                                    ("linefit", 2500, "dream"), ("banana", 777, "demc")])
-def test_small_d_persistent_kernel_equals_per_phase_path(target, n_chains, algo):
-    """fused=1 runs every generation of a run_mcmc call in ONE cooperative launch (Feistel shuffle evaluated on
-    the fly, grid-wide barriers between half-phases); fused=0 launches split / propose / likelihood / accept /
-    CR reduction per generation.  Same seed: identical histories, cached likelihoods, counters, running
-    moments and -- the CR block partials are summed in the same order -- bit-identical p_cr."""
+def test_small_d_shuffle_free_kernels_equal_split_path(target, n_chains, algo, fused):
+    """fused=1 (default): two launches per generation whose threads walk the chains in order and evaluate the
+    Feistel shuffle on the fly (no split / list-packing kernels); fused=6: every generation of a run_mcmc call in
+    ONE cooperative launch.  fused=0 launches split / propose / likelihood / accept / CR reduction per generation
+    over the materialised shuffle.  Same seed: identical histories, cached likelihoods, counters, running moments
+    and -- the CR block partials are summed in the same order -- bit-identical p_cr."""
     import ctypes as C
     import torch
     from bipymc_b200 import DreamMpi, DeMcMpi, targets, _lib
@@ -71,21 +73,24 @@ def test_small_d_persistent_kernel_equals_per_phase_path(target, n_chains, algo)
     th0 = [-0.8, 4.5, 0.2] if target == "linefit" else [0.0, 0.0]
     G = 37
     runs = []
-    for fused in (1, 0):
+    for f in (fused, 0):
         np.random.seed(21)
         if algo == "dream":
             s = DreamMpi(tgt.ln_like, th0, n_chains=n_chains, seed=9, varepsilon=1e-2 if target == "linefit" else 0.3,
-                         n_cr_gen=3, burnin_gen=30, fused=fused)
+                         n_cr_gen=3, burnin_gen=30, fused=f)
         else:
-            s = DeMcMpi(tgt.ln_like, th0, n_chains=n_chains, seed=9, varepsilon=0.3, fused=fused)
+            s = DeMcMpi(tgt.ln_like, th0, n_chains=n_chains, seed=9, varepsilon=0.3, fused=f)
         _lib.check(s._libh.bpm_profile(s._handle, 1))
         s.run_mcmc(n_chains * (G + 1), flip=0.3)
         ms, n = (C.c_double * 8)(), (C.c_int64 * 8)()
         _lib.check(s._libh.bpm_profile_read(s._handle, ms, n))
         runs.append((s, [int(v) for v in n]))
     (a, ka), (b, kb) = runs
-    assert ka[4] == 1 and ka[1] == 0 and ka[0] == 0, ka          # one launch for the whole run
-    assert kb[4] == 0 and kb[1] == 2 * G, kb
+    if fused == 6:
+        assert ka[4] == 1 and ka[1] == 0 and ka[0] == 0, ka          # one launch for the whole run
+    else:
+        assert ka[4] == 2 * G and ka[0] == 0 and ka[1] == 0, ka      # no split / packing launches at all
+    assert kb[4] == 0 and kb[1] == 2 * G and kb[0] == G, kb
     assert torch.equal(a._hist.tensor(), b._hist.tensor())
     assert torch.equal(a._lnl, b._lnl) and torch.equal(a._X, b._X)
     assert torch.equal(a._mean, b._mean) and torch.equal(a._m2, b._m2)
