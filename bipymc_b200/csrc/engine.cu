@@ -295,12 +295,26 @@ struct bpm_engine {
   }
   // DREAM on the v4 kernel: the CR statistics are reduced in the kernels' tails, no cr_update launch
   bool cr_fold_plan() const {
+    static const bool off = [] {
+      const char* e = getenv("BIPYMC_B200_NO_CR_FOLD");      // A/B switch: separate cr_update launch as in round 1
+      return e && e[0] == '1';
+    }();
+    if (off) return false;
     return cfg.algo == BPM_ALGO_DREAM && lazy_plan() && fused_ok != 5 &&
            bpm::fused_v4_fits(cfg.dim, cfg.ld, gauss_r, cfg.del_pairs);
   }
   // Native-RNG generations that never materialise the shuffle ("fly" mode, step.cuh): the lazy-protocol Gaussian
   // kernels (sharded or not) and the d <= 4 fused kernel on a handle that owns every chain.
+  // MEASURED AND SWITCHED OFF (profiles/r2/r2h_*): with the balanced 6-round Feistel network and cycle walking
+  // (2.6 walks at N = 10^5) one list entry costs ~160 instructions, seven of them per chain-step; the fused 100-D
+  // launch went 114 -> 160 us and the line-fit generation 91 -> 132 us.  A table lookup in the materialised
+  // shuffle (one 8 us split kernel per generation) is cheaper.  BIPYMC_B200_FLY=1 re-enables the mode.
   bool fly_plan() const {
+    static const bool on = [] {
+      const char* e = getenv("BIPYMC_B200_FLY");
+      return e && e[0] == '1';
+    }();
+    if (!on) return false;
     if (lazy_plan()) return true;
     return fused_ok == 1 && !serial() && !sharded() && cfg.dim <= 4 &&
            (target == BPM_TARGET_BANANA || target == BPM_TARGET_BIMODAL || target == BPM_TARGET_LINEFIT);
@@ -887,7 +901,7 @@ int bpm_begin_generation(bpm_handle h, bpm_state* st, int64_t k_gen, const bpm_r
   h->cur_lazy = h->lazy_plan() && !(h->target == BPM_TARGET_EXTERNAL);
   h->cur_phases_run = 0;
   if (st->pending && (!h->cur_lazy || rp)) BPM_TRY(h->flush(st, (cudaStream_t)stream));
-  BPM_TRY(h->begin(st, rp, (cudaStream_t)stream, h->cur_lazy && !rp));
+  BPM_TRY(h->begin(st, rp, (cudaStream_t)stream, h->cur_lazy && !rp && h->fly_plan()));
   h->cur = h->make_args(st, k_gen, 0, rp, nullptr);
   h->cur_replay = rp != nullptr;
   h->cur_k_gen = k_gen;
@@ -953,7 +967,8 @@ int bpm_phase(bpm_handle h, bpm_state* st, int32_t phase, bpm_stream stream) {
   const int64_t k_gen = h->cur_k_gen;
   h->cur_phases_run += 1;
   if (h->cur_replay) return h->phase<true>(st, k_gen, phase, rp, nullptr, (cudaStream_t)stream, h->cur_lazy, false);
-  return h->phase<false>(st, k_gen, phase, nullptr, nullptr, (cudaStream_t)stream, h->cur_lazy, h->cur_lazy);
+  return h->phase<false>(st, k_gen, phase, nullptr, nullptr, (cudaStream_t)stream, h->cur_lazy,
+                         h->cur_lazy && h->fly_plan());
 }
 
 int bpm_end_generation(bpm_handle h, bpm_state* st, bpm_stream stream) {

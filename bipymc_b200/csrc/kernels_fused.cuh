@@ -1278,6 +1278,13 @@ __device__ __forceinline__ int small_chain_step(const PhaseArgs& a, const Target
   const int npair = dream ? a.del_pairs : 1;
   ChainDraws D;
   chain_scalar_draws<REPLAY>(a, c, n_pool, D);
+  BPM_CHECK(c >= a.chain_lo && c < a.chain_hi, "own chain id", c);
+  for (int p = 0; p < npair; ++p) {
+    BPM_CHECK(D.r1[p] >= 0 && D.r1[p] < n_pool && D.r2[p] >= 0 && D.r2[p] < n_pool && D.r1[p] != D.r2[p],
+              "pair draw", D.r1[p] * 100000LL + D.r2[p]);
+    BPM_CHECK(pool_id(D.r1[p]) >= 0 && pool_id(D.r1[p]) < a.N && pool_id(D.r2[p]) >= 0 && pool_id(D.r2[p]) < a.N,
+              "partner chain id", pool_id(D.r1[p]));
+  }
   uint32_t mbits = 0xFu;
   double gamma;
   if (dream) {

@@ -189,8 +189,11 @@ fused_gauss_v4_kernel(const PhaseArgs a, const GaussArgs g) {
     if (lane < 2 * npair) {
       const int p = lane >> 1;
       const int id = (lane & 1) ? T.pb[row][p] : T.pa[row][p];
+      BPM_CHECK(id >= 0 && id < a.N, "partner chain id (TMA source row)", id);
+      BPM_CHECK((size_t)((lane + 1) * d) <= (size_t)L4.land_rows * d, "landing slot row", lane);
       bulk_g2s(land + (size_t)lane * d, a.X + (size_t)id * a.ld, (uint32_t)(d * 8), LAND + pw);
     }
+    BPM_CHECK(c >= a.chain_lo && c < a.chain_hi, "own chain id", c);
     const double* xc = a.X + (size_t)c * a.ld + 4 * lc;
     pre.u0 = ldg2(xc); pre.u1 = ldg2(xc + 2);
     if (need_m2) {
@@ -201,6 +204,7 @@ fused_gauss_v4_kernel(const PhaseArgs a, const GaussArgs g) {
   // row `row` of the tile is complete: all 32 lanes arrive on the m-tile's named barrier (the consumer
   // blocks in bar.sync there -- a hardware wait that costs no issue slots, unlike an mbarrier poll)
   auto hand_over = [&](int i, int row, int cw, int c, double u, const double* prv) {
+    BPM_CHECK(row >= 0 && row < kTileRows && cw == (row >> 3), "tile row", row);
     if (i >= 1) mbar_wait(DONEm + cw, (i - 1) & 1);     // consumer cw released tile i-1's m-tile
     if (act) {
       double* prow = P + row * pld + 4 * lane;
@@ -372,18 +376,25 @@ fused_gauss_v4_kernel(const PhaseArgs a, const GaussArgs g) {
     }
     if (dream) {
       delta = group_sum_d<32>(act ? delta : 0.0);
-      if (lane == 0 && adapt) {          // (the engine always plans the fold for this kernel: cr_fold_plan())
-        double* crs = reinterpret_cast<double*>(smem4 + L4.crs) + pw * 2 * BPM_MAX_CR;
-        const int m = T.cr_idx[row];
-        crs[m] += delta;
-        crs[a.n_cr + m] += 1.0;
+      if (lane == 0) {
+        if (a.cr_fold_part) {              // the engine's default for this kernel (cr_fold_plan())
+          if (adapt) {
+            double* crs = reinterpret_cast<double*>(smem4 + L4.crs) + pw * 2 * BPM_MAX_CR;
+            const int m = T.cr_idx[row];
+            crs[m] += delta;
+            crs[a.n_cr + m] += 1.0;
+          }
+        } else {                           // BIPYMC_B200_NO_CR_FOLD=1: per-chain statistics for cr_update_kernel
+          a.cr_pick[c] = adapt ? T.cr_idx[row] : -1;
+          a.cr_delta[c] = delta;
+        }
       }
     }
     hand_over(i, row, cw, c, T.accept_u[row], prv);
   }
   // ---- CR statistics of this half-phase: warp partials -> CTA partial -> (last CTA of the second half-phase)
   //      the generation's sums in a fixed (phase, cta, warp) order and the p_cr update
-  if (dream) {
+  if (dream && a.cr_fold_part) {
     __syncwarp();
     nbar_sync(BAR_PROD, kV3ProdThreads);                   // every producer warp's partials are final
     if (pw == 0) {

@@ -8,6 +8,27 @@
 #include "rng.cuh"
 #include "../../include/bipymc_b200.h"
 
+// compute-sanitizer is closed on the GPU pool this was developed on (profiles/r2/r2e_sanitizer_*.log), so the
+// index checks it would have made are built in: -DBPM_CHECKS=1 turns every chain / partner / list index of the
+// phase kernels into a checked access that prints and traps (tools/sanitize_case.py runs all kernel families
+// under such a build; the shipped library compiles the checks away).
+#ifndef BPM_CHECKS
+#define BPM_CHECKS 0
+#endif
+#if BPM_CHECKS
+#include <stdio.h>
+#define BPM_CHECK(cond, what, v)                                                                          \
+  do {                                                                                                   \
+    if (!(cond)) {                                                                                       \
+      printf("BPM_CHECK failed: %s = %lld (%s:%d, block %d thread %d)\n", what, (long long)(v), __FILE__,  \
+             __LINE__, (int)blockIdx.x, (int)threadIdx.x);                                               \
+      __trap();                                                                                          \
+    }                                                                                                    \
+  } while (0)
+#else
+#define BPM_CHECK(cond, what, v) do { } while (0)
+#endif
+
 namespace bpm {
 
 // Everything a phase kernel needs, passed by value (fits the 4 KB param space easily).
@@ -115,17 +136,30 @@ struct PhaseLists {
 };
 // list entries, materialised or evaluated on the fly (kernels that can be launched in fly mode use these)
 __device__ __forceinline__ int lself(const PhaseArgs& a, const PhaseLists& L, int i) {
-  if (L.self) return L.self[i];
-  const uint32_t j = (uint32_t)(L.self_off + i);
-  return a.fly_shuffle ? (int)feistel_perm(a.fk, j) : (int)j;
+  BPM_CHECK(i >= 0 && i < L.n_self, "self list position", i);
+  int c;
+  if (L.self) c = L.self[i];
+  else {
+    const uint32_t j = (uint32_t)(L.self_off + i);
+    c = a.fly_shuffle ? (int)feistel_perm(a.fk, j) : (int)j;
+  }
+  BPM_CHECK(c >= a.chain_lo && c < a.chain_hi, "own chain id", c);
+  return c;
 }
 __device__ __forceinline__ int lpool(const PhaseArgs& a, const PhaseLists& L, int r) {
-  if (L.pool) return L.pool[r];
-  const uint32_t j = (uint32_t)(L.pool_off + r);
-  return a.fly_shuffle ? (int)feistel_perm(a.fk, j) : (int)j;
+  BPM_CHECK(r >= 0 && r < L.n_pool, "pool position", r);
+  int c;
+  if (L.pool) c = L.pool[r];
+  else {
+    const uint32_t j = (uint32_t)(L.pool_off + r);
+    c = a.fly_shuffle ? (int)feistel_perm(a.fk, j) : (int)j;
+  }
+  BPM_CHECK(c >= 0 && c < a.N, "partner chain id", c);
+  return c;
 }
 // global chain id of pool position r for the chain c being stepped
 __device__ __forceinline__ int pool_chain(const PhaseLists& L, int r, int c) {
+  BPM_CHECK(r >= 0 && r < L.n_pool, "pool position", r);
   return L.skip_self ? r + (r >= c ? 1 : 0) : L.pool[r];
 }
 __device__ __forceinline__ PhaseLists phase_lists(const PhaseArgs& a) {

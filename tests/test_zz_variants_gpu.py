@@ -3,6 +3,8 @@ default fused Gaussian kernel that the golden / headline configurations do not r
   * the run-time-general proposal stage (DREAM with del_pairs != 3, DE-MC) at d = 100, several tiles;
   * a target with a non-zero mean (the CENTER instantiation of the tile product).
 Runs last (file name) so that a regression here does not mask the main parity suite under `pytest -x`."""
+import os
+
 import numpy as np
 import pytest
 from scipy.stats import multivariate_normal
@@ -57,7 +59,7 @@ def test_replay_extra_golden_cases(name, fused):
 
 
 # ---- d <= 4: the shuffle-free ("fly") fused kernel and the persistent cooperative kernel against the split path ---
-@pytest.mark.parametrize("fused", [1, 6], ids=["fly", "persistent"])
+@pytest.mark.parametrize("fused", [1, 6, "fly"], ids=["default", "persistent", "fly"])
 @pytest.mark.parametrize("target,n_chains,algo", [("banana", 1000, "dream"), ("dblgauss", 4099, "dream"),
                                                    ("linefit", 2500, "dream"), ("banana", 777, "demc")])
 def test_small_d_shuffle_free_kernels_equal_split_path(target, n_chains, algo, fused):
@@ -73,6 +75,13 @@ def test_small_d_shuffle_free_kernels_equal_split_path(target, n_chains, algo, f
     th0 = [-0.8, 4.5, 0.2] if target == "linefit" else [0.0, 0.0]
     G = 37
     runs = []
+    if fused == "fly":
+        # the shuffle-free mode is read from the environment once per process (BIPYMC_B200_FLY=1): it is covered
+        # by the suite's second pass (tools/gpu_job: BIPYMC_B200_FLY=1 pytest -k "native or variants or replay")
+        if os.environ.get("BIPYMC_B200_FLY", "") != "1":
+            pytest.skip("run with BIPYMC_B200_FLY=1")
+        fused = 1
+    fly = os.environ.get("BIPYMC_B200_FLY", "") == "1"
     for f in (fused, 0):
         np.random.seed(21)
         if algo == "dream":
@@ -89,7 +98,8 @@ def test_small_d_shuffle_free_kernels_equal_split_path(target, n_chains, algo, f
     if fused == 6:
         assert ka[4] == 1 and ka[1] == 0 and ka[0] == 0, ka          # one launch for the whole run
     else:
-        assert ka[4] == 2 * G and ka[0] == 0 and ka[1] == 0, ka      # no split / packing launches at all
+        assert ka[4] == 2 * G and ka[1] == 0, ka
+        assert ka[0] == (0 if fly else G), ka                        # fly mode: no split / packing launches at all
     assert kb[4] == 0 and kb[1] == 2 * G and kb[0] == G, kb
     assert torch.equal(a._hist.tensor(), b._hist.tensor())
     assert torch.equal(a._lnl, b._lnl) and torch.equal(a._X, b._X)
