@@ -76,8 +76,6 @@ struct bpm_engine {
   double* cr_part = nullptr;
   double* cr_block = nullptr;
   unsigned int* cr_ticket = nullptr;
-  double* cr_fold_part = nullptr;          // [2][148][2 BPM_MAX_CR] per-CTA CR partials of the fused v4 launches
-  unsigned int* cr_fold_ticket = nullptr;
   unsigned long long* counters = nullptr;  // [0] accepted, [1] rejected
   int32_t* nan_flag = nullptr;
   // target
@@ -154,7 +152,6 @@ struct bpm_engine {
 
   ~bpm_engine() {
     cudaFree(inv); cudaFree(loc_list); cudaFree(loc_cnt); cudaFree(phase_cnt); cudaFree(cmp_blk); cudaFree(cr_ticket);
-    cudaFree(cr_fold_part); cudaFree(cr_fold_ticket);
     cudaFree(perm); cudaFree(flip); cudaFree(prop); cudaFree(lnl_prop); cudaFree(cr_delta);
     cudaFree(cr_pick); cudaFree(p_cr); cudaFree(cr_dm); cudaFree(cr_cnt); cudaFree(cr_part); cudaFree(cr_block);
     cudaFree(counters); cudaFree(nan_flag); cudaFree(tparams); cudaFree(hX); cudaFree(hL); cudaFree(hMean); cudaFree(hM2);
@@ -190,10 +187,6 @@ struct bpm_engine {
     CU_TRY(cudaMalloc(&cr_block, sizeof(double) * 2 * BPM_MAX_CR * bpm::kCrBlocks));
     CU_TRY(cudaMalloc(&cr_ticket, sizeof(unsigned int)));
     CU_TRY(cudaMemset(cr_ticket, 0, sizeof(unsigned int)));
-    CU_TRY(cudaMalloc(&cr_fold_part, sizeof(double) * 2 * 148 * 2 * BPM_MAX_CR));
-    CU_TRY(cudaMemset(cr_fold_part, 0, sizeof(double) * 2 * 148 * 2 * BPM_MAX_CR));
-    CU_TRY(cudaMalloc(&cr_fold_ticket, sizeof(unsigned int)));
-    CU_TRY(cudaMemset(cr_fold_ticket, 0, sizeof(unsigned int)));
     CU_TRY(cudaMalloc(&counters, sizeof(unsigned long long) * 2));
     CU_TRY(cudaMalloc(&nan_flag, sizeof(int32_t)));
     CU_TRY(cudaMemset(flip, 0, sizeof(int32_t)));
@@ -262,11 +255,6 @@ struct bpm_engine {
     a.n_acc = counters; a.n_rej = counters + 1; a.nan_flag = nan_flag;
     a.rng = bpm::make_rng(cfg.seed, (uint64_t)st->hist_len);
     if (fly && !rp && !serial()) fill_fly(a);
-    if (lazy && cr_fold_plan()) {
-      a.cr_fold_part = cr_fold_part; a.cr_fold_ticket = cr_fold_ticket; a.cr_fold_out = cr_part;
-      a.cr_fold_dm = cr_dm; a.cr_fold_cnt = cr_cnt; a.cr_fold_pcr = p_cr;
-      a.cr_fold_apply = sharded() ? 0 : 1;
-    }
     if (rp) a.rp = *rp;
     if (tr) a.tr = *tr;
     return a;
@@ -293,30 +281,18 @@ struct bpm_engine {
   bool lazy_plan() const {
     return fused_ok && !serial() && bpm::fused_plan_is_v3(target, cfg.dim, cfg.ld, gauss_r, fused_ok);
   }
-  // DREAM on the v4 kernel: the CR statistics are reduced in the kernels' tails, no cr_update launch
-  bool cr_fold_plan() const {
-    static const bool off = [] {
-      const char* e = getenv("BIPYMC_B200_NO_CR_FOLD");      // A/B switch: separate cr_update launch as in round 1
-      return e && e[0] == '1';
-    }();
-    if (off) return false;
-    return cfg.algo == BPM_ALGO_DREAM && lazy_plan() && fused_ok != 5 &&
-           bpm::fused_v4_fits(cfg.dim, cfg.ld, gauss_r, cfg.del_pairs);
-  }
-  // Native-RNG generations that never materialise the shuffle ("fly" mode, step.cuh): the lazy-protocol Gaussian
-  // kernels (sharded or not) and the d <= 4 fused kernel on a handle that owns every chain.
-  // MEASURED AND SWITCHED OFF (profiles/r2/r2h_*): with the balanced 6-round Feistel network and cycle walking
-  // (2.6 walks at N = 10^5) one list entry costs ~160 instructions, seven of them per chain-step; the fused 100-D
-  // launch went 114 -> 160 us and the line-fit generation 91 -> 132 us.  A table lookup in the materialised
-  // shuffle (one 8 us split kernel per generation) is cheaper.  BIPYMC_B200_FLY=1 re-enables the mode.
+  // Native-RNG generations that never materialise the shuffle ("fly" mode, step.cuh) -- d <= 4 fused kernel on a
+  // handle that owns every chain.  MEASURED AND SWITCHED OFF (profiles/r2/r2h_*): with the balanced 6-round
+  // Feistel network and cycle walking (2.6 walks at N = 10^5) one list entry costs ~160 instructions, seven of
+  // them per chain-step; the line-fit generation went 91 -> 132 us (and the 100-D kernel, which tried the same,
+  // 114 -> 160 us).  A table lookup in the materialised shuffle (one 8 us split kernel per generation) is
+  // cheaper.  BIPYMC_B200_FLY=1 re-enables the mode for d <= 4.
   bool fly_plan() const {
     static const bool on = [] {
       const char* e = getenv("BIPYMC_B200_FLY");
       return e && e[0] == '1';
     }();
-    if (!on) return false;
-    if (lazy_plan()) return true;
-    return fused_ok == 1 && !serial() && !sharded() && cfg.dim <= 4 &&
+    return on && fused_ok == 1 && !serial() && !sharded() && cfg.dim <= 4 &&
            (target == BPM_TARGET_BANANA || target == BPM_TARGET_BIMODAL || target == BPM_TARGET_LINEFIT);
   }
   // bpm_flush: history row hist_len - 1 and its moment sample, left pending by a lazy generation
@@ -348,27 +324,7 @@ struct bpm_engine {
 
   int begin(const bpm_state* st, const bpm_replay* rp, cudaStream_t s, bool fly = false) {
     const int N = cfg.n_chains;
-    if (fly && !rp && !serial()) {
-      // nothing to materialise; sharded ranks still pack their local chains of both halves, reading list
-      // positions from the inverse permutation evaluated on the fly (O(n_local), not O(N))
-      if (sharded()) {
-        prof_begin(0, s);
-        bpm::PhaseArgs t;
-        memset(&t, 0, sizeof(t));
-        t.rng = bpm::make_rng(cfg.seed, (uint64_t)st->hist_len);
-        fill_fly(t);
-        bpm::ListPos pos;
-        pos.inv = nullptr; pos.fly = 1; pos.shuffle = t.fly_shuffle; pos.fk = t.fk;
-        const int nblk = cdiv(cfg.chain_hi - cfg.chain_lo, bpm::kCompactBlock);
-        bpm::compact_count_kernel<<<nblk, bpm::kCompactThreads, 0, s>>>(pos, nA, cfg.chain_lo, cfg.chain_hi, cmp_blk);
-        bpm::compact_scan_kernel<<<1, 1024, 0, s>>>(cmp_blk, nblk, cmp_blk + 2 * nblk, loc_cnt);
-        bpm::compact_write_kernel<<<nblk, bpm::kCompactThreads, 0, s>>>(pos, nA, cfg.chain_lo, cfg.chain_hi,
-                                                                       cmp_blk + 2 * nblk, loc_list);
-        prof_end(s);
-        CU_TRY(cudaGetLastError());
-      }
-      return 0;
-    }
+    if (fly && !rp && !serial()) return 0;      // nothing to materialise (unsharded d <= 4 only, see fly_plan)
     prof_begin(0, s);
     if (serial()) {
       bpm::identity_split_kernel<<<cdiv(N, 256), 256, 0, s>>>(perm, inv, flip, N);
@@ -490,8 +446,8 @@ struct bpm_engine {
     return 0;
   }
 
-  int end(cudaStream_t s, bool folded = false) {
-    if (cfg.algo != BPM_ALGO_DREAM || folded) return 0;
+  int end(cudaStream_t s) {
+    if (cfg.algo != BPM_ALGO_DREAM) return 0;
     prof_begin(5, s);
     const int nloc = cfg.chain_hi - cfg.chain_lo;
     int nb = cdiv(nloc, 2048);
@@ -642,7 +598,7 @@ struct bpm_engine {
       if (sync_on) BPM_TRY(peer_barrier(s));          // every rank's phase-a rows are in every replica
       BPM_TRY(phase<REPLAY>(st, k_gen, 1, rp, tr, s, lazy, fly));
     }
-    BPM_TRY(end(s, lazy && cr_fold_plan()));
+    BPM_TRY(end(s));
     if (sync_on) {
       if (cfg.algo == BPM_ALGO_DREAM) BPM_TRY(peer_cr_exchange(s));
       else BPM_TRY(peer_barrier(s));
@@ -901,7 +857,7 @@ int bpm_begin_generation(bpm_handle h, bpm_state* st, int64_t k_gen, const bpm_r
   h->cur_lazy = h->lazy_plan() && !(h->target == BPM_TARGET_EXTERNAL);
   h->cur_phases_run = 0;
   if (st->pending && (!h->cur_lazy || rp)) BPM_TRY(h->flush(st, (cudaStream_t)stream));
-  BPM_TRY(h->begin(st, rp, (cudaStream_t)stream, h->cur_lazy && !rp && h->fly_plan()));
+  BPM_TRY(h->begin(st, rp, (cudaStream_t)stream, false));
   h->cur = h->make_args(st, k_gen, 0, rp, nullptr);
   h->cur_replay = rp != nullptr;
   h->cur_k_gen = k_gen;
@@ -918,8 +874,6 @@ int bpm_propose(bpm_handle h, bpm_state* st, int32_t phase, double** prop, int32
     if (h->cur_phases_run) return fail("bpm_propose after bpm_phase in the same generation");
     BPM_TRY(h->flush(st, (cudaStream_t)stream));
     h->cur_lazy = false;
-    // bpm_begin_generation planned fly mode and materialised no shuffle: do it now
-    BPM_TRY(h->begin(st, h->cur_replay ? &h->cur.rp : nullptr, (cudaStream_t)stream, false));
     h->cur = h->make_args(st, h->cur_k_gen, 0, h->cur_replay ? &h->cur.rp : nullptr, nullptr);
   }
   h->cur.phase = phase;
@@ -967,15 +921,14 @@ int bpm_phase(bpm_handle h, bpm_state* st, int32_t phase, bpm_stream stream) {
   const int64_t k_gen = h->cur_k_gen;
   h->cur_phases_run += 1;
   if (h->cur_replay) return h->phase<true>(st, k_gen, phase, rp, nullptr, (cudaStream_t)stream, h->cur_lazy, false);
-  return h->phase<false>(st, k_gen, phase, nullptr, nullptr, (cudaStream_t)stream, h->cur_lazy,
-                         h->cur_lazy && h->fly_plan());
+  return h->phase<false>(st, k_gen, phase, nullptr, nullptr, (cudaStream_t)stream, h->cur_lazy, false);
 }
 
 int bpm_end_generation(bpm_handle h, bpm_state* st, bpm_stream stream) {
   if (!h || !st) return fail("null argument");
   if (!h->in_generation) return fail("bpm_end_generation without bpm_begin_generation");
   CU_TRY(cudaSetDevice(h->cfg.device));
-  BPM_TRY(h->end((cudaStream_t)stream, h->cur_lazy && h->cur_phases_run == 2 && h->cr_fold_plan()));
+  BPM_TRY(h->end((cudaStream_t)stream));
   BPM_TRY(h->track_omega(st, (cudaStream_t)stream));
   st->hist_len += 1;
   if (st->mom_len > 0) st->mom_len += 1;

@@ -1068,7 +1068,7 @@ __device__ __forceinline__ void warp_stage_draws(const PhaseArgs& a, const Phase
     const int row = pw + kV3ProdWarps * j;
     const int gid = gid0 + row;
     bool valid = gid < gid_end;
-    const int c = valid ? lself(a, L, gid) : 0;
+    const int c = valid ? L.self[gid] : 0;
     valid = valid && c >= a.chain_lo && c < a.chain_hi;
     if (slot == 0) T.cid[row] = valid ? c : -1;
     if (!valid) continue;
@@ -1088,8 +1088,8 @@ __device__ __forceinline__ void warp_stage_draws(const PhaseArgs& a, const Phase
         T.fallback[row] = dream ? a.rp.fallback_dim[c] : -1;
       } else {
         const int p = slot - 2;
-        T.pa[row][p] = lpool(a, L, a.rp.pairs[((size_t)c * npair + p) * 2 + 0]);
-        T.pb[row][p] = lpool(a, L, a.rp.pairs[((size_t)c * npair + p) * 2 + 1]);
+        T.pa[row][p] = L.pool[a.rp.pairs[((size_t)c * npair + p) * 2 + 0]];
+        T.pb[row][p] = L.pool[a.rp.pairs[((size_t)c * npair + p) * 2 + 1]];
         v3_prefetch_x(a.X + (size_t)T.pa[row][p] * a.ld, row_bytes);
         v3_prefetch_x(a.X + (size_t)T.pb[row][p] * a.ld, row_bytes);
       }
@@ -1111,7 +1111,9 @@ __device__ __forceinline__ void warp_stage_draws(const PhaseArgs& a, const Phase
       } else {
         int r1, r2;
         slot_pair(q, L.n_pool, r1, r2);
-        const int ga = lpool(a, L, r1), gb = lpool(a, L, r2);
+        BPM_CHECK(r1 >= 0 && r1 < L.n_pool && r2 >= 0 && r2 < L.n_pool && r1 != r2, "pair draw", r1 * 100000LL + r2);
+        const int ga = L.pool[r1], gb = L.pool[r2];
+        BPM_CHECK(ga >= 0 && ga < a.N && gb >= 0 && gb < a.N, "partner chain id", ga);
         T.pa[row][slot - 2] = ga;
         T.pb[row][slot - 2] = gb;
         v3_prefetch_x(a.X + (size_t)ga * a.ld, row_bytes);

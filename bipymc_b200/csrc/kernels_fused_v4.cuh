@@ -35,7 +35,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 struct V4Layout {
-  size_t wf, mus, gam, cdf, crv, thr, P, acc_u, cid, land, scratch, bars, crs, total;   // byte offsets
+  size_t wf, mus, gam, cdf, crv, thr, P, acc_u, cid, land, scratch, bars, total;   // byte offsets
   int land_rows;
 };
 __host__ __device__ inline V4Layout v4_layout(int d, int r, int npair) {
@@ -55,7 +55,6 @@ __host__ __device__ inline V4Layout v4_layout(int d, int r, int npair) {
   L.land = take(sizeof(double) * (size_t)kV3ProdWarps * L.land_rows * d);
   L.scratch = take(2 * ((sizeof(TileScratch) + 127) & ~(size_t)127));
   L.bars = take(sizeof(uint64_t) * (kV3ProdWarps + 2 * kV3ConsWarps));
-  L.crs = take(sizeof(double) * kV3ProdWarps * 2 * BPM_MAX_CR);
   L.total = o;
   return L;
 }
@@ -156,10 +155,7 @@ fused_gauss_v4_kernel(const PhaseArgs a, const GaussArgs g) {
   // ------------------------------ producers --------------------------------------------
   asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
   const int pw = warp - kV3ConsWarps;
-  // this warp's CR statistics (dream.py:126-130: n_cr_updates[cr]++, delta_m[cr] += jump statistic), summed
-  // over its chains in chain order; lane 0 is the only writer
-  if (lane < 2 * BPM_MAX_CR) (reinterpret_cast<double*>(smem4 + L4.crs) + pw * 2 * BPM_MAX_CR)[lane] = 0.0;
-  __syncwarp();
+  if (n_my == 0) return;
   const size_t t_stride = (sizeof(TileScratch) + 127) & ~(size_t)127;
   auto scratch = [&](int tile) -> TileScratch& {
     return *reinterpret_cast<TileScratch*>(smem4 + L4.scratch + (size_t)(tile & 1) * t_stride);
@@ -218,13 +214,10 @@ fused_gauss_v4_kernel(const PhaseArgs a, const GaussArgs g) {
     nbar_arrive(kV4BarFull0 + cw, kV4FullCount);
   };
 
+  warp_stage_draws<REPLAY>(a, L, tb, scratch(0), g_lo, g_hi, pw, lane);
   V4Pre pre;
   pre.u0 = pre.u1 = pre.w0 = pre.w1 = make_double2(0.0, 0.0);
-  pre.c = -1;
-  if (n_my > 0) {
-    warp_stage_draws<REPLAY>(a, L, tb, scratch(0), g_lo, g_hi, pw, lane);
-    start_chain(0, pre);
-  }
+  start_chain(0, pre);
 #pragma unroll 1
   for (int n = 0; n < n_total; ++n) {
     const int i = n >> 2, j = n & 3;
@@ -377,55 +370,11 @@ fused_gauss_v4_kernel(const PhaseArgs a, const GaussArgs g) {
     if (dream) {
       delta = group_sum_d<32>(act ? delta : 0.0);
       if (lane == 0) {
-        if (a.cr_fold_part) {              // the engine's default for this kernel (cr_fold_plan())
-          if (adapt) {
-            double* crs = reinterpret_cast<double*>(smem4 + L4.crs) + pw * 2 * BPM_MAX_CR;
-            const int m = T.cr_idx[row];
-            crs[m] += delta;
-            crs[a.n_cr + m] += 1.0;
-          }
-        } else {                           // BIPYMC_B200_NO_CR_FOLD=1: per-chain statistics for cr_update_kernel
-          a.cr_pick[c] = adapt ? T.cr_idx[row] : -1;
-          a.cr_delta[c] = delta;
-        }
+        a.cr_pick[c] = adapt ? T.cr_idx[row] : -1;
+        a.cr_delta[c] = delta;
       }
     }
     hand_over(i, row, cw, c, T.accept_u[row], prv);
-  }
-  // ---- CR statistics of this half-phase: warp partials -> CTA partial -> (last CTA of the second half-phase)
-  //      the generation's sums in a fixed (phase, cta, warp) order and the p_cr update
-  if (dream && a.cr_fold_part) {
-    __syncwarp();
-    nbar_sync(BAR_PROD, kV3ProdThreads);                   // every producer warp's partials are final
-    if (pw == 0) {
-      const int nv = 2 * a.n_cr;
-      const double* all = reinterpret_cast<const double*>(smem4 + L4.crs);
-      if (lane < nv) {
-        double w = 0.0;
-        for (int q = 0; q < kV3ProdWarps; ++q) w += all[q * 2 * BPM_MAX_CR + lane];
-        a.cr_fold_part[((size_t)a.phase * gridDim.x + blockIdx.x) * 2 * BPM_MAX_CR + lane] = w;
-      }
-      if (a.phase == 1) {
-        __threadfence();
-        __syncwarp();
-        unsigned t = 0;
-        if (lane == 0) t = atomicAdd(a.cr_fold_ticket, 1u);
-        t = __shfl_sync(0xFFFFFFFFu, t, 0);
-        if (t == gridDim.x - 1) {                          // last CTA: phase a's partials are a launch old
-          __threadfence();
-          if (lane < nv) {
-            double w = 0.0;
-            for (unsigned b = 0; b < 2 * gridDim.x; ++b) w += __ldcg(&a.cr_fold_part[(size_t)b * 2 * BPM_MAX_CR + lane]);
-            a.cr_fold_out[lane] = w;
-          }
-          __syncwarp();
-          if (lane == 0) {
-            *a.cr_fold_ticket = 0u;
-            if (a.cr_fold_apply) cr_apply(a.cr_fold_out, a.n_cr, a.cr_fold_dm, a.cr_fold_cnt, a.cr_fold_pcr);
-          }
-        }
-      }
-    }
   }
 }
 

@@ -74,16 +74,6 @@ struct PhaseArgs {
   const double* p_cr;  // [n_cr]
   double* cr_delta;    // [N] per-chain jump statistic of this generation (or untouched)
   int32_t* cr_pick;    // [N] chosen CR index, -1 when no statistic was recorded
-  // CR statistics folded into the fused kernel (fused_gauss_v4_kernel): per-CTA partial sums of both
-  // half-phases land in cr_fold_part[phase][cta][2 BPM_MAX_CR]; the last CTA of the SECOND half-phase adds
-  // them up in (phase, cta) order and -- cr_fold_apply -- applies dream.py:132-140.  nullptr = not folded.
-  double* cr_fold_part;
-  unsigned int* cr_fold_ticket;
-  double* cr_fold_out;       // [2 n_cr] this rank's sums of the generation (what cr_update_kernel writes)
-  double* cr_fold_dm;
-  double* cr_fold_cnt;
-  double* cr_fold_pcr;
-  int32_t cr_fold_apply;
   // workspace
   double* prop;      // [nA][ld] proposals in phase order
   double* lnl_prop;  // [nA]
@@ -94,10 +84,11 @@ struct PhaseArgs {
   unsigned long long* n_acc;
   unsigned long long* n_rej;
   int32_t* nan_flag;
-  // "fly" mode (the lazy-protocol kernels, native RNG): the shuffle of demc.py:84-86 is never materialised.
-  // flip and the Feistel key are functions of (seed, generation) only, so the HOST evaluates them per
-  // generation and passes them by value; kernels turn list positions into chain ids (feistel_perm) and
-  // chain ids into positions (feistel_inv) on the fly -- no O(N) split kernel, no perm / inv arrays.
+  // "fly" mode (EXPERIMENT, fused_small_fly_kernel / small_generations_kernel only): the shuffle of
+  // demc.py:84-86 is never materialised.  flip and the Feistel key are functions of (seed, generation) only, so
+  // the HOST evaluates them per generation and passes them by value; kernels turn list positions into chain
+  // ids (feistel_perm) and chain ids into positions (feistel_inv) on the fly.  Measured slower than a table
+  // lookup in the materialised shuffle, hence opt-in.
   int32_t fly;
   int32_t flip_val;
   int32_t fly_shuffle;     // 0: identity permutation (run_mcmc(shuffle=False))
@@ -128,57 +119,20 @@ __device__ __forceinline__ void store_peers1(const PhaseArgs& a, size_t elem_off
 
 // Phase-list helpers.  self = chains updated in this phase, pool = the other half.
 struct PhaseLists {
-  const int32_t* self;   // nullptr in fly mode (unless packed): entry i = image of list position self_off + i
-  const int32_t* pool;   // nullptr in fly mode:                entry r = image of list position pool_off + r
+  const int32_t* self;
+  const int32_t* pool;
   int32_t n_self, n_pool;
   int32_t skip_self;   // pool position r of chain c means chain r + (r >= c): np.delete(range(N), c)[r]
-  int32_t self_off, pool_off;
 };
-// list entries, materialised or evaluated on the fly (kernels that can be launched in fly mode use these)
-__device__ __forceinline__ int lself(const PhaseArgs& a, const PhaseLists& L, int i) {
-  BPM_CHECK(i >= 0 && i < L.n_self, "self list position", i);
-  int c;
-  if (L.self) c = L.self[i];
-  else {
-    const uint32_t j = (uint32_t)(L.self_off + i);
-    c = a.fly_shuffle ? (int)feistel_perm(a.fk, j) : (int)j;
-  }
-  BPM_CHECK(c >= a.chain_lo && c < a.chain_hi, "own chain id", c);
-  return c;
-}
-__device__ __forceinline__ int lpool(const PhaseArgs& a, const PhaseLists& L, int r) {
-  BPM_CHECK(r >= 0 && r < L.n_pool, "pool position", r);
-  int c;
-  if (L.pool) c = L.pool[r];
-  else {
-    const uint32_t j = (uint32_t)(L.pool_off + r);
-    c = a.fly_shuffle ? (int)feistel_perm(a.fk, j) : (int)j;
-  }
-  BPM_CHECK(c >= 0 && c < a.N, "partner chain id", c);
-  return c;
-}
 // global chain id of pool position r for the chain c being stepped
 __device__ __forceinline__ int pool_chain(const PhaseLists& L, int r, int c) {
   BPM_CHECK(r >= 0 && r < L.n_pool, "pool position", r);
   return L.skip_self ? r + (r >= c ? 1 : 0) : L.pool[r];
 }
 __device__ __forceinline__ PhaseLists phase_lists(const PhaseArgs& a) {
-  const int32_t flipped = a.fly ? a.flip_val : (*a.flip != 0);
-  const int32_t first = (a.phase ^ flipped) == 0;  // true: self is perm[0:nA)
+  const int32_t first = (a.phase ^ (*a.flip != 0)) == 0;  // true: self is perm[0:nA)
   PhaseLists L;
   L.skip_self = 0;
-  L.self_off = first ? 0 : a.nA;
-  L.pool_off = first ? a.nA : 0;
-  if (a.fly) {             // never serial (the engine plans fly mode for the a/b samplers only)
-    L.self = nullptr; L.pool = nullptr;
-    L.n_self = first ? a.nA : a.N - a.nA;
-    L.n_pool = first ? a.N - a.nA : a.nA;
-    if (a.loc_cnt) {
-      L.self = a.loc_list + (first ? 0 : a.nA);
-      L.n_self = a.loc_cnt[first ? 0 : 1];
-    }
-    return L;
-  }
   if (a.serial) {   // samplers.py:275-277: valid_pool_ids = np.delete(range(n_chains), i)
     L.self = a.perm; L.n_self = a.N; L.pool = a.perm; L.n_pool = a.N - 1; L.skip_self = 1;
     if (a.loc_cnt) { L.self = a.loc_list; L.n_self = a.loc_cnt[0]; }
