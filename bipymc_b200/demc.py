@@ -1063,6 +1063,9 @@ class DeMcMpi(object):
         import torch.distributed as dist
         G, nl = self.comm.size, len(self.rank_chain_ids)
         self._flush()          # moments travel with the chains: fold the pending sample first
+        import time as _time
+        torch.cuda.synchronize(self._device)
+        _t0 = _time.perf_counter()
         cuts = [b1 - b0 for b0, b1 in shard_bounds(nl, G)]
         if len(set(len(np.array_split(np.arange(self.n_chains), G)[r]) for r in range(G))) != 1:
             raise RuntimeError("subpop_k needs n_chains divisible by the number of ranks")
@@ -1073,6 +1076,9 @@ class DeMcMpi(object):
         out = torch.empty_like(self._lnl)
         dist.all_to_all_single(out, self._lnl, output_split_sizes=cuts, input_split_sizes=cuts)
         self._lnl.copy_(out)
+        torch.cuda.synchronize(self._device)
+        self.redeal_seconds = getattr(self, "redeal_seconds", 0.0) + (_time.perf_counter() - _t0)
+        self.n_redeals = getattr(self, "n_redeals", 0) + 1
 
     def _allreduce_cr(self):
         torch = _torch()

@@ -172,6 +172,7 @@ def c5full():
                "n_chains": N, "dim": d, "generations_timed": gens,
                "chain_steps_per_s": N * gens / (float(ms.item()) * 1e-3), "ms_per_generation": float(ms.item()) / gens,
                "acceptance_fraction": acc, "rhat_trend": trend, "avg_launch_ms_by_kernel": kms,
+               "redeals": getattr(s, "n_redeals", 0), "redeal_seconds_total": getattr(s, "redeal_seconds", 0.0),
                "torch_peak_alloc_GiB_per_gpu": mem}
         if "likelihood" in kms:
             tf = 2.0 * d * d * chains_per_launch / (kms["likelihood"] * 1e-3) / 1e12
