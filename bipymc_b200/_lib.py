@@ -97,6 +97,7 @@ SIGNATURES = {
     "bpm_ipc_open": (C.c_int, [C.c_int32, C.c_char_p, C.POINTER(C.c_void_p)]),
     "bpm_ipc_close": (C.c_int, [C.c_int32, C.c_void_p]),
     "bpm_set_peers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32]),
+    "bpm_peer_copy": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "bpm_sync_bytes": (C.c_int, [C.POINTER(C.c_uint64)]),
     "bpm_set_sync": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]),
     "bpm_peer_barrier": (C.c_int, [C.c_void_p, C.c_void_p]),

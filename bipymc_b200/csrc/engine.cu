@@ -1128,6 +1128,12 @@ int bpm_ipc_close(int32_t device, void* dev_ptr) {
   CU_TRY(cudaIpcCloseMemHandle(dev_ptr));
   return 0;
 }
+int bpm_peer_copy(int32_t device, void* dst, const void* src, uint64_t bytes, bpm_stream stream) {
+  if (!dst || !src) return fail("null argument");
+  CU_TRY(cudaSetDevice(device));
+  CU_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return 0;
+}
 int bpm_set_peers(bpm_handle h, double* const* peer_X, int32_t n_peers) {
   if (!h) return fail("null handle");
   if (n_peers < 0 || n_peers > BPM_MAX_PEERS) return fail("n_peers must be in [0, 15]");

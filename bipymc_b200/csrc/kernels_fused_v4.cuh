@@ -34,6 +34,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
 
+// Accepted row -> own replica and every peer replica as TMA bulk copies straight out of the proposal tile:
+// one instruction per destination (1 + n_peers of them) from ONE lane, asynchronous -- instead of two 16-byte
+// stores per lane per destination that the deciding warp has to push through its own store path (at 8 GPUs the
+// peer stores cost 17 us of a 141 us launch, profiles/r2/r2k_bench_n8_nopeerstores.json).
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(dst), "r"(smem_addr(src_smem)), "r"(bytes) : "memory");
+}
+
 struct V4Layout {
   size_t wf, mus, gam, cdf, crv, thr, P, acc_u, cid, land, scratch, bars, total;   // byte offsets
   int land_rows;
@@ -115,7 +124,6 @@ fused_gauss_v4_kernel(const PhaseArgs a, const GaussArgs g) {
     load_W_fragments(tb.Ws, tb.mus, g.W, g.mu, d, g.r, threadIdx.x, kV3ConsThreads);
     nbar_sync(BAR_CONS, kV3ConsThreads);
     unsigned n_acc = 0, n_rej = 0;
-    const WbMap mp = wb_map(d, lane);
     const bool decider = (lane & 3) == 0;
     const int my_row = 8 * warp + (lane >> 2);
     for (int i = 0; i < n_my; ++i) {
@@ -137,14 +145,27 @@ fused_gauss_v4_kernel(const PhaseArgs a, const GaussArgs g) {
       unsigned am = __ballot_sync(0xFFFFFFFFu, c >= 0 && acc);
       n_acc += __popc(am);
       n_rej += __popc(__ballot_sync(0xFFFFFFFFu, c >= 0 && !acc));
-      while (am) {                                   // ~1 accepted row per m-tile
-        const int row = 8 * warp + ((__ffs(am) - 1) >> 2);
-        am &= am - 1;
-        cons_store_row(a, P + row * pld, row_c[row], mp);
+      if (am) {                                      // ~1 accepted row per m-tile
+        if (lane == 0) {
+          // the rows were written through the generic proxy (producers' st.shared, ordered by the named barrier)
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          const uint32_t row_bytes = (uint32_t)(d * 8);
+          while (am) {
+            const int row = 8 * warp + ((__ffs(am) - 1) >> 2);
+            am &= am - 1;
+            const size_t ox = (size_t)row_c[row] * a.ld;
+            const double* src = P + row * pld;
+            bulk_s2g(a.X + ox, src, row_bytes);
+            for (int p = 0; p < a.n_peers; ++p) bulk_s2g(a.peers[p] + ox, src, row_bytes);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the tile rows have been read
+        }
+        __syncwarp();
       }
-      __syncwarp();                                  // the tile reads above precede the m-tile's release
-      if (lane == 0) mbar_arrive(DONEm + warp);
+      if (lane == 0) mbar_arrive(DONEm + warp);      // (lane 0's tile reads, the last of the warp's, are done)
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every row has reached memory
     if (lane == 0) {
       if (n_acc) atomicAdd(a.n_acc, (unsigned long long)n_acc);
       if (n_rej) atomicAdd(a.n_rej, (unsigned long long)n_rej);

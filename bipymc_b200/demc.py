@@ -491,12 +491,60 @@ class DeMcMpi(object):
             self._X = None
             lib.bpm_dev_free(self._device_index, C.c_void_p(self._own_X_ptr))
             self._own_X_ptr = None
+        if getattr(self, "_ipc", None):
+            self._X = self._lnl = self._mean_t = self._m2_t = None
+            self._release_ipc()
+
+    def _ipc_alloc(self, name, shape):
+        """Sub-population mode: a float64 device array every OTHER island can read (plain cudaMalloc block, IPC
+        handle exchanged once): the re-deal pulls chains straight out of the peers' arrays over NVLink.  Returns
+        the torch view; self._ipc[name] = (own pointer, {rank: mapped pointer})."""
+        torch = _torch()
+        import torch.distributed as dist
+        lib = self._libh
+        nbytes = int(np.prod(shape)) * 8
+        ptr = C.c_void_p()
+        _lib.check(lib.bpm_dev_alloc(self._device_index, nbytes, C.byref(ptr)))
+        t = self._wrap_device(ptr.value, shape)
+        t.zero_()
+        hbuf = C.create_string_buffer(64)
+        _lib.check(lib.bpm_ipc_export(self._device_index, ptr, hbuf))
+        handles = [None] * self.comm.size
+        dist.all_gather_object(handles, bytes(hbuf.raw))
+        peers = {}
+        for r, hb in enumerate(handles):
+            if r == self.comm.rank:
+                continue
+            q = C.c_void_p()
+            if lib.bpm_ipc_open(self._device_index, C.create_string_buffer(hb, 64), C.byref(q)) != 0:
+                self._ipc_ok = False
+                break
+            peers[r] = q.value
+        self._ipc[name] = (ptr.value, peers)
+        return t
+
+    def _release_ipc(self):
+        lib = getattr(self, "_libh", None)
+        for name, (own, peers) in list(getattr(self, "_ipc", {}).items()):
+            for q in peers.values():
+                lib.bpm_ipc_close(self._device_index, C.c_void_p(q))
+            lib.bpm_dev_free(self._device_index, C.c_void_p(own))
+        self._ipc = {}
 
     def _alloc_population(self, N, ld):
         """[N, ld] float64 population replica.  Sharded runs with exchange="p2p" take it from
         bpm_dev_alloc (a plain cudaMalloc block, so its IPC handle can be opened by the peers)
         and register every other rank's replica with the engine (bpm_set_peers)."""
         torch = _torch()
+        if self._subpop:
+            if getattr(self, "_ipc", None):
+                torch.cuda.synchronize(self._device)
+                import torch.distributed as dist
+                dist.barrier()
+                self._X = self._lnl = self._mean_t = self._m2_t = None
+                self._release_ipc()
+            self._ipc, self._ipc_ok = {}, True
+            return self._ipc_alloc("X", (N, ld))
         if not self._sharded or self._exchange != "p2p":
             return torch.zeros((N, ld), dtype=torch.float64, device=self._device)
         import torch.distributed as dist
@@ -654,10 +702,16 @@ class DeMcMpi(object):
             import torch.distributed as dist
             torch.cuda.synchronize(self._device)
             dist.barrier()          # nobody steps before every replica holds the initial states
-        self._lnl = torch.zeros((N,), dtype=torch.float64, device=self._device)
         self._pending = 0
-        self._mean_t = self._X[lo:hi].clone()
-        self._m2_t = torch.zeros((nl, ld), dtype=torch.float64, device=self._device)
+        if self._subpop:       # every array that travels in a re-deal is readable by the other islands
+            self._lnl = self._ipc_alloc("lnl", (N,))
+            self._mean_t = self._ipc_alloc("mean", (nl, ld))
+            self._mean_t.copy_(self._X[lo:hi])
+            self._m2_t = self._ipc_alloc("m2", (nl, ld))
+        else:
+            self._lnl = torch.zeros((N,), dtype=torch.float64, device=self._device)
+            self._mean_t = self._X[lo:hi].clone()
+            self._m2_t = torch.zeros((nl, ld), dtype=torch.float64, device=self._device)
         self._hist = HistoryStore(nl, d, ld, self._device, policy=self._history_policy,
                                   chunk_bytes=self._chunk_bytes, reserve_rows=self._reserve_rows)
         self._hist._current = self._X[lo:hi]
@@ -1069,6 +1123,31 @@ class DeMcMpi(object):
         cuts = [b1 - b0 for b0, b1 in shard_bounds(nl, G)]
         if len(set(len(np.array_split(np.arange(self.n_chains), G)[r]) for r in range(G))) != 1:
             raise RuntimeError("subpop_k needs n_chains divisible by the number of ranks")
+        if getattr(self, "_ipc_ok", False) and nl % G == 0 and all(k in self._ipc for k in ("X", "lnl", "mean", "m2")):
+            # pull: chunk i of my new arrays = block `rank` of island i's arrays, copied over NVLink by the copy
+            # engines (cudaMemcpyAsync on IPC-mapped peer memory).  Two barriers: everyone has stopped stepping
+            # before anyone reads, everyone has finished reading before anyone overwrites.
+            lib, cut, r = self._libh, nl // G, self.comm.rank
+            dist.barrier()
+            outs = []
+            for name, t in (("X", self._X), ("mean", self._mean_t), ("m2", self._m2_t), ("lnl", self._lnl)):
+                out = torch.empty_like(t)
+                row_bytes = (t.shape[1] if t.dim() == 2 else 1) * 8
+                own, peers = self._ipc[name]
+                for i in range(G):
+                    src = (own if i == r else peers[i]) + r * cut * row_bytes
+                    _lib.check(lib.bpm_peer_copy(self._device_index, C.c_void_p(out.data_ptr() + i * cut * row_bytes),
+                                                 C.c_void_p(src), cut * row_bytes, self._stream()))
+                outs.append((t, out))
+            torch.cuda.synchronize(self._device)
+            dist.barrier()
+            for t, out in outs:
+                t.copy_(out)
+            del outs
+            torch.cuda.synchronize(self._device)
+            self.redeal_seconds = getattr(self, "redeal_seconds", 0.0) + (_time.perf_counter() - _t0)
+            self.n_redeals = getattr(self, "n_redeals", 0) + 1
+            return
         for t in (self._X, self._mean, self._m2):
             out = torch.empty_like(t)
             dist.all_to_all_single(out, t.contiguous(), output_split_sizes=cuts, input_split_sizes=cuts)

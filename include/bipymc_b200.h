@@ -218,6 +218,10 @@ int bpm_ipc_export(int32_t device, const void* dev_ptr, unsigned char handle64[6
 int bpm_ipc_open(int32_t device, const unsigned char handle64[64], void** dev_ptr);
 int bpm_ipc_close(int32_t device, void* dev_ptr);
 int bpm_set_peers(bpm_handle h, double* const* peer_X, int32_t n_peers);
+/* Plain asynchronous copy between two device pointers of this process' address space, either of which may
+ * be a peer allocation mapped with bpm_ipc_open (NVLink copy engines): the sub-population re-deal pulls its
+ * chains out of the other islands with it (NCCL's all-to-all moved the same 30 GB per rank at ~20 GB/s). */
+int bpm_peer_copy(int32_t device, void* dst, const void* src, uint64_t bytes, bpm_stream stream);
 
 /* Peer-memory barrier: the comm.Barrier() of demc.py:135 and the synchronisation implied by the two
  * Allgathers (demc.py:93,116) without a collective library on the path.  Every rank allocates one sync
