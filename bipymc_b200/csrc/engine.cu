@@ -326,6 +326,7 @@ struct bpm_engine {
     const int N = cfg.n_chains;
     if (fly && !rp && !serial()) return 0;      // nothing to materialise (unsharded d <= 4 only, see fly_plan)
     prof_begin(0, s);
+    bool inv_on_the_fly = false;
     if (serial()) {
       bpm::identity_split_kernel<<<cdiv(N, 256), 256, 0, s>>>(perm, inv, flip, N);
     } else if (rp) {
@@ -334,13 +335,21 @@ struct bpm_engine {
       if (inv) bpm::invert_perm_kernel<<<cdiv(N, 256), 256, 0, s>>>(perm, inv, N);
     } else {
       bpm::RngCtx rng = bpm::make_rng(cfg.seed, (uint64_t)st->hist_len);
-      bpm::split_native_kernel<<<cdiv(N, 256), 256, 0, s>>>(perm, inv, flip, N, cfg.shuffle, cfg.flip, rng);
+      // packed handles read list positions from the INVERSE permutation evaluated on the fly (ListPos below), so
+      // the split kernel does not scatter an O(N) inverse array any more
+      bpm::split_native_kernel<<<cdiv(N, 256), 256, 0, s>>>(perm, packed() ? nullptr : inv, flip, N, cfg.shuffle,
+                                                            cfg.flip, rng);
+      inv_on_the_fly = packed();
     }
     if (packed()) {
       const int nblk = cdiv(cfg.chain_hi - cfg.chain_lo, bpm::kCompactBlock);
       bpm::ListPos pos;
       memset(&pos, 0, sizeof(pos));
       pos.inv = inv;
+      if (inv_on_the_fly) {         // native shuffle: the key is a function of (seed, generation), evaluated here
+        pos.inv = nullptr; pos.fly = 1; pos.shuffle = cfg.shuffle ? 1 : 0;
+        if (cfg.shuffle) pos.fk = bpm::make_feistel(bpm::make_rng(cfg.seed, (uint64_t)st->hist_len), (uint32_t)N);
+      }
       bpm::compact_count_kernel<<<nblk, bpm::kCompactThreads, 0, s>>>(pos, nA, cfg.chain_lo, cfg.chain_hi, cmp_blk);
       bpm::compact_scan_kernel<<<1, 1024, 0, s>>>(cmp_blk, nblk, cmp_blk + 2 * nblk, loc_cnt);
       bpm::compact_write_kernel<<<nblk, bpm::kCompactThreads, 0, s>>>(pos, nA, cfg.chain_lo, cfg.chain_hi,

@@ -1,9 +1,8 @@
-# round 2, 2-GPU job: TMA bulk stores of accepted rows (own + peer + host-mapped replicas), NVLink-copy re-deal
+# round 2, second 8-GPU job: bulk-store peer exchange + on-the-fly inverse in the list packing; C5 with the NVLink-copy re-deal
 set -x
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2m_pytest.log 2>&1; tail -6 gpurun_out/r2m_pytest.log
-timeout 300 python bench.py --steps 50 --warmup 3 --no-cpu --no-stationary > gpurun_out/r2m_bench.json 2> gpurun_out/r2m_bench.err; tail -c 1500 gpurun_out/r2m_bench.json; tail -3 gpurun_out/r2m_bench.err
-timeout 900 $TR --nproc-per-node 2 --master-port 29551 tools/multigpu_check.py > gpurun_out/r2m_mg.log 2>&1; grep -v "^\*\|OMP_NUM\|^$" gpurun_out/r2m_mg.log | tail -18
-timeout 600 $TR --nproc-per-node 2 --master-port 29552 bench.py --gpus 2 --steps 50 --warmup 5 --no-stationary > gpurun_out/r2m_bench_n2.json 2> gpurun_out/r2m_bench_n2.err; tail -c 1800 gpurun_out/r2m_bench_n2.json; tail -5 gpurun_out/r2m_bench_n2.err
-C5_PER_GPU=1250000 C5_GENS=10 C5_K=5 timeout 600 $TR --nproc-per-node 2 --master-port 29571 tools/bench_configs.py c5full > gpurun_out/r2m_c5_n2.txt 2>&1; grep config gpurun_out/r2m_c5_n2.txt | cut -c1-1700; tail -3 gpurun_out/r2m_c5_n2.txt | cut -c1-300
+timeout 600 $TR --nproc-per-node 8 --master-port 29561 bench.py --gpus 8 --steps 50 --warmup 5 > gpurun_out/r2n_bench_n8.json 2> gpurun_out/r2n_bench_n8.err; tail -c 2200 gpurun_out/r2n_bench_n8.json; tail -4 gpurun_out/r2n_bench_n8.err
+timeout 900 $TR --nproc-per-node 8 --master-port 29562 tools/bench_configs.py c5full > gpurun_out/r2n_c5full.txt 2>&1; grep config gpurun_out/r2n_c5full.txt | cut -c1-1800; tail -3 gpurun_out/r2n_c5full.txt | cut -c1-300
+timeout 500 $TR --nproc-per-node 4 --master-port 29564 bench.py --gpus 4 --steps 50 --warmup 5 --no-stationary > gpurun_out/r2n_bench_n4.json 2> gpurun_out/r2n_bench_n4.err; tail -c 1200 gpurun_out/r2n_bench_n4.json
+timeout 600 $TR --nproc-per-node 8 --master-port 29565 tools/multigpu_check.py > gpurun_out/r2n_mg8.log 2>&1; grep -v "^\*\|OMP_NUM\|^$" gpurun_out/r2n_mg8.log | tail -6
