@@ -335,11 +335,13 @@ struct bpm_engine {
       if (inv) bpm::invert_perm_kernel<<<cdiv(N, 256), 256, 0, s>>>(perm, inv, N);
     } else {
       bpm::RngCtx rng = bpm::make_rng(cfg.seed, (uint64_t)st->hist_len);
-      // packed handles read list positions from the INVERSE permutation evaluated on the fly (ListPos below), so
-      // the split kernel does not scatter an O(N) inverse array any more
-      bpm::split_native_kernel<<<cdiv(N, 256), 256, 0, s>>>(perm, packed() ? nullptr : inv, flip, N, cfg.shuffle,
+      // sharded handles read list positions from the INVERSE permutation evaluated on the fly (ListPos below), so
+      // the split kernel does not scatter an O(N) inverse array there any more
+      // (sharded handles only: there the scatter is O(N) against O(n_local) evaluations.  On an unsharded d <= 4
+      // handle the evaluations cost more than the scatter: 122 vs 91 us per line-fit generation, profiles/r2/r2o_*.)
+      bpm::split_native_kernel<<<cdiv(N, 256), 256, 0, s>>>(perm, sharded() ? nullptr : inv, flip, N, cfg.shuffle,
                                                             cfg.flip, rng);
-      inv_on_the_fly = packed();
+      inv_on_the_fly = sharded();
     }
     if (packed()) {
       const int nblk = cdiv(cfg.chain_hi - cfg.chain_lo, bpm::kCompactBlock);
