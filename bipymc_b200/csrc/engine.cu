@@ -335,13 +335,12 @@ struct bpm_engine {
       if (inv) bpm::invert_perm_kernel<<<cdiv(N, 256), 256, 0, s>>>(perm, inv, N);
     } else {
       bpm::RngCtx rng = bpm::make_rng(cfg.seed, (uint64_t)st->hist_len);
-      // sharded handles read list positions from the INVERSE permutation evaluated on the fly (ListPos below), so
-      // the split kernel does not scatter an O(N) inverse array there any more
-      // (sharded handles only: there the scatter is O(N) against O(n_local) evaluations.  On an unsharded d <= 4
-      // handle the evaluations cost more than the scatter: 122 vs 91 us per line-fit generation, profiles/r2/r2o_*.)
-      bpm::split_native_kernel<<<cdiv(N, 256), 256, 0, s>>>(perm, sharded() ? nullptr : inv, flip, N, cfg.shuffle,
-                                                            cfg.flip, rng);
-      inv_on_the_fly = sharded();
+      // (Evaluating the INVERSE permutation on the fly inside the list packing instead of scattering `inv` was
+      // measured and dropped: the split bucket went 31 -> 41 us at 8 GPUs and 34 -> 63 us at 4, 91 -> 122 us per
+      // line-fit generation on one -- profiles/r2/r2n_*, r2o_*.  ListPos keeps the hook.)  A rank only ever looks
+      // up the list positions of ITS chains, so the scatter is limited to [chain_lo, chain_hi).
+      bpm::split_native_kernel<<<cdiv(N, 256), 256, 0, s>>>(perm, inv, flip, N, cfg.shuffle, cfg.flip, rng,
+                                                            cfg.chain_lo, cfg.chain_hi);
     }
     if (packed()) {
       const int nblk = cdiv(cfg.chain_hi - cfg.chain_lo, bpm::kCompactBlock);

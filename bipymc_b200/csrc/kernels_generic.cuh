@@ -17,7 +17,8 @@ constexpr int kThreads = 256;
 
 // ---- demc.py:81-100: flip coin + shuffled split (native RNG) ----------------------
 __global__ void split_native_kernel(int32_t* __restrict__ perm, int32_t* __restrict__ inv,
-                                    int32_t* __restrict__ flip, int N, int shuffle, double flip_p, RngCtx rng) {
+                                    int32_t* __restrict__ flip, int N, int shuffle, double flip_p, RngCtx rng,
+                                    int inv_lo, int inv_hi) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j == 0) {
     Philox4 q = draw4(rng, 0xFFFFFFFFu, RNG_GEN, 0);
@@ -32,7 +33,7 @@ __global__ void split_native_kernel(int32_t* __restrict__ perm, int32_t* __restr
   int32_t c = j;
   if (shuffle) c = (int32_t)feistel_perm(fkey, (uint32_t)j);
   perm[j] = c;
-  if (inv) inv[c] = j;        // list position of chain c (used to pack the phase lists in chain order)
+  if (inv && c >= inv_lo && c < inv_hi) inv[c] = j;   // list position of chain c (packs the phase lists in chain order)
 }
 __global__ void invert_perm_kernel(const int32_t* __restrict__ perm, int32_t* __restrict__ inv, int N) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;

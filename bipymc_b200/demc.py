@@ -213,6 +213,23 @@ class HistoryStore(object):
         base = last.data_ptr() - (self.length - used) * self.row_bytes
         return base, last.shape[0] - used
 
+    def reserve_contiguous(self, rows):
+        """Like reserve(), but every stored row AND the next `rows` rows sit in ONE block, so the returned base is
+        a real array base: replay steps walk the whole stored history of a chain (exact np.std, step.cuh:
+        cr_variance) and must not cross a chunk boundary through the synthetic base of reserve()."""
+        if self.policy != "full":
+            return None, rows
+        torch = self._torch
+        used = self._used_in_last()
+        if len(self.chunks) == 1 and self.chunks[0].shape[0] - used >= 1:
+            return self.chunks[0].data_ptr(), self.chunks[0].shape[0] - used
+        whole = self.tensor()                                   # coalesced [stored, n_local, ld]
+        blk = torch.empty((self.stored + max(rows, self.reserve_rows, 1), self.n_local, self.ld), dtype=torch.float64,
+                          device=self.device)
+        blk[:self.stored].copy_(whole)
+        self.chunks = [blk]
+        return blk.data_ptr(), blk.shape[0] - self.stored
+
     def advance(self, rows):
         self.length += rows
         if self.policy == "full":
@@ -1002,7 +1019,10 @@ class DeMcMpi(object):
         while k_gen < G:
             if self._pending and self._hist.will_grow():
                 self._flush()      # the pending row belongs to the chunk that is full now
-            base, avail = self._hist.reserve(G - k_gen)
+            if replay is not None:
+                base, avail = self._hist.reserve_contiguous(G - k_gen)
+            else:
+                base, avail = self._hist.reserve(G - k_gen)
             avail = min(avail, G - k_gen)
             if self.checkpoint > 0:
                 avail = min(avail, self.checkpoint - (k_gen % self.checkpoint))
@@ -1388,5 +1408,8 @@ class DeMcMpi(object):
         """hist: (T, N, dim) array of every chain's history (what load_state reads)."""
         hist = np.asarray(hist, dtype=float)
         assert hist.shape[1] == self.n_chains and hist.shape[2] == self.dim
-        lo, hi = self._local_range()
+        if self._subpop:      # an island's rows inside the job-wide history are its GLOBAL chain ids
+            lo, hi = int(self.rank_chain_ids[0]), int(self.rank_chain_ids[-1]) + 1
+        else:
+            lo, hi = self._local_range()
         self._set_population(hist[-1], history=hist[:, lo:hi, :])
