@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/bipymc_b200.h"
@@ -61,6 +62,37 @@ struct bpm_engine {
   int32_t* loc_cnt = nullptr;    // [2]
   int32_t* phase_cnt = nullptr;  // [1] rows of the phase being stepped (selected from loc_cnt on the device)
   int32_t* cmp_blk = nullptr;    // [2][nblk][2] block counts / offsets
+  // Second set of split buffers + a side stream: inside a multi-generation call the shuffle / list packing of
+  // generation g+1 -- functions of (seed, generation) only -- are enqueued on the side stream while generation g
+  // runs, so they execute in the tail of its last fused launch instead of between two launches (11 us of a
+  // 250 us generation on one GPU, ~30 us of 340 on eight).  BIPYMC_B200_NO_SIDE=1 switches it off.
+  struct SplitBuf { int32_t *perm = nullptr, *flip = nullptr, *inv = nullptr, *loc_list = nullptr, *loc_cnt = nullptr,
+                             *cmp_blk = nullptr; } alt;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_split = nullptr, ev_done = nullptr;
+  void swap_split() {
+    std::swap(perm, alt.perm); std::swap(flip, alt.flip); std::swap(inv, alt.inv);
+    std::swap(loc_list, alt.loc_list); std::swap(loc_cnt, alt.loc_cnt); std::swap(cmp_blk, alt.cmp_blk);
+  }
+  int side_setup() {
+    if (side) return 0;
+    const int N = cfg.n_chains;
+    CU_TRY(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&ev_split, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+    CU_TRY(cudaMalloc(&alt.perm, sizeof(int32_t) * N));
+    CU_TRY(cudaMalloc(&alt.flip, sizeof(int32_t)));
+    CU_TRY(cudaMemset(alt.flip, 0, sizeof(int32_t)));
+    if (packed()) {
+      const int nblk = cdiv(cfg.chain_hi - cfg.chain_lo, bpm::kCompactBlock);
+      CU_TRY(cudaMalloc(&alt.inv, sizeof(int32_t) * N));
+      CU_TRY(cudaMalloc(&alt.loc_list, sizeof(int32_t) * N));
+      CU_TRY(cudaMalloc(&alt.loc_cnt, sizeof(int32_t) * 2));
+      CU_TRY(cudaMalloc(&alt.cmp_blk, sizeof(int32_t) * 4 * nblk));
+    }
+    return 0;
+  }
   bool serial() const { return cfg.algo == BPM_ALGO_DEMC_SERIAL; }
   bool sharded() const { return cfg.chain_lo != 0 || cfg.chain_hi != cfg.n_chains; }
   // packed, chain-ordered phase lists: always when sharded; unsharded for the 16/24/32-byte rows
@@ -152,6 +184,10 @@ struct bpm_engine {
 
   ~bpm_engine() {
     cudaFree(inv); cudaFree(loc_list); cudaFree(loc_cnt); cudaFree(phase_cnt); cudaFree(cmp_blk); cudaFree(cr_ticket);
+    cudaFree(alt.perm); cudaFree(alt.flip); cudaFree(alt.inv); cudaFree(alt.loc_list); cudaFree(alt.loc_cnt);
+    cudaFree(alt.cmp_blk);
+    if (side) cudaStreamDestroy(side);
+    if (ev_start) { cudaEventDestroy(ev_start); cudaEventDestroy(ev_split); cudaEventDestroy(ev_done); }
     cudaFree(perm); cudaFree(flip); cudaFree(prop); cudaFree(lnl_prop); cudaFree(cr_delta);
     cudaFree(cr_pick); cudaFree(p_cr); cudaFree(cr_dm); cudaFree(cr_cnt); cudaFree(cr_part); cudaFree(cr_block);
     cudaFree(counters); cudaFree(nan_flag); cudaFree(tparams); cudaFree(hX); cudaFree(hL); cudaFree(hMean); cudaFree(hM2);
@@ -595,14 +631,14 @@ struct bpm_engine {
 
   template <bool REPLAY>
   int generation(bpm_state* st, int64_t k_gen, const bpm_replay* rp, const bpm_trace_out* tr,
-                 cudaStream_t s) {
+                 cudaStream_t s, bool split_ready = false) {
     // lazy protocol: the v3 kernel folds the row the previous generation left pending and leaves its own
     // pending; every other path (and a replay step, whose exact np.std walks the stored history) needs
     // the row materialised first
     const bool lazy = lazy_plan();
     const bool fly = !REPLAY && fly_plan();
     if (st->pending && (!lazy || REPLAY)) BPM_TRY(flush(st, s));
-    BPM_TRY(begin(st, rp, s, fly));
+    if (!split_ready) BPM_TRY(begin(st, rp, s, fly));
     BPM_TRY(phase<REPLAY>(st, k_gen, 0, rp, tr, s, lazy, fly));
     if (!serial()) {
       if (sync_on) BPM_TRY(peer_barrier(s));          // every rank's phase-a rows are in every replica
@@ -827,8 +863,38 @@ int bpm_step_generations(bpm_handle h, bpm_state* st, int64_t k_gen0, int32_t n_
     BPM_TRY(h->try_small_generations(st, k_gen0, n_gen, (cudaStream_t)stream, &done));
     if (done) return 0;
   }
-  for (int g = 0; g < n_gen; ++g)
-    BPM_TRY(h->generation<false>(st, k_gen0 + g, nullptr, nullptr, (cudaStream_t)stream));
+  static const bool no_side = [] {
+    const char* e = getenv("BIPYMC_B200_NO_SIDE");
+    return e && e[0] == '1';
+  }();
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool side_ok = !no_side && n_gen >= 2 && !h->serial() && !h->fly_plan();
+  if (side_ok) {
+    BPM_TRY(h->side_setup());
+    CU_TRY(cudaEventRecord(h->ev_start, s));
+  }
+  bool have_next = false;        // the split of the generation about to run was prepared on the side stream
+  for (int g = 0; g < n_gen; ++g) {
+    if (have_next) {
+      h->swap_split();                                   // current <- the buffers the side stream filled
+      CU_TRY(cudaStreamWaitEvent(s, h->ev_split, 0));
+    }
+    const bool ready = have_next;
+    have_next = side_ok && g + 1 < n_gen;
+    if (have_next) {
+      // generation g+1's shuffle into the other buffer set, free once generation g-1 (its last user) is done
+      CU_TRY(cudaStreamWaitEvent(h->side, g >= 1 ? h->ev_done : h->ev_start, 0));
+      bpm_state nxt = *st;
+      nxt.hist_len = st->hist_len + 1;
+      h->swap_split();
+      const int rc = h->begin(&nxt, nullptr, h->side, false);
+      h->swap_split();
+      if (rc) return rc;
+      CU_TRY(cudaEventRecord(h->ev_split, h->side));
+    }
+    BPM_TRY(h->generation<false>(st, k_gen0 + g, nullptr, nullptr, s, ready));
+    if (have_next) CU_TRY(cudaEventRecord(h->ev_done, s));
+  }
   return 0;
 }
 
