@@ -344,7 +344,9 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": per_kind_bytes[kinds[dom]] * chains_per_launch,
                 "avg_launch_ms": avg_ms,
                 "bytes_per_chain_step": per_kind_bytes[kinds[dom]], "peak_source": peak_src,
-                "share_of_step": ms_k[dom] / max(sum(ms_k), 1e-12)}
+                # share of the event pass's wall time (the shuffle of generation g+1 runs on a side stream under
+                # generation g, so the per-kind times do not add up to the step)
+                "share_of_step": ms_k[dom] / max(ms_prof, 1e-12)}
         if kinds[dom] == "likelihood":
             fl = 2.0 * d * d * chains_per_launch / (avg_ms * 1e-3) / 1e12
             roof.update({"fp64_tflops": fl})
@@ -476,7 +478,8 @@ def run_ours(args):
                            "timing": "value / ms_per_step: K generations with only the engine's launches on the "
                                      "stream; kernel_ms / roofline: the next K generations with CUDA events around "
                                      "every launch (ms_per_step_event_pass); gpu_launches counted in the event "
-                                     "pass, the timed pass launches the same kernels",
+                                     "pass, the timed pass launches the same kernels; kernel_ms['split'] is measured "
+                                     "on the side stream and includes its wait for free SMs under the fused launch",
                            "init": "theta_0 + N(0, diag(Sigma)), %d untimed setup generations" % SETUP_GENS,
                            "rng": "philox4x32-10 seed 42", "parallelism": "chains sharded x%d" % world,
                            "exchange": ("none (1 GPU)" if world == 1 else
