@@ -1268,6 +1268,9 @@ inline int launch_fused_v3(const PhaseArgs& a, const GaussArgs& g, int grid, siz
 }
 
 // ---- d <= 4 analytic targets: one thread per chain ------------------------------------
+#ifndef BPM_LINEFIT_LANES4
+#define BPM_LINEFIT_LANES4 0
+#endif
 // One chain-step of a d <= 4 target, start to finish (draws, proposal, likelihood, Metropolis decision,
 // state / moments / history update).  pool_id(r) maps a pool position to a global chain id: a lookup in the
 // materialised shuffle for the per-phase kernel, the Feistel permutation evaluated on the fly for the
@@ -1391,7 +1394,10 @@ __global__ void __launch_bounds__(128) fused_small_kernel(const PhaseArgs a, con
     __syncthreads();
   }
   const PhaseLists L = phase_lists(a);
-  constexpr int SUBS = TARGET == BPM_TARGET_LINEFIT ? 4 : 1;       // lanes per chain
+  // lanes per chain.  Four lanes per line-fit chain (one partial sum of the likelihood each) were measured and
+  // are NOT used: the redundant draws / proposal of the three extra lanes cost more issue slots than the shorter
+  // likelihood saves -- 73 -> 86 us per generation at 10^5 chains (profiles/r2/r2r_secondary.txt).
+  constexpr int SUBS = (BPM_LINEFIT_LANES4 && TARGET == BPM_TARGET_LINEFIT) ? 4 : 1;
   const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / SUBS;
   const int sub = threadIdx.x % SUBS;
   bool valid = gid < L.n_self;
@@ -1665,9 +1671,9 @@ inline int try_fused_phase(const TargetView& tv, const PhaseArgs& a, cudaStream_
       fused_small_kernel<REPLAY, BPM_TARGET_BANANA><<<grid, 128, 0, s>>>(a, tv);
     else if (tv.target == BPM_TARGET_BIMODAL)
       fused_small_kernel<REPLAY, BPM_TARGET_BIMODAL><<<grid, 128, 0, s>>>(a, tv);
-    else                                            // four lanes per chain
+    else
       fused_small_kernel<REPLAY, BPM_TARGET_LINEFIT>
-          <<<(4 * a.nA + 127) / 128, 128, sizeof(double) * 3 * tv.linefit_M, s>>>(a, tv);
+          <<<((BPM_LINEFIT_LANES4 ? 4 : 1) * a.nA + 127) / 128, 128, sizeof(double) * 3 * tv.linefit_M, s>>>(a, tv);
     if (cudaGetLastError() != cudaSuccess) return 1;
     *done = 1;
     return 0;

@@ -84,6 +84,17 @@ __device__ __forceinline__ double linefit_lnl(const double* x, const double* y, 
                                               int M, double m, double b, double lnf) {
   if (!linefit_prior_ok(m, b, lnf)) return -INFINITY;
   const double e2 = exp(__dmul_rn(2.0, lnf));
+#ifdef BPM_LINEFIT_SEQ      // A/B: the sequential sum of round 1, unrolled by five
+  double sq = 0.0;
+#pragma unroll 5
+  for (int i = 0; i < M; ++i) {
+    double model = __dadd_rn(__dmul_rn(m, x[i]), b);
+    double inv = __ddiv_rn(1.0, __dadd_rn(__dmul_rn(yerr[i], yerr[i]), __dmul_rn(__dmul_rn(model, model), e2)));
+    double r = __dsub_rn(y[i], model);
+    sq += __dsub_rn(__dmul_rn(__dmul_rn(r, r), inv), log(inv));
+  }
+  return 0.0 + -0.5 * sq;
+#endif
   double p[4] = {0.0, 0.0, 0.0, 0.0};
   for (int i = 0; i < M; ++i) {            // the four partials advance together: ILP 4 for one thread
     double model = __dadd_rn(__dmul_rn(m, x[i]), b);

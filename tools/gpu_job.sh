@@ -1,11 +1,6 @@
-# round 2, final 1-GPU artefacts of the shipped tree
+# round 2, 1-GPU A/B: line-fit likelihood summation form (four interleaved partials vs the sequential sum unrolled by five)
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2r_pytest.log 2>&1; tail -4 gpurun_out/r2r_pytest.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2r_smoke.log 2>&1; tail -2 gpurun_out/r2r_smoke.log
-timeout 600 python bench.py > gpurun_out/r2r_bench.json 2> gpurun_out/r2r_bench.err; tail -c 2800 gpurun_out/r2r_bench.json; tail -3 gpurun_out/r2r_bench.err
-timeout 400 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/r2r_bench_ref.json 2> gpurun_out/r2r_bench_ref.err; tail -c 500 gpurun_out/r2r_bench_ref.json
-timeout 400 python tools/bench_configs.py c3 c4 demc100 c5shape > gpurun_out/r2r_secondary.txt 2>&1; cat gpurun_out/r2r_secondary.txt
-BIPYMC_B200_LIB=$PWD/build_ab/lib_checks.so timeout 300 python tools/sanitize_case.py > gpurun_out/r2r_checked_build.log 2>&1; tail -5 gpurun_out/r2r_checked_build.log
-python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e --no-stationary > gpurun_out/r2r_plain.log 2>&1 && timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2r_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e --no-stationary > gpurun_out/r2r_ncu_l.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_gauss_v4 -s 130 -c 1 -o gpurun_out/prof_r2r -f python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-stationary > gpurun_out/r2r_ncu_full.log 2>&1; tail -2 gpurun_out/r2r_ncu_full.log
+timeout 300 python tools/bench_configs.py c4 c3 > gpurun_out/r2s_c4_partials.txt 2>&1; cat gpurun_out/r2s_c4_partials.txt
+BIPYMC_B200_LIB=$PWD/build_ab/lib_linefitseq.so timeout 300 python tools/bench_configs.py c4 > gpurun_out/r2s_c4_seq.txt 2>&1; cat gpurun_out/r2s_c4_seq.txt
+timeout 600 python -m pytest tests -m gpu -x -q -k "linefit or small_d or replay" > gpurun_out/r2s_pytest.log 2>&1; tail -3 gpurun_out/r2s_pytest.log
