@@ -1268,19 +1268,13 @@ inline int launch_fused_v3(const PhaseArgs& a, const GaussArgs& g, int grid, siz
 }
 
 // ---- d <= 4 analytic targets: one thread per chain ------------------------------------
-#ifndef BPM_LINEFIT_LANES4
-#define BPM_LINEFIT_LANES4 0
-#endif
 // One chain-step of a d <= 4 target, start to finish (draws, proposal, likelihood, Metropolis decision,
 // state / moments / history update).  pool_id(r) maps a pool position to a global chain id: a lookup in the
 // materialised shuffle for the per-phase kernel, the Feistel permutation evaluated on the fly for the
 // persistent multi-generation kernel.  Returns 1 when the proposal was accepted.
-// SUBS = 4 (line fit only): four consecutive lanes step the SAME chain -- identical draws and proposal in each,
-// the likelihood's four partial sums split among them -- and lane sub == 0 alone writes.
-template <bool REPLAY, int TARGET, typename PoolFn, int SUBS = 1>
+template <bool REPLAY, int TARGET, typename PoolFn>
 __device__ __forceinline__ int small_chain_step(const PhaseArgs& a, const TargetView& tv, const double* sdata,
-                                                int c, int n_pool, PoolFn pool_id, int sub = 0) {
-  const bool writer = SUBS == 1 || sub == 0;
+                                                int c, int n_pool, PoolFn pool_id) {
   const int d = a.d;
   const bool dream = a.algo == BPM_ALGO_DREAM;
   const int npair = dream ? a.del_pairs : 1;
@@ -1342,27 +1336,24 @@ __device__ __forceinline__ int small_chain_step(const PhaseArgs& a, const Target
         pr[q] = demc_prop(cur[q], S[q], nn[q], gamma);
       }
     }
-  if (dream && writer) {
+  if (dream) {
     a.cr_pick[c] = a.adapt ? D.cr_idx : -1;
     a.cr_delta[c] = delta;
   }
-  if (REPLAY && a.tr.prop && writer)
+  if (REPLAY && a.tr.prop)
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       if (q < d) a.tr.prop[(size_t)c * d + q] = pr[q];
   double lp;
   if (TARGET == BPM_TARGET_BANANA) lp = banana_lnl(tv.banana, pr[0], pr[1]);
   else if (TARGET == BPM_TARGET_BIMODAL) lp = bimodal_lnl(tv.bimodal, pr[0], pr[1]);
-  else if (SUBS == 4) lp = linefit_lnl_lanes4(sdata, sdata + tv.linefit_M, sdata + 2 * tv.linefit_M, tv.linefit_M,
-                                              pr[0], pr[1], pr[2], sub);
   else lp = linefit_lnl(sdata, sdata + tv.linefit_M, sdata + 2 * tv.linefit_M, tv.linefit_M, pr[0],
                         pr[1], pr[2]);
   int acc = metropolis(a.lnl[c], lp, accept_uniform<REPLAY>(a, c));
   if (acc < 0) {
-    if (writer) *a.nan_flag = 1;
+    *a.nan_flag = 1;
     acc = 0;
   }
-  if (!writer) return acc;
   const size_t o = (size_t)(c - a.chain_lo) * a.ld;
 #pragma unroll
   for (int q = 0; q < 4; ++q)
@@ -1394,28 +1385,12 @@ __global__ void __launch_bounds__(128) fused_small_kernel(const PhaseArgs a, con
     __syncthreads();
   }
   const PhaseLists L = phase_lists(a);
-  // lanes per chain.  Four lanes per line-fit chain (one partial sum of the likelihood each) were measured and
-  // are NOT used: the redundant draws / proposal of the three extra lanes cost more issue slots than the shorter
-  // likelihood saves -- 73 -> 86 us per generation at 10^5 chains (profiles/r2/r2r_secondary.txt).
-  constexpr int SUBS = (BPM_LINEFIT_LANES4 && TARGET == BPM_TARGET_LINEFIT) ? 4 : 1;
-  const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / SUBS;
-  const int sub = threadIdx.x % SUBS;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = gid < L.n_self;
   const int c = valid ? L.self[gid] : 0;
   valid = valid && c >= a.chain_lo && c < a.chain_hi;
   int acc = 0;
-  auto pool = [&](int r) { return L.pool[r]; };
-  if (SUBS == 1) {
-    if (valid) acc = small_chain_step<REPLAY, TARGET>(a, tv, sdata, c, L.n_pool, pool);
-  } else {
-    // The likelihood shuffles with full-warp masks, so every lane of the warp has to run the step: quads past
-    // the end of the list repeat a valid chain's arithmetic with writes disabled (sub = 1 never writes).
-    const int cc = valid ? c : (L.n_self > 0 ? L.self[0] : a.chain_lo);
-    const int r = small_chain_step<REPLAY, TARGET, decltype(pool), SUBS>(a, tv, sdata, cc, L.n_pool, pool,
-                                                                         valid ? sub : 1);
-    acc = valid && sub == 0 ? r : 0;
-    valid = valid && sub == 0;
-  }
+  if (valid) acc = small_chain_step<REPLAY, TARGET>(a, tv, sdata, c, L.n_pool, [&](int r) { return L.pool[r]; });
   const unsigned am = __ballot_sync(0xFFFFFFFFu, valid && acc);
   const unsigned rm = __ballot_sync(0xFFFFFFFFu, valid && !acc);
   if ((threadIdx.x & 31) == 0) {
@@ -1673,7 +1648,7 @@ inline int try_fused_phase(const TargetView& tv, const PhaseArgs& a, cudaStream_
       fused_small_kernel<REPLAY, BPM_TARGET_BIMODAL><<<grid, 128, 0, s>>>(a, tv);
     else
       fused_small_kernel<REPLAY, BPM_TARGET_LINEFIT>
-          <<<((BPM_LINEFIT_LANES4 ? 4 : 1) * a.nA + 127) / 128, 128, sizeof(double) * 3 * tv.linefit_M, s>>>(a, tv);
+          <<<grid, 128, sizeof(double) * 3 * tv.linefit_M, s>>>(a, tv);
     if (cudaGetLastError() != cudaSuccess) return 1;
     *done = 1;
     return 0;

@@ -61,62 +61,22 @@ __device__ __forceinline__ double gauss_finish(double c0, double maha, int log_o
 }
 
 // Line fit, examples/ex_para_fit.py:39-55.  data = x[M], y[M], yerr[M] (device).
-// The M terms are summed as FOUR interleaved partial sums (term i goes to partial i mod 4, each partial in
-// index order) combined as (p0 + p1) + (p2 + p3): a single thread gets four independent chains of divisions /
-// logarithms in flight, and four lanes of a warp can take one partial each and combine them with two shuffles --
-// same value, bit for bit, either way (the sequential form was ~25 us of pure latency per chain at M = 50).
-__device__ __forceinline__ bool linefit_prior_ok(double m, double b, double lnf) {
-  return -5.0 < m && m < 0.5 && 0.0 < b && b < 10.0 && -10.0 < lnf && lnf < 1.0;
-}
-__device__ __forceinline__ double linefit_partial(const double* x, const double* y, const double* yerr, int M,
-                                                  double m, double b, double e2, int k) {
-  double s = 0.0;
-  for (int i = k; i < M; i += 4) {
-    double model = __dadd_rn(__dmul_rn(m, x[i]), b);
-    double inv = __ddiv_rn(1.0, __dadd_rn(__dmul_rn(yerr[i], yerr[i]),
-                                          __dmul_rn(__dmul_rn(model, model), e2)));
-    double r = __dsub_rn(y[i], model);
-    s = __dadd_rn(s, __dsub_rn(__dmul_rn(__dmul_rn(r, r), inv), log(inv)));
-  }
-  return s;
-}
+// The M terms are independent up to the (ordered) accumulation: unrolled so that five divisions / logarithms
+// are in flight per thread.  (Measured alternatives, profiles/r2/r2r_secondary.txt, r2s_*: four interleaved
+// partial sums 76 us per generation of 10^5 chains, this form 73 us, four LANES per chain 86 us.)
 __device__ __forceinline__ double linefit_lnl(const double* x, const double* y, const double* yerr,
                                               int M, double m, double b, double lnf) {
-  if (!linefit_prior_ok(m, b, lnf)) return -INFINITY;
+  if (!(-5.0 < m && m < 0.5 && 0.0 < b && b < 10.0 && -10.0 < lnf && lnf < 1.0)) return -INFINITY;
   const double e2 = exp(__dmul_rn(2.0, lnf));
-#ifdef BPM_LINEFIT_SEQ      // A/B: the sequential sum of round 1, unrolled by five
-  double sq = 0.0;
+  double s = 0.0;
 #pragma unroll 5
   for (int i = 0; i < M; ++i) {
     double model = __dadd_rn(__dmul_rn(m, x[i]), b);
-    double inv = __ddiv_rn(1.0, __dadd_rn(__dmul_rn(yerr[i], yerr[i]), __dmul_rn(__dmul_rn(model, model), e2)));
-    double r = __dsub_rn(y[i], model);
-    sq += __dsub_rn(__dmul_rn(__dmul_rn(r, r), inv), log(inv));
-  }
-  return 0.0 + -0.5 * sq;
-#endif
-  double p[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int i = 0; i < M; ++i) {            // the four partials advance together: ILP 4 for one thread
-    double model = __dadd_rn(__dmul_rn(m, x[i]), b);
     double inv = __ddiv_rn(1.0, __dadd_rn(__dmul_rn(yerr[i], yerr[i]),
                                           __dmul_rn(__dmul_rn(model, model), e2)));
     double r = __dsub_rn(y[i], model);
-    p[i & 3] = __dadd_rn(p[i & 3], __dsub_rn(__dmul_rn(__dmul_rn(r, r), inv), log(inv)));
+    s += __dsub_rn(__dmul_rn(__dmul_rn(r, r), inv), log(inv));
   }
-  const double s = __dadd_rn(__dadd_rn(p[0], p[1]), __dadd_rn(p[2], p[3]));
-  return 0.0 + -0.5 * s;
-}
-// the same value computed by four consecutive lanes (sub = lane & 3 owns partial `sub`); every lane returns it
-__device__ __forceinline__ double linefit_lnl_lanes4(const double* x, const double* y, const double* yerr,
-                                                     int M, double m, double b, double lnf, int sub) {
-  const bool ok = linefit_prior_ok(m, b, lnf);
-  const double e2 = exp(__dmul_rn(2.0, lnf));
-  const double mine = ok ? linefit_partial(x, y, yerr, M, m, b, e2, sub) : 0.0;
-  const int base = (threadIdx.x & 31) & ~3;
-  const double p0 = __shfl_sync(0xFFFFFFFFu, mine, base + 0), p1 = __shfl_sync(0xFFFFFFFFu, mine, base + 1);
-  const double p2 = __shfl_sync(0xFFFFFFFFu, mine, base + 2), p3 = __shfl_sync(0xFFFFFFFFu, mine, base + 3);
-  if (!ok) return -INFINITY;
-  const double s = __dadd_rn(__dadd_rn(p0, p1), __dadd_rn(p2, p3));
   return 0.0 + -0.5 * s;
 }
 
