@@ -60,6 +60,31 @@ def _worker(rank, world, port, n_chains, q):
                 j += len(s.rank_chain_ids)
                 gens += 1
             assert DeMcMpi._n_generations(s, n) == gens, (n, gens)
+        # uneven shards are refused up front (the reference hangs there: per-rank j counters, demc.py:79,93) --
+        # the check sits before any device work, so it runs on this CPU-only box
+        if n_chains % world != 0:
+            try:
+                DeMcMpi(lambda th: 0.0, np.zeros(2), n_chains=n_chains)
+                raise AssertionError("uneven shards were accepted")
+            except ValueError as e:
+                assert "divisible" in str(e)
+        # an mpi4py-style communicator must describe the torch.distributed world
+        class _Fake(object):
+            def __init__(self, rank, size):
+                self.rank, self.size = rank, size
+
+            def Get_size(self):
+                return self.size
+
+            def Get_rank(self):
+                return self.rank
+        from bipymc_b200.demc import _resolve_comm
+        assert _resolve_comm(_Fake(rank, world)).size == world
+        try:
+            _resolve_comm(_Fake(rank, world + 1))
+            raise AssertionError("mismatching communicator was accepted")
+        except RuntimeError as e:
+            assert "disagree" in str(e)
         # ownership lookup (demc.py:327-338)
         for c in (0, lo, hi - 1, n_chains - 1):
             r = DeMcMpi.get_chain_rank(s, c)

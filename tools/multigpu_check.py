@@ -67,6 +67,24 @@ def main():
             print("case", name, exchange, "->", s._exchange, "ok", flush=True)
         dist.barrier()
         del s
+    # ---- serial DeMc (delayed accept) on several ranks: every chain of a sweep reads ALL other chains of the frozen
+    #      population, so the ranks exchange with an all-gather after the sweep, never with in-kernel peer stores
+    #      (ADVICE r1); the sharded sweep must reproduce the single-GPU one bit for bit
+    from bipymc_b200 import DeMc
+    Ns = 64 * world
+    np.random.seed(4)
+    sd = DeMc(targets.Banana_2D().ln_like, n_chains=Ns, seed=6, device=local, exchange="p2p")
+    assert sd._exchange == "allgather"
+    sd.run_mcmc(Ns * 9, [0.0, 0.0], varepsilon=1e-2)
+    full = sd.super_chain_mpi(0)
+    if rank == 0:
+        np.random.seed(4)
+        one = DeMc(targets.Banana_2D().ln_like, n_chains=Ns, seed=6, device=local, mpi_comm=_SingleComm())
+        one.run_mcmc(Ns * 9, [0.0, 0.0], varepsilon=1e-2)
+        assert np.array_equal(full, one.super_chain), "sharded serial sweep differs from the single-GPU sweep"
+        print("case serial-demc sharded ok", flush=True)
+    dist.barrier()
+    del sd
     # ---- sharded end-to-end entry (bpm_generations_host_sharded): host shards in / out every generation ==
     #      the device-resident sharded run of the same seed (adaptation on: moments live in the sampler state)
     import ctypes as C
