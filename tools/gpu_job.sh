@@ -1,11 +1,8 @@
-# Recipe of the round-2 final artefacts under profiles/r2/r2t_* (one gpurun call on one B200)
+# round 2, final 8-GPU job: weak-scaling points of the shipped tree (8, 4 GPUs), sharded correctness incl. the serial sampler
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2t_pytest.log 2>&1; tail -4 gpurun_out/r2t_pytest.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2t_smoke.log 2>&1; tail -2 gpurun_out/r2t_smoke.log
-timeout 600 python bench.py > gpurun_out/r2t_bench.json 2> gpurun_out/r2t_bench.err; tail -c 2800 gpurun_out/r2t_bench.json; tail -3 gpurun_out/r2t_bench.err
-timeout 400 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/r2t_bench_ref.json 2> gpurun_out/r2t_bench_ref.err; tail -c 500 gpurun_out/r2t_bench_ref.json
-timeout 400 python tools/bench_configs.py c3 c4 demc100 c5shape > gpurun_out/r2t_secondary.txt 2>&1; cat gpurun_out/r2t_secondary.txt
-BIPYMC_B200_LIB=$PWD/build_ab/lib_checks.so timeout 300 python tools/sanitize_case.py > gpurun_out/r2t_checked_build.log 2>&1; tail -5 gpurun_out/r2t_checked_build.log
-python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e --no-stationary > gpurun_out/r2t_plain.log 2>&1 && timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2t_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e --no-stationary > gpurun_out/r2t_ncu_l.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_gauss_v4 -s 130 -c 1 -o gpurun_out/prof_r2t -f python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-stationary > gpurun_out/r2t_ncu_full.log 2>&1; tail -2 gpurun_out/r2t_ncu_full.log
+TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+timeout 600 $TR --nproc-per-node 8 --master-port 29561 bench.py --gpus 8 --steps 50 --warmup 5 > gpurun_out/r2u_bench_n8.json 2> gpurun_out/r2u_bench_n8.err; tail -c 2200 gpurun_out/r2u_bench_n8.json; tail -4 gpurun_out/r2u_bench_n8.err
+timeout 500 $TR --nproc-per-node 4 --master-port 29564 bench.py --gpus 4 --steps 50 --warmup 5 > gpurun_out/r2u_bench_n4.json 2> gpurun_out/r2u_bench_n4.err; tail -c 1200 gpurun_out/r2u_bench_n4.json
+timeout 600 $TR --nproc-per-node 4 --master-port 29565 tools/multigpu_check.py > gpurun_out/r2u_mg4.log 2>&1; grep -v "^\*\|OMP_NUM\|^$" gpurun_out/r2u_mg4.log | tail -8
+timeout 300 $TR --nproc-per-node 4 --master-port 29566 tools/bench_configs.py c4multi > gpurun_out/r2u_c4_n4.txt 2>&1; grep config gpurun_out/r2u_c4_n4.txt
