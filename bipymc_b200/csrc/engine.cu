@@ -70,6 +70,7 @@ struct bpm_engine {
                              *cmp_blk = nullptr; } alt;
   cudaStream_t side = nullptr;
   cudaEvent_t ev_start = nullptr, ev_split = nullptr, ev_done = nullptr;
+  cudaEvent_t ev_chunk[8] = {nullptr};       // sharded host entry: chunked host copy -> peer forwarding
   void swap_split() {
     std::swap(perm, alt.perm); std::swap(flip, alt.flip); std::swap(inv, alt.inv);
     std::swap(loc_list, alt.loc_list); std::swap(loc_cnt, alt.loc_cnt); std::swap(cmp_blk, alt.cmp_blk);
@@ -188,6 +189,7 @@ struct bpm_engine {
     cudaFree(alt.cmp_blk);
     if (side) cudaStreamDestroy(side);
     if (ev_start) { cudaEventDestroy(ev_start); cudaEventDestroy(ev_split); cudaEventDestroy(ev_done); }
+    for (auto e : ev_chunk) if (e) cudaEventDestroy(e);
     cudaFree(perm); cudaFree(flip); cudaFree(prop); cudaFree(lnl_prop); cudaFree(cr_delta);
     cudaFree(cr_pick); cudaFree(p_cr); cudaFree(cr_dm); cudaFree(cr_cnt); cudaFree(cr_part); cudaFree(cr_block);
     cudaFree(counters); cudaFree(nan_flag); cudaFree(tparams); cudaFree(hX); cudaFree(hL); cudaFree(hMean); cudaFree(hM2);
@@ -1139,9 +1141,40 @@ int bpm_generations_host_sharded(bpm_handle h, bpm_state* st, double* X_host, do
   sa.n2 = (int64_t)nloc * ld / 2;
   unsigned long long acc0 = 0, acc1 = 0;
   CU_TRY(cudaMemcpyAsync(&acc0, h->counters, sizeof(acc0), cudaMemcpyDeviceToHost, s));
+  static const bool shard_in_kernel_opt = [] {
+    const char* e = getenv("BIPYMC_B200_SHARD_IN_KERNEL");
+    return e && e[0] == '1';
+  }();
   h->prof_begin(7, s);
-  bpm::shard_in_kernel<<<296, 512, 0, s>>>(sa);
-  CU_TRY(cudaGetLastError());
+  if (shard_in_kernel_opt) {
+    // one kernel: zero-copy PCIe reads, stores into every replica (SM-issued NVLink stores)
+    bpm::shard_in_kernel<<<296, 512, 0, s>>>(sa);
+    CU_TRY(cudaGetLastError());
+  } else {
+    // Default: copy engines.  The shard comes in as kChunks DMA copies on the caller's stream; as soon as a chunk
+    // has landed the side stream forwards it to every peer replica with peer copies (NVLink copy engines), under
+    // the next chunk's host copy.  Measured against the one-kernel form (SM-issued remote stores: 4.7 ms per step
+    // at 8 GPUs, 2.2 ms at 2): see DESIGN.md section 6.
+    constexpr int kChunks = 4;
+    BPM_TRY(h->side_setup());
+    if (!h->ev_chunk[0])
+      for (int k = 0; k <= kChunks; ++k) CU_TRY(cudaEventCreateWithFlags(&h->ev_chunk[k], cudaEventDisableTiming));
+    const size_t total = (size_t)nloc * ld, per = ((total / kChunks) + 1) & ~(size_t)1;
+    CU_TRY(cudaEventRecord(h->ev_chunk[kChunks], s));
+    CU_TRY(cudaStreamWaitEvent(h->side, h->ev_chunk[kChunks], 0));     // the side stream starts after the caller's prior work
+    for (int k = 0; k < kChunks; ++k) {
+      const size_t o0 = (size_t)k * per;
+      if (o0 >= total) break;
+      const size_t n = (o0 + per <= total ? per : total - o0) * sizeof(double);
+      CU_TRY(cudaMemcpyAsync(st->X + off + o0, X_host + o0, n, cudaMemcpyHostToDevice, s));
+      CU_TRY(cudaEventRecord(h->ev_chunk[k], s));
+      CU_TRY(cudaStreamWaitEvent(h->side, h->ev_chunk[k], 0));
+      for (int p = 0; p < h->n_peers; ++p)
+        CU_TRY(cudaMemcpyAsync(h->peers[p] + off + o0, st->X + off + o0, n, cudaMemcpyDefault, h->side));
+    }
+    CU_TRY(cudaEventRecord(h->ev_chunk[kChunks], h->side));
+    CU_TRY(cudaStreamWaitEvent(s, h->ev_chunk[kChunks], 0));           // every peer copy of this rank is done
+  }
   h->prof_end(s);
   CU_TRY(cudaMemcpyAsync(st->lnl + lo, lnl_host, sizeof(double) * nloc, cudaMemcpyHostToDevice, s));
   BPM_TRY(h->peer_barrier(s));                  // every replica holds every shard

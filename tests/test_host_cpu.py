@@ -196,3 +196,51 @@ def test_history_store_chunks_and_super_chain_layout():
     assert hs2.reserve(5) == (None, 5)
     hs2.advance(5)
     assert hs2.length == 6 and hs2.stored == 1
+
+
+def test_history_store_pending_row_and_contiguous_reserve():
+    """Host bookkeeping of the lazy protocol (bpm_state.pending): the newest row of a generation is written
+    one generation later (or by bpm_flush) at flat_base() + (length - 1) rows -- which must stay inside the LAST
+    chunk, so the owner flushes before reserve() opens a new one (will_grow()); the before-read hook runs
+    whenever the stored rows are read; replay steps get every stored row in ONE block (reserve_contiguous)."""
+    import torch
+    from bipymc_b200.demc import HistoryStore
+    hs = HistoryStore(n_local=2, dim=2, ld=2, device=torch.device("cpu"), chunk_bytes=2 * 2 * 8 * 3)
+    x0 = torch.zeros((2, 2), dtype=torch.float64)
+    hs.set_initial(x0)
+    calls = []
+    hs._before_read = lambda: calls.append(hs.length)
+    pending = None                      # row index a lazy generation left unwritten
+    for g in range(1, 9):
+        if pending is not None and hs.will_grow():
+            # flush: the pending row lives in the chunk that is full now
+            base = hs.flat_base()
+            off = (base + pending * hs.row_bytes - hs.chunks[-1].data_ptr()) // hs.row_bytes
+            assert 0 <= off < hs.chunks[-1].shape[0]
+            hs.chunks[-1][off] = x0 + pending
+            pending = None
+        base, avail = hs.reserve(1)
+        assert avail >= 1
+        if pending is not None:         # the next generation's proposal stage writes the pending row
+            off = (base + pending * hs.row_bytes - hs.chunks[-1].data_ptr()) // hs.row_bytes
+            assert 0 <= off < hs.chunks[-1].shape[0], "pending row must sit in the chunk reserve() returned"
+            hs.chunks[-1][off] = x0 + pending
+        pending = hs.length             # this generation's row stays pending
+        hs.advance(1)
+    base = hs.flat_base()
+    off = (base + pending * hs.row_bytes - hs.chunks[-1].data_ptr()) // hs.row_bytes
+    hs.chunks[-1][off] = x0 + pending
+    full = hs.tensor()
+    assert calls and full.shape[0] == 9
+    for r in range(9):
+        assert torch.equal(full[r], x0 + r)
+    # one block for replay steps: base is a real array base and old rows are preserved
+    hs3 = HistoryStore(2, 2, 2, torch.device("cpu"), chunk_bytes=2 * 2 * 8 * 2)
+    hs3.set_initial(x0 + 7)
+    for g in range(5):
+        base, avail = hs3.reserve_contiguous(1)
+        assert len(hs3.chunks) == 1 and base == hs3.chunks[0].data_ptr() and avail >= 1
+        hs3.chunks[0][hs3.length] = x0 + 7 + hs3.length
+        hs3.advance(1)
+    t3 = hs3.tensor()
+    assert t3.shape[0] == 6 and all(torch.equal(t3[r], x0 + 7 + r) for r in range(6))
