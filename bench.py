@@ -384,9 +384,9 @@ def run_ours(args):
 
     if world > 1 and not args.no_e2e and args.subpop_k == 0 and s._sync_on:
         # sharded end-to-end step through the C-ABI (bpm_generations_host_sharded): every rank hands in ITS
-        # shard (states + cached likelihoods) in pinned host memory; it is copied in chunk by chunk and each chunk
-        # forwarded to every peer replica (host copy + all-gather overlapped), a generation runs, accepted rows are
-        # stored back into the host shard by the phase kernels, the cached likelihoods return with one copy.
+        # shard (states + cached likelihoods) in pinned host memory; one kernel reads it over PCIe and stores it into
+        # every replica (host copy + all-gather fused), a generation runs, accepted rows are stored back into the
+        # host shard by the phase kernels, the cached likelihoods return with one copy.
         numa = bind_to_gpu_numa(local_rank)
         lo, hi = int(s.rank_chain_ids[0]), int(s.rank_chain_ids[-1]) + 1
         Xh = torch.empty((hi - lo, s._ld), dtype=torch.float64).pin_memory()
@@ -418,11 +418,12 @@ def run_ours(args):
         nb = (N * s._ld * 8 + N * 8)
         e2e = {"value": N * ke / dt, "unit": UNIT, "h2d_bytes_per_step": nb, "d2h_bytes_per_step": d2h_all,
                "steps": ke, "ms_per_step": 1e3 * dt / ke, "host_numa_node": numa,
-               "note": "bpm_generations_host_sharded, per rank: pinned host shard -> H2D in chunks, every chunk forwarded "
-                       "to the other %d replicas by peer copies as soon as it has landed (host copy and all-gather "
-                       "overlapped on the copy engines) -> peer barrier -> one sharded generation (adaptation ON) whose "
-                       "phase kernels store accepted rows back into the host shard -> cached likelihoods D2H; bytes are "
-                       "summed over ranks" % (world - 1)}
+               "shard_in": "copy engines" if os.environ.get("BIPYMC_B200_SHARD_DMA") == "1" else "one kernel",
+               "note": "bpm_generations_host_sharded, per rank: pinned host shard -> read over PCIe (zero-copy) and stored "
+                       "into the rank's own and the other %d replicas by one kernel (host copy and all-gather fused; "
+                       "BIPYMC_B200_SHARD_DMA=1: chunked copies on the copy engines) -> peer barrier -> one sharded "
+                       "generation (adaptation ON) whose phase kernels store accepted rows back into the host shard -> "
+                       "cached likelihoods D2H; bytes are summed over ranks" % (world - 1)}
 
     # ---- second point: the same engine on a population AT STATIONARITY (chains drawn from the target) ---
     # acceptance-dependent traffic (accepted-row stores, peer stores, changed-rows write-back) is then

@@ -1141,20 +1141,22 @@ int bpm_generations_host_sharded(bpm_handle h, bpm_state* st, double* X_host, do
   sa.n2 = (int64_t)nloc * ld / 2;
   unsigned long long acc0 = 0, acc1 = 0;
   CU_TRY(cudaMemcpyAsync(&acc0, h->counters, sizeof(acc0), cudaMemcpyDeviceToHost, s));
-  static const bool shard_in_kernel_opt = [] {
-    const char* e = getenv("BIPYMC_B200_SHARD_IN_KERNEL");
+  static const bool shard_dma_opt = [] {
+    const char* e = getenv("BIPYMC_B200_SHARD_DMA");
     return e && e[0] == '1';
   }();
   h->prof_begin(7, s);
-  if (shard_in_kernel_opt) {
-    // one kernel: zero-copy PCIe reads, stores into every replica (SM-issued NVLink stores)
+  if (!shard_dma_opt) {
+    // Default, one kernel: zero-copy PCIe reads, every 16-byte piece stored into every replica (SM-issued NVLink
+    // stores riding under the PCIe read)
     bpm::shard_in_kernel<<<296, 512, 0, s>>>(sa);
     CU_TRY(cudaGetLastError());
   } else {
-    // Default: copy engines.  The shard comes in as kChunks DMA copies on the caller's stream; as soon as a chunk
-    // has landed the side stream forwards it to every peer replica with peer copies (NVLink copy engines), under
-    // the next chunk's host copy.  Measured against the one-kernel form (SM-issued remote stores: 4.7 ms per step
-    // at 8 GPUs, 2.2 ms at 2): see DESIGN.md section 6.
+    // BIPYMC_B200_SHARD_DMA=1: copy engines.  The shard comes in as kChunks DMA copies on the caller's stream; as
+    // soon as a chunk has landed the side stream forwards it to every peer replica with peer copies (NVLink copy
+    // engines), under the next chunk's host copy.  Measured against the one-kernel form (profiles/r2/r2v_*, r2w_*):
+    // 2.04 vs 2.09 ms per end-to-end step at 2 GPUs, 3.87 vs 3.69 at 4, 5.06 vs 4.65 at 8 -- the step is bound by
+    // the ranks' concurrent reads of host memory, and 7 x 4 peer copies per rank only add submission work.
     constexpr int kChunks = 4;
     BPM_TRY(h->side_setup());
     if (!h->ev_chunk[0])

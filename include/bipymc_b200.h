@@ -252,10 +252,10 @@ int bpm_generations_host(bpm_handle h, double* X_host, double* lnl_host, int64_t
 int bpm_host_entry_restart(bpm_handle h);
 /* The same end-to-end step for a SHARDED population (one process per GPU; needs bpm_set_peers and
  * bpm_set_sync).  X_host [n_local][ld] / lnl_host [n_local] are THIS rank's chains in pinned
- * (device-mapped) host memory; st is the rank's device state (st->X = its full replica).  The shard is
- * copied in chunk by chunk and every chunk is forwarded to all peer replicas as soon as it has landed
- * (host->device copy and the reference's Allgather, demc.py:93, overlapped on the copy engines;
- * BIPYMC_B200_SHARD_IN_KERNEL=1 selects the one-kernel form with SM-issued stores), a peer barrier follows,
+ * (device-mapped) host memory; st is the rank's device state (st->X = its full replica).  One kernel reads
+ * the shard over PCIe (zero-copy) and stores every piece into the rank's own and all peer replicas
+ * (host->device copy and the reference's Allgather, demc.py:93, fused; BIPYMC_B200_SHARD_DMA=1 selects the
+ * copy-engine form: chunked host copies, each chunk forwarded by peer copies), a peer barrier follows,
  * n_gen generations run with the host array registered as one more replica -- so accepted rows are
  * written back by the phase kernels themselves -- and the cached likelihoods come back with one copy.
  * Collective: every rank calls it with the same k_gen0 / n_gen.  Synchronous. */

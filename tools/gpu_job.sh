@@ -1,7 +1,7 @@
-# round 2, 2-GPU job: sharded host entry on the copy engines (A/B against the one-kernel form) + sharded correctness
+# round 2, 8-GPU A/B of the sharded host entry: copy engines (default) vs the one-kernel form
 set -x
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-timeout 900 $TR --nproc-per-node 2 --master-port 29551 tools/multigpu_check.py > gpurun_out/r2v_mg.log 2>&1; grep -v "^\*\|OMP_NUM\|^$" gpurun_out/r2v_mg.log | tail -5
-timeout 600 $TR --nproc-per-node 2 --master-port 29552 bench.py --gpus 2 --steps 30 --warmup 5 --no-stationary > gpurun_out/r2v_bench_n2_dma.json 2> gpurun_out/r2v_bench_n2.err; tail -c 900 gpurun_out/r2v_bench_n2_dma.json; tail -3 gpurun_out/r2v_bench_n2.err
-BIPYMC_B200_SHARD_IN_KERNEL=1 timeout 600 $TR --nproc-per-node 2 --master-port 29553 bench.py --gpus 2 --steps 30 --warmup 5 --no-stationary > gpurun_out/r2v_bench_n2_kernel.json 2>> gpurun_out/r2v_bench_n2.err; tail -c 900 gpurun_out/r2v_bench_n2_kernel.json
+timeout 600 $TR --nproc-per-node 8 --master-port 29561 bench.py --gpus 8 --steps 30 --warmup 5 --no-stationary > gpurun_out/r2w_bench_n8_dma.json 2> gpurun_out/r2w_bench_n8.err; tail -c 1000 gpurun_out/r2w_bench_n8_dma.json; tail -3 gpurun_out/r2w_bench_n8.err
+BIPYMC_B200_SHARD_IN_KERNEL=1 timeout 600 $TR --nproc-per-node 8 --master-port 29562 bench.py --gpus 8 --steps 30 --warmup 5 --no-stationary > gpurun_out/r2w_bench_n8_kernel.json 2>> gpurun_out/r2w_bench_n8.err; tail -c 1000 gpurun_out/r2w_bench_n8_kernel.json
+timeout 400 $TR --nproc-per-node 4 --master-port 29563 bench.py --gpus 4 --steps 30 --warmup 5 --no-stationary > gpurun_out/r2w_bench_n4_dma.json 2>> gpurun_out/r2w_bench_n8.err; tail -c 700 gpurun_out/r2w_bench_n4_dma.json
