@@ -79,12 +79,13 @@ class McmcChain(object):
 
     # -- HDF5 (chain.py:59-93): dataset /chains/chain_id_<global_id>, gzip, (T, dim) f64 ----
     def write_chain_h5(self, h5_file):
-        import h5py  # lazy: not installed in every image
+        from . import h5lite       # h5py where it imports, else the package's own HDF5 writer / reader
+        h5py = h5lite.get_h5()
         name = "/chains/chain_id_" + str(self.global_id)
         if isinstance(h5_file, str):
             with h5py.File(h5_file, "w") as h5f:
                 h5f.create_dataset(name, data=self.chain, compression="gzip")
-        elif isinstance(h5_file, h5py.File):
+        elif h5lite.is_file(h5_file):
             if name in h5_file:
                 del h5_file[name]
             h5_file.create_dataset(name, data=self.chain, compression="gzip")
@@ -92,12 +93,13 @@ class McmcChain(object):
             raise RuntimeError
 
     def read_chain_h5(self, h5_file, c_id=None):
-        import h5py
+        from . import h5lite
+        h5py = h5lite.get_h5()
         name = "/chains/chain_id_" + str(self.global_id)
         if isinstance(h5_file, str):
             with h5py.File(h5_file, "r") as h5f:
                 self.load_chain_state(h5f[name][:])
-        elif isinstance(h5_file, h5py.File):
+        elif h5lite.is_file(h5_file):
             self.load_chain_state(h5_file[name][:])
         else:
             raise RuntimeError

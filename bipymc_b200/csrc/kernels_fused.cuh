@@ -1308,9 +1308,33 @@ __device__ __forceinline__ int small_chain_step(const PhaseArgs& a, const Target
   }
   double* xc = a.X + (size_t)c * a.ld;
   double cur[4] = {0, 0, 0, 0}, S[4] = {0, 0, 0, 0}, pr[4] = {0, 0, 0, 0};
+  // Everything the step reads of its OWN chain is requested here, in one batch of independent loads: the
+  // cached likelihood and the moments rows would otherwise each cost an exposed round trip AFTER the likelihood
+  // (the stores in between keep the compiler from hoisting them; ncu: long scoreboard 27 % of the line-fit
+  // kernel's warp time, profiles/r2/r2x_fused_small_linefit_ncu_summary.txt).
+  // Only where one chain-step is long and few warps are resident (the line fit): on the 2-D targets the twelve
+  // extra registers cost a resident block per SM (94 -> 106 registers; 10^6 bimodal chains: 0.22 -> 0.27 ms per
+  // generation, profiles/r2/r2y_secondary.txt), so those load late as before.
+  constexpr bool kPreload = TARGET == BPM_TARGET_LINEFIT;
+  double mu_c[4] = {0, 0, 0, 0}, m2_c[4] = {0, 0, 0, 0};
+  double lnl_c = 0.0;
+  if constexpr (kPreload) {
+    const size_t o = (size_t)(c - a.chain_lo) * a.ld;
+    lnl_c = a.lnl[c];
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
-    if (q < d) cur[q] = xc[q];
+    for (int q = 0; q < 4; ++q)
+      if (q < d) {
+        cur[q] = xc[q];
+        if (a.mean) {
+          mu_c[q] = a.mean[o + q];
+          m2_c[q] = a.m2[o + q];
+        }
+      }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q < d) cur[q] = xc[q];
+  }
 #pragma unroll
   for (int p = 0; p < BPM_MAX_PAIRS; ++p)
     if (p < npair) {
@@ -1331,7 +1355,20 @@ __device__ __forceinline__ int small_chain_step(const PhaseArgs& a, const Target
     if (q < d) {
       if (dream) {
         pr[q] = dream_prop(cur[q], S[q], e[q], nn[q], gamma, (mbits >> q) & 1u ? 1.0 : 0.0);
-        if (a.adapt) delta += cr_term(cur[q], pr[q], cr_variance<REPLAY>(a, c, q));
+        if constexpr (kPreload) {
+          if (a.adapt) {
+            double v;
+            if ((REPLAY && a.hist_base != nullptr) || !a.mean) {
+              v = cr_variance<REPLAY>(a, c, q);
+            } else {                             // cr_variance's running-moments branch on the preloaded row
+              v = __dmul_rn(m2_c[q], a.inv_mom);
+              if (!(v > 0.0)) v = 1e-12 * 1e-12;
+            }
+            delta += cr_term(cur[q], pr[q], v);
+          }
+        } else {
+          if (a.adapt) delta += cr_term(cur[q], pr[q], cr_variance<REPLAY>(a, c, q));
+        }
       } else {
         pr[q] = demc_prop(cur[q], S[q], nn[q], gamma);
       }
@@ -1349,7 +1386,9 @@ __device__ __forceinline__ int small_chain_step(const PhaseArgs& a, const Target
   else if (TARGET == BPM_TARGET_BIMODAL) lp = bimodal_lnl(tv.bimodal, pr[0], pr[1]);
   else lp = linefit_lnl(sdata, sdata + tv.linefit_M, sdata + 2 * tv.linefit_M, tv.linefit_M, pr[0],
                         pr[1], pr[2]);
-  int acc = metropolis(a.lnl[c], lp, accept_uniform<REPLAY>(a, c));
+  int acc;
+  if constexpr (kPreload) acc = metropolis(lnl_c, lp, accept_uniform<REPLAY>(a, c));
+  else acc = metropolis(a.lnl[c], lp, accept_uniform<REPLAY>(a, c));
   if (acc < 0) {
     *a.nan_flag = 1;
     acc = 0;
@@ -1364,7 +1403,9 @@ __device__ __forceinline__ int small_chain_step(const PhaseArgs& a, const Target
         store_peers1(a, (size_t)c * a.ld + q, s);
       }
       if (a.mean) {
-        double mu = a.mean[o + q], v = a.m2[o + q];
+        double mu, v;
+        if constexpr (kPreload) { mu = mu_c[q]; v = m2_c[q]; }
+        else { mu = a.mean[o + q]; v = a.m2[o + q]; }
         welford_update(s, a.inv_n1, mu, v);
         a.mean[o + q] = mu;
         a.m2[o + q] = v;
@@ -1642,6 +1683,9 @@ inline int try_fused_phase(const TargetView& tv, const PhaseArgs& a, cudaStream_
   if (a.d <= 4 && (tv.target == BPM_TARGET_BANANA || tv.target == BPM_TARGET_BIMODAL ||
                    tv.target == BPM_TARGET_LINEFIT)) {
     const int grid = (a.nA + 127) / 128;
+    // (Programmatic dependent launches between phase a, phase b and the CR reduction -- griddepcontrol.wait after
+    // the list lookups, launch_dependents at the top -- were measured and dropped: 10^5 line-fit chains 52.6 -> 59.7 us
+    // per generation, 10^6 bimodal chains 241 -> 264 us; profiles/r2/r2z_secondary*.txt.)
     if (tv.target == BPM_TARGET_BANANA)
       fused_small_kernel<REPLAY, BPM_TARGET_BANANA><<<grid, 128, 0, s>>>(a, tv);
     else if (tv.target == BPM_TARGET_BIMODAL)

@@ -171,7 +171,9 @@ __global__ void __launch_bounds__(kCompactThreads) compact_write_kernel(const Li
 
 // ---- proposal ---------------------------------------------------------------------
 template <bool REPLAY, int LPC>
-__global__ void __launch_bounds__(kThreads) propose_kernel(const PhaseArgs a) {
+// (LPC = 32: two 256-thread blocks per SM, i.e. at most 128 registers -- without the bound the block-wise pass 2
+// takes 174 and one block per SM)
+__global__ void __launch_bounds__(kThreads, LPC == 32 ? 2 : 1) propose_kernel(const PhaseArgs a) {
   const int gid = (blockIdx.x * kThreads + threadIdx.x) / LPC;
   const int sub = threadIdx.x % LPC;
   const PhaseLists L = phase_lists(a);
@@ -188,6 +190,11 @@ __global__ void __launch_bounds__(kThreads) propose_kernel(const PhaseArgs a) {
   // pass 1 (DREAM): crossover mask of this lane's dimensions, d' (dream.py:51-58)
   uint32_t mbits = 0xFFFFFFFFu;
   double gamma;
+  // large d (one warp per chain, rows of whole 32-byte sectors): pass 2 below works block-wise with 16-byte
+  // accesses and reuses pass 1's Philox words
+  constexpr bool kKeepDraws = LPC == 32 && !REPLAY && BPM_ZEN_ONE;
+  const bool vec = LPC == 32 && (a.ld & 3) == 0;
+  Philox4 qs[kKeepDraws ? kMaxBlocksPerLane : 1];
   if (dream) {
     mbits = 0u;
     const double cr = __ddiv_rn((double)(D.cr_idx + 1), (double)a.n_cr);
@@ -197,7 +204,14 @@ __global__ void __launch_bounds__(kThreads) propose_kernel(const PhaseArgs a) {
         const int b = sub + t * LPC;
         if (b < nblk) {
           double z[4];
-          z4<REPLAY>(a, c, b, z);
+          if constexpr (kKeepDraws) {          // z4's native branch, keeping the call's words for zen_en4
+            const Philox4 q = draw4(a.rng, (uint32_t)c, RNG_ZEN, (uint32_t)b);
+            qs[t] = q;
+            z[0] = ((double)(q.x & 0xFFFu) + 0.5) * (1.0 / 4096.0); z[1] = ((double)(q.y & 0xFFFu) + 0.5) * (1.0 / 4096.0);
+            z[2] = ((double)(q.z & 0xFFFu) + 0.5) * (1.0 / 4096.0); z[3] = ((double)(q.w & 0xFFFu) + 0.5) * (1.0 / 4096.0);
+          } else {
+            z4<REPLAY>(a, c, b, z);
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             if (4 * b + q < a.d && z[q] <= cr) mbits |= 1u << (4 * t + q);
@@ -231,7 +245,96 @@ __global__ void __launch_bounds__(kThreads) propose_kernel(const PhaseArgs a) {
   const double* xc = a.X + (size_t)c * a.ld;
   double* out = a.prop + (size_t)gid * a.ld;
   double delta = 0.0;
-  if (valid) {
+  if (valid && vec) {
+    // Block-wise: ALL loads of a 4-dim block (own row, 2 * npair partner rows, the M2 row) are issued as 16-byte
+    // loads before anything of the block is stored.  The per-dimension form below stores out[i] before it loads
+    // dimension i + 1 -- the pointers may alias as far as the compiler knows -- so every load's latency was
+    // exposed: d = 1000, 10^4 chains per launch: 234 us, DRAM at 19 % (profiles/r2/r2x_c5_propose_accept_ncu.txt).
+    // Same arithmetic per dimension, same order of the per-lane sum `delta`.
+    const bool hist_var = REPLAY && a.hist_base != nullptr;
+    const bool adapt = dream && a.adapt;
+    const double* m2row = a.m2 + (size_t)(c - a.chain_lo) * a.ld;     // read only when adapt && !hist_var
+#pragma unroll
+    for (int t = 0; t < kMaxBlocksPerLane; ++t) {
+      const int b = sub + t * LPC;
+      if (b < nblk) {
+        const int i0 = 4 * b;
+        const double2 c0 = *reinterpret_cast<const double2*>(xc + i0);
+        const double2 c1 = *reinterpret_cast<const double2*>(xc + i0 + 2);
+        double2 w0 = make_double2(0.0, 0.0), w1 = w0;
+        if (adapt && !hist_var) {
+          w0 = *reinterpret_cast<const double2*>(m2row + i0);
+          w1 = *reinterpret_cast<const double2*>(m2row + i0 + 2);
+        }
+        double S[4];
+        {
+          const double2 s0 = *reinterpret_cast<const double2*>(pa[0] + i0);
+          const double2 s1 = *reinterpret_cast<const double2*>(pa[0] + i0 + 2);
+          const double2 t0 = *reinterpret_cast<const double2*>(pb[0] + i0);
+          const double2 t1 = *reinterpret_cast<const double2*>(pb[0] + i0 + 2);
+          S[0] = __dsub_rn(s0.x, t0.x); S[1] = __dsub_rn(s0.y, t0.y);
+          S[2] = __dsub_rn(s1.x, t1.x); S[3] = __dsub_rn(s1.y, t1.y);
+        }
+#pragma unroll
+        for (int p = 1; p < BPM_MAX_PAIRS; ++p)
+          if (p < npair) {
+            const double2 s0 = *reinterpret_cast<const double2*>(pa[p] + i0);
+            const double2 s1 = *reinterpret_cast<const double2*>(pa[p] + i0 + 2);
+            const double2 t0 = *reinterpret_cast<const double2*>(pb[p] + i0);
+            const double2 t1 = *reinterpret_cast<const double2*>(pb[p] + i0 + 2);
+            S[0] = __dadd_rn(S[0], __dsub_rn(s0.x, t0.x)); S[1] = __dadd_rn(S[1], __dsub_rn(s0.y, t0.y));
+            S[2] = __dadd_rn(S[2], __dsub_rn(s1.x, t1.x)); S[3] = __dadd_rn(S[3], __dsub_rn(s1.y, t1.y));
+          }
+        double e[4], n[4];
+        if (kKeepDraws && dream) {
+          e[0] = e[1] = e[2] = e[3] = 0.0;
+          n[0] = n[1] = n[2] = n[3] = 0.0;
+          if (a.u_eps > 0.0 || a.eps > 0.0) zen_en4(a, qs[kKeepDraws ? t : 0], e, n);
+        } else {
+          en4<REPLAY>(a, c, b, e, n);
+        }
+        const double cur[4] = {c0.x, c0.y, c1.x, c1.y};
+        const double m2v[4] = {w0.x, w0.y, w1.x, w1.y};
+        double prv[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = i0 + q;
+          if (i < a.d) {
+            double pr;
+            if (dream) {
+              const double mf = (mbits >> (4 * t + q)) & 1u ? 1.0 : 0.0;
+              pr = dream_prop(cur[q], S[q], e[q], n[q], gamma, mf);
+              if (a.adapt) {
+                double v;
+                if (hist_var) {
+                  v = cr_variance<REPLAY>(a, c, i);
+                } else {                          // cr_variance's running-moments branch on the preloaded row
+                  v = __dmul_rn(m2v[q], a.inv_mom);
+                  if (!(v > 0.0)) v = 1e-12 * 1e-12;
+                }
+                delta += cr_term(cur[q], pr, v);
+              }
+            } else {
+              pr = demc_prop(cur[q], S[q], n[q], gamma);
+            }
+            prv[q] = pr;
+          }
+        }
+        if (i0 + 3 < a.d) {
+          *reinterpret_cast<double2*>(out + i0) = make_double2(prv[0], prv[1]);
+          *reinterpret_cast<double2*>(out + i0 + 2) = make_double2(prv[2], prv[3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (i0 + q < a.d) out[i0 + q] = prv[q];
+        }
+        if (a.tr.prop)
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (i0 + q < a.d) a.tr.prop[(size_t)c * a.d + i0 + q] = prv[q];
+      }
+    }
+  } else if (valid) {
 #pragma unroll
     for (int t = 0; t < kMaxBlocksPerLane; ++t) {
       const int b = sub + t * LPC;
@@ -295,6 +398,45 @@ __global__ void __launch_bounds__(kThreads) accept_kernel(const PhaseArgs a) {
     // every array here is per-dimension independent, so the lanes of a chain take CONSECUTIVE
     // dimensions (whole 32-byte sectors per access) instead of the proposal stage's 4-dim blocks
     // (d = 1000 generation 3.34 -> 3.30 ms, gpurun_out/ab10 in profiles/r1_consumer_experiments.txt)
+    if (LPC == 32 && ((a.ld | a.d) & 1) == 0) {
+      // pairs of consecutive dimensions per lane (16-byte accesses), four pairs per lane loaded before the first
+      // store: the scalar loop below cannot overlap an iteration's loads with the previous one's stores (possible
+      // aliasing), which left this kernel at 35 % of the DRAM peak at d = 1000
+      // (profiles/r2/r2x_c5_propose_accept_ncu.txt).  Same per-dimension arithmetic.
+      const size_t ro = (size_t)(c - a.chain_lo) * a.ld;
+      const int np2 = a.d >> 1;
+      for (int k0 = sub; k0 < np2; k0 += 4 * LPC) {
+        double2 sv[4], mu[4], vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + u * LPC;
+          if (k < np2) {
+            sv[u] = *reinterpret_cast<const double2*>((acc ? pr : xc) + 2 * k);
+            if (a.mean) {
+              mu[u] = *reinterpret_cast<const double2*>(a.mean + ro + 2 * k);
+              vv[u] = *reinterpret_cast<const double2*>(a.m2 + ro + 2 * k);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + u * LPC;
+          if (k < np2) {
+            if (acc) {
+              *reinterpret_cast<double2*>(xc + 2 * k) = sv[u];
+              store_peers2(a, (size_t)c * a.ld + 2 * k, sv[u].x, sv[u].y);
+            }
+            if (a.mean) {
+              welford_update(sv[u].x, a.inv_n1, mu[u].x, vv[u].x);
+              welford_update(sv[u].y, a.inv_n1, mu[u].y, vv[u].y);
+              *reinterpret_cast<double2*>(a.mean + ro + 2 * k) = mu[u];
+              *reinterpret_cast<double2*>(a.m2 + ro + 2 * k) = vv[u];
+            }
+            if (a.hist_row) *reinterpret_cast<double2*>(a.hist_row + ro + 2 * k) = sv[u];
+          }
+        }
+      }
+    } else
 #pragma unroll 4
     for (int i = sub; i < a.d; i += LPC) {
       double s = xc[i];

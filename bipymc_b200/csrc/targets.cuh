@@ -61,13 +61,22 @@ __device__ __forceinline__ double gauss_finish(double c0, double maha, int log_o
 }
 
 // Line fit, examples/ex_para_fit.py:39-55.  data = x[M], y[M], yerr[M] (device).
-// The M terms are independent up to the (ordered) accumulation: unrolled so that five divisions / logarithms
-// are in flight per thread.  (Measured alternatives, profiles/r2/r2r_secondary.txt, r2s_*: four interleaved
-// partial sums 76 us per generation of 10^5 chains, this form 73 us, four LANES per chain 86 us.)
-__device__ __forceinline__ double linefit_lnl(const double* x, const double* y, const double* yerr,
-                                              int M, double m, double b, double lnf) {
-  if (!(-5.0 < m && m < 0.5 && 0.0 < b && b < 10.0 && -10.0 < lnf && lnf < 1.0)) return -INFINITY;
-  const double e2 = exp(__dmul_rn(2.0, lnf));
+//   lnL = -0.5 * sum_i [ r_i^2 * inv_i - log(inv_i) ],  inv_i = 1 / (yerr_i^2 + model_i^2 e^{2 lnf}),  r_i = y_i - model_i
+// Reference form, one IEEE division and one logarithm per data point (~120 instructions per term, 6 000 of the
+// 7 300 instructions of a whole line-fit chain-step: profiles/r2/r2x_fused_small_linefit_ncu_summary.txt).
+// Kept as the exact fallback and for the A/B (-DBPM_LINEFIT_GROUPED=0).  Measured alternatives of the same form
+// (profiles/r2/r2r_secondary.txt, r2s_*): four interleaved partial sums 76 us per generation of 10^5 chains,
+// this form 73 us, four LANES per chain 86 us.
+#ifndef BPM_LINEFIT_GROUPED
+#define BPM_LINEFIT_GROUPED 1
+#endif
+#if BPM_LINEFIT_GROUPED
+#define BPM_LINEFIT_EXACT_ATTR __noinline__          // the rare fallback stays out of the hot kernels' bodies
+#else
+#define BPM_LINEFIT_EXACT_ATTR __forceinline__
+#endif
+__device__ BPM_LINEFIT_EXACT_ATTR double linefit_lnl_per_term(const double* x, const double* y, const double* yerr,
+                                                    int M, double m, double b, double e2) {
   double s = 0.0;
 #pragma unroll 5
   for (int i = 0; i < M; ++i) {
@@ -78,6 +87,74 @@ __device__ __forceinline__ double linefit_lnl(const double* x, const double* y, 
     s += __dsub_rn(__dmul_rn(__dmul_rn(r, r), inv), log(inv));
   }
   return 0.0 + -0.5 * s;
+}
+
+// Default: five data points share ONE reciprocal and ONE logarithm.  With P = den_1 ... den_5 (den_i and r_i
+// computed exactly as above): inv_i = (1 / P) * prod_{j != i} den_j from prefix / suffix products, and
+// -sum log(inv_i) = log(P).  15 multiplications + 1 reciprocal + 1 logarithm per group instead of 5 divisions +
+// 5 logarithms.  inv_i carries ~3 ulp instead of 0.5, log(P) the same absolute error as one of the five
+// logarithms it replaces: |lnL - reference| / |lnL| stays ~1e-15 (the RNG-replay gate is 1e-12; tests compare
+// it with the oracle's per-term numpy form).  A group whose product leaves [1e-250, 1e250] sends the whole
+// evaluation to the exact form.
+__device__ __forceinline__ double fast_rcp_target(double v) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v));
+  double e = fma(-v, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-v, r, 1.0);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ double linefit_lnl(const double* x, const double* y, const double* yerr,
+                                              int M, double m, double b, double lnf) {
+  if (!(-5.0 < m && m < 0.5 && 0.0 < b && b < 10.0 && -10.0 < lnf && lnf < 1.0)) return -INFINITY;
+  const double e2 = exp(__dmul_rn(2.0, lnf));
+#if BPM_LINEFIT_GROUPED
+  double s = 0.0, lg = 0.0;
+  bool ok = true;
+  // one group of five points: adds sum r_i^2 inv_i to s, returns P = den_1 ... den_5
+  auto group5 = [&](int i) -> double {
+    double den[5], rr[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const double model = __dadd_rn(__dmul_rn(m, x[i + q]), b);
+      den[q] = __dadd_rn(__dmul_rn(yerr[i + q], yerr[i + q]), __dmul_rn(__dmul_rn(model, model), e2));
+      const double r = __dsub_rn(y[i + q], model);
+      rr[q] = __dmul_rn(r, r);
+    }
+    const double p12 = den[0] * den[1], p123 = p12 * den[2], p1234 = p123 * den[3], P = p1234 * den[4];
+    const double s45 = den[3] * den[4], s345 = den[2] * s45, s2345 = den[1] * s345;
+    ok = ok && P > 1e-120 && P < 1e120;
+    const double ip = fast_rcp_target(P);
+    s += rr[0] * (ip * s2345);
+    s += rr[1] * (ip * (den[0] * s345));
+    s += rr[2] * (ip * (p12 * s45));
+    s += rr[3] * (ip * (p123 * den[4]));
+    s += rr[4] * (ip * p1234);
+    return P;
+  };
+  int i = 0;
+#pragma unroll 1
+  for (; i + 10 <= M; i += 10) {               // two groups share one logarithm (|log10 P| < 240 for the pair)
+    const double Pa = group5(i);
+    const double Pb = group5(i + 5);
+    lg += log(Pa * Pb);
+  }
+  if (i + 5 <= M) {
+    lg += log(group5(i));
+    i += 5;
+  }
+  if (!ok) return linefit_lnl_per_term(x, y, yerr, M, m, b, e2);
+  for (; i < M; ++i) {                         // M % 5 leftover points, reference form
+    const double model = __dadd_rn(__dmul_rn(m, x[i]), b);
+    const double inv = __ddiv_rn(1.0, __dadd_rn(__dmul_rn(yerr[i], yerr[i]), __dmul_rn(__dmul_rn(model, model), e2)));
+    const double r = __dsub_rn(y[i], model);
+    s += __dmul_rn(__dmul_rn(r, r), inv);
+    lg -= log(inv);
+  }
+  return 0.0 + -0.5 * (s + lg);
+#else
+  return linefit_lnl_per_term(x, y, yerr, M, m, b, e2);
+#endif
 }
 
 // Exponential-relaxation fit, examples/ex_exp_fit.py:38-121.

@@ -42,11 +42,10 @@ def _torch():
 
 
 def _try_h5py():
-    try:
-        import h5py
-        return h5py if hasattr(h5py, "File") else None
-    except ImportError:
-        return None
+    """The HDF5 module checkpoints go through: h5py where it imports, else the package's own pure-Python
+    HDF5 writer / reader (bipymc_b200/h5lite.py, same File / create_dataset / attrs calls)."""
+    from . import h5lite
+    return h5lite.get_h5()
 
 
 def _npz_name(h5_file):
@@ -1342,8 +1341,8 @@ class DeMcMpi(object):
         """demc.py:198-215: one gzip dataset /chains/chain_id_<id> of shape (T, dim) per chain.
         Extension: the sampler state the reference loses on resume -- Philox seed, CR
         adaptation state -- is stored next to the chains (HDF5 attributes of /chains).
-        Without h5py (it is an optional dependency) or for a name ending in ".npz" the same
-        content goes to a numpy archive."""
+        Written through h5py where it imports and through bipymc_b200.h5lite (pure Python, same on-disk
+        format) where it does not.  For a name ending in ".npz" the same content goes to a numpy archive."""
         if not h5_file:
             h5_file = self.h5_file
         sc = self._super_chain(0)
@@ -1376,6 +1375,9 @@ class DeMcMpi(object):
         h5py = None if h5_file.endswith(".npz") else _try_h5py()
         if h5py is not None:
             with h5py.File(h5_file, "r") as h5f:
+                names = set(h5f["/chains"].keys())
+                if names != set("chain_id_" + str(int(c)) for c in range(self.n_chains)):
+                    raise RuntimeError        # another population's file (the .npz branch below rejects it too)
                 chains = [h5f["/chains/chain_id_" + str(int(c))][:] for c in range(self.n_chains)]
                 extra = dict((k, np.asarray(v)) for k, v in h5f["/chains"].attrs.items())
             k_gen = len(chains[0])

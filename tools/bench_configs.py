@@ -32,10 +32,21 @@ def run(name, make, N, d, bytes_per_step, gens=100, warm=20):
     v = N * gens / (ms * 1e-3)
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    # untimed extra pass with CUDA events around every launch: average launch time per kernel family
+    import ctypes as C
+    pg = max(4, gens // 5)
+    _lib.check(s._libh.bpm_profile(s._handle, 1))
+    s.run_mcmc(N * (pg + 1), _k_gen0=k + gens)
+    torch.cuda.synchronize()
+    ms_k, n_k = (C.c_double * 8)(), (C.c_int64 * 8)()
+    _lib.check(s._libh.bpm_profile_read(s._handle, ms_k, n_k))
+    _lib.check(s._libh.bpm_profile(s._handle, 0))
+    kinds = ["split", "propose", "likelihood", "accept", "fused_phase", "cr_reduce", "other6", "other7"]
+    kms = dict((kinds[i], {"avg_ms": ms_k[i] / n_k[i], "per_generation": n_k[i] / pg}) for i in range(8) if n_k[i])
     print(json.dumps({"config": name, "n_chains": N, "dim": d, "chain_steps_per_s": v, "ms_per_generation": ms / gens,
                       "algorithmic_bytes_per_chain_step": bytes_per_step,
                       "algorithmic_GBps": v * bytes_per_step / 1e9, "frac_of_hbm_peak": v * bytes_per_step / 1e9 / peak,
-                      "acceptance_fraction": s.acceptance_fraction}))
+                      "acceptance_fraction": s.acceptance_fraction, "launches_event_pass": kms}))
 
 
 def main():

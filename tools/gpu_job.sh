@@ -1,7 +1,7 @@
-# round 2, 8-GPU A/B of the sharded host entry: copy engines (default) vs the one-kernel form
+# round 2 (session 2), 1 GPU: block-wise 16-byte propose / accept kernels (large d), A/B of the register cap and against the previous commit
 set -x
 mkdir -p gpurun_out
-TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-timeout 600 $TR --nproc-per-node 8 --master-port 29561 bench.py --gpus 8 --steps 30 --warmup 5 --no-stationary > gpurun_out/r2w_bench_n8_dma.json 2> gpurun_out/r2w_bench_n8.err; tail -c 1000 gpurun_out/r2w_bench_n8_dma.json; tail -3 gpurun_out/r2w_bench_n8.err
-BIPYMC_B200_SHARD_IN_KERNEL=1 timeout 600 $TR --nproc-per-node 8 --master-port 29562 bench.py --gpus 8 --steps 30 --warmup 5 --no-stationary > gpurun_out/r2w_bench_n8_kernel.json 2>> gpurun_out/r2w_bench_n8.err; tail -c 1000 gpurun_out/r2w_bench_n8_kernel.json
-timeout 400 $TR --nproc-per-node 4 --master-port 29563 bench.py --gpus 4 --steps 30 --warmup 5 --no-stationary > gpurun_out/r2w_bench_n4_dma.json 2>> gpurun_out/r2w_bench_n8.err; tail -c 700 gpurun_out/r2w_bench_n4_dma.json
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2zb_pytest.log 2>&1; tail -4 gpurun_out/r2zb_pytest.log
+timeout 300 python tools/bench_configs.py c4 c3 demc100 c5shape > gpurun_out/r2zb_new.txt 2>&1; grep "^{" gpurun_out/r2zb_new.txt | cut -c1-250
+BIPYMC_B200_LIB=$PWD/build_ab/lib_p174.so timeout 300 python tools/bench_configs.py c5shape > gpurun_out/r2zb_p174.txt 2>&1; grep "^{" gpurun_out/r2zb_p174.txt | cut -c1-250
+BIPYMC_B200_LIB=$PWD/build_ab/lib_head.so timeout 300 python tools/bench_configs.py c3 c5shape > gpurun_out/r2zb_head.txt 2>&1; grep "^{" gpurun_out/r2zb_head.txt | cut -c1-250
