@@ -733,6 +733,7 @@ int bpm_set_target(bpm_handle h, int32_t target, const double* params, int64_t n
       h->bimodal.log_of_pdf = params[0]; h->bimodal.w1 = params[1]; h->bimodal.w2 = params[2];
       fill_mvn2(h->bimodal.g1, params + 3);
       fill_mvn2(h->bimodal.g2, params + 10);
+      h->bimodal.lw1 = log(h->bimodal.w1); h->bimodal.lw2 = log(h->bimodal.w2);
       break;
     case BPM_TARGET_GAUSS: {
       // [log_of_pdf, c0, r, mu[d], W[d][r]]

@@ -1643,11 +1643,14 @@ inline int try_fused_phase(const TargetView& tv, const PhaseArgs& a, cudaStream_
       // default: TMA-staged gathers (v4) whenever its shared-memory layout fits; variant 5 = v3 (register gathers)
       if (variant != 5 && fused_v4_fits(a.d, a.ld, tv.r, npair)) {
         const size_t sm4 = v4_layout(a.d, tv.r, npair).total;
+        const bool d1 = a.algo == BPM_ALGO_DEMC;
         if (tv.mu_is_zero)
           rc = d3 ? launch_fused_v4<REPLAY, false, 3>(a, g, grid, sm4, s)
+             : d1 ? launch_fused_v4<REPLAY, false, 1>(a, g, grid, sm4, s)
                   : launch_fused_v4<REPLAY, false, 0>(a, g, grid, sm4, s);
         else
           rc = d3 ? launch_fused_v4<REPLAY, true, 3>(a, g, grid, sm4, s)
+             : d1 ? launch_fused_v4<REPLAY, true, 1>(a, g, grid, sm4, s)
                   : launch_fused_v4<REPLAY, true, 0>(a, g, grid, sm4, s);
         if (rc) return 1;
         if (cudaGetLastError() != cudaSuccess) return 1;

@@ -86,8 +86,10 @@ __global__ void __launch_bounds__(kV3Threads, 1)
 fused_gauss_v4_kernel(const PhaseArgs a, const GaussArgs g) {
   extern __shared__ __align__(128) unsigned char smem4[];
   const int d = a.d, pld = dmma_pld(d), NT = dmma_ntiles(g.r);
-  const bool dream = NPAIR == 3 ? true : a.algo == BPM_ALGO_DREAM;
-  const int npair = NPAIR == 3 ? 3 : (dream ? a.del_pairs : 1);
+  // NPAIR = 3: DREAM with three pairs, NPAIR = 1: DE-MC (one pair, no crossover / CR statistics), both resolved at
+  // compile time; NPAIR = 0: algorithm and pair count read from the arguments
+  const bool dream = NPAIR == 3 ? true : (NPAIR == 1 ? false : a.algo == BPM_ALGO_DREAM);
+  const int npair = NPAIR == 3 ? 3 : (NPAIR == 1 ? 1 : (dream ? a.del_pairs : 1));
   const V4Layout L4 = v4_layout(d, g.r, npair);
   GaussTables tb;
   tb.Ws = reinterpret_cast<double*>(smem4 + L4.wf);

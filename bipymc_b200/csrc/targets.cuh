@@ -41,13 +41,14 @@ __device__ __forceinline__ double banana_lnl(const BananaParams& p, double y1, d
 struct BimodalParams {
   double log_of_pdf, w1, w2;
   Mvn2 g1, g2;
+  double lw1, lw2;            // log(w1), log(w2): taken once on the host (bpm_set_target), not once per chain-step
 };
 // dblgauss_rv.py:26-32
 __device__ __forceinline__ double bimodal_lnl(const BimodalParams& p, double y1, double y2) {
   double l1 = mvn2_logpdf(p.g1, y1, y2), l2 = mvn2_logpdf(p.g2, y1, y2);
   if (p.log_of_pdf != 0.0)
     return log(__dadd_rn(__dmul_rn(p.w1, exp(l1)), __dmul_rn(p.w2, exp(l2))));
-  double a = l1 + log(p.w1), b = l2 + log(p.w2);
+  double a = l1 + p.lw1, b = l2 + p.lw2;
   double m = fmax(a, b);
   if (!(m > -INFINITY)) return -INFINITY;
   return m + log(exp(a - m) + exp(b - m));

@@ -378,6 +378,17 @@ def test_checkpoint_roundtrip_resumes_the_same_chains(tmp_path):
     a = DreamMpi(tgt.ln_like, [0.0, 0.0], seed=31, **kw)
     a.run_mcmc(24 * 11)
     a.save_state(f)
+    # the file IS the reference's HDF5 layout (chain.py:59-93): /chains/chain_id_<id>, gzip, (T, dim) float64 --
+    # written by h5py where it imports, by bipymc_b200.h5lite (same on-disk format) where it does not
+    from bipymc_b200 import h5lite
+    assert open(f, "rb").read(8) == b"\x89HDF\r\n\x1a\n"
+    with h5lite.File(f, "r") as h5f:
+        assert h5f["/chains"].keys() == sorted("chain_id_%d" % i for i in range(24))
+        for i in (0, 7, 23):
+            ds = h5f["/chains/chain_id_%d" % i]
+            assert ds.shape == (11, 2) and ds.dtype == np.float64 and ds.compression == "gzip"
+            np.testing.assert_array_equal(ds[:], a.am_chains[i].chain)
+        assert int(h5f["/chains"].attrs["b200_seed"]) == 31
     a.run_mcmc(24 * 6)
     np.random.seed(99)
     b = DreamMpi(tgt.ln_like, [0.0, 0.0], warm_start=True, h5_file=f, **kw)      # no seed given

@@ -25,7 +25,13 @@ def main():
                  n_cr_gen=1, burnin_gen=100)
     s.run_mcmc(160 * 3)
     print("gauss1000 ok, acceptance %.3f" % s.acceptance_fraction, flush=True)
+    s = DeMcMpi(targets.Gauss_100D().ln_like, np.zeros(100), n_chains=300, seed=3, varepsilon=0.5)
+    s.run_mcmc(300 * 5)
+    print("gauss100 DE-MC (compile-time one-pair v4 kernel) ok, acceptance %.3f" % s.acceptance_fraction, flush=True)
     s = DeMcMpi(targets.Banana_2D().ln_like, [0.0, 0.0], n_chains=500, seed=3, varepsilon=0.5)
+    s.run_mcmc(500 * 6)
+    s = DreamMpi(targets.LineFit().ln_like, [-0.8, 4.5, 0.2], n_chains=500, seed=3, varepsilon=1e-2, n_cr_gen=1,
+                 burnin_gen=100)
     s.run_mcmc(500 * 6)
     s = DreamMpi(targets.BimodeGauss_2D().ln_like, [0.0, 0.0], n_chains=500, seed=3, varepsilon=0.5, n_cr_gen=1,
                  burnin_gen=100, outlier_gen=2)
