@@ -116,6 +116,7 @@ struct bpm_engine {
   bpm::BananaParams banana;
   bpm::BimodalParams bimodal;
   double* tparams = nullptr;  // device copy of gauss / linefit parameters
+  double* wfrag = nullptr;    // Gaussian target: W in DMMA fragment order (w_fragment_kernel)
   int64_t n_tparams = 0;
   int gauss_r = 0, gauss_logpdf_flag = 0, gauss_mu_zero = 0;
   double gauss_c0 = 0.0;
@@ -192,7 +193,7 @@ struct bpm_engine {
     for (auto e : ev_chunk) if (e) cudaEventDestroy(e);
     cudaFree(perm); cudaFree(flip); cudaFree(prop); cudaFree(lnl_prop); cudaFree(cr_delta);
     cudaFree(cr_pick); cudaFree(p_cr); cudaFree(cr_dm); cudaFree(cr_cnt); cudaFree(cr_part); cudaFree(cr_block);
-    cudaFree(counters); cudaFree(nan_flag); cudaFree(tparams); cudaFree(hX); cudaFree(hL); cudaFree(hMean); cudaFree(hM2);
+    cudaFree(counters); cudaFree(nan_flag); cudaFree(tparams); cudaFree(wfrag); cudaFree(hX); cudaFree(hL); cudaFree(hMean); cudaFree(hM2);
     cudaFree(h_accept); cudaFree(h_changed); cudaFree(h_nrows);
     cudaFree(omega_sum); cudaFree(omega_buf); cudaFree(diag_out); cudaFree(diag_i); cudaFree(sort_tmp);
     cudaFree(rh_mean); cudaFree(rh_m2); cudaFree(rh_out); cudaFree(sync_err); cudaFree(cov_acc);
@@ -292,6 +293,10 @@ struct bpm_engine {
     if (no_peer_stores) a.n_peers = 0;
     a.n_acc = counters; a.n_rej = counters + 1; a.nan_flag = nan_flag;
     a.rng = bpm::make_rng(cfg.seed, (uint64_t)st->hist_len);
+    if (!serial()) {          // what begin() makes the device flag: the replayed coin, or the native one
+      a.flip_known = 1;
+      a.flip_val = rp ? (rp->flip ? 1 : 0) : host_flip(a.rng);
+    }
     if (fly && !rp && !serial()) fill_fly(a);
     if (rp) a.rp = *rp;
     if (tr) a.tr = *tr;
@@ -351,11 +356,15 @@ struct bpm_engine {
 
   // fly mode: the generation's flip and permutation key, evaluated on the host (demc.py:81-86; the same
   // Philox calls and the same IEEE arithmetic split_native_kernel makes on the device)
+  // the generation's flip coin on the host: the same Philox call and IEEE arithmetic as split_native_kernel
+  int host_flip(const bpm::RngCtx& rng) const {
+    const bpm::Philox4 q = bpm::draw4(rng, 0xFFFFFFFFu, bpm::RNG_GEN, 0);
+    const double thr = cfg.flip / (cfg.flip + (1.0 - cfg.flip));
+    return bpm::u53(q.x, q.y) < thr ? 1 : 0;
+  }
   void fill_fly(bpm::PhaseArgs& a) const {
     a.fly = 1;
-    const bpm::Philox4 q = bpm::draw4(a.rng, 0xFFFFFFFFu, bpm::RNG_GEN, 0);
-    const double thr = cfg.flip / (cfg.flip + (1.0 - cfg.flip));
-    a.flip_val = bpm::u53(q.x, q.y) < thr ? 1 : 0;
+    a.flip_val = host_flip(a.rng);
     a.fly_shuffle = cfg.shuffle ? 1 : 0;
     if (cfg.shuffle) a.fk = bpm::make_feistel(a.rng, (uint32_t)cfg.n_chains);
   }
@@ -571,6 +580,7 @@ struct bpm_engine {
     tv.bimodal = bimodal;
     tv.mu = tparams;
     tv.W = tparams ? tparams + cfg.dim : nullptr;
+    tv.Wf = target == BPM_TARGET_GAUSS ? wfrag : nullptr;
     tv.r = gauss_r;
     tv.c0 = gauss_c0;
     tv.log_of_pdf = gauss_logpdf_flag;
@@ -746,6 +756,15 @@ int bpm_set_target(bpm_handle h, int32_t target, const double* params, int64_t n
       cudaFree(h->tparams); h->tparams = nullptr;
       CU_TRY(cudaMalloc(&h->tparams, sizeof(double) * (n - 3)));
       CU_TRY(cudaMemcpy(h->tparams, params + 3, sizeof(double) * (n - 3), cudaMemcpyHostToDevice));
+      // W once more in DMMA fragment order, for the fused kernels' single bulk copy (kernels_fused.cuh)
+      cudaFree(h->wfrag); h->wfrag = nullptr;
+      if ((d % 4) == 0 && bpm::gauss_rows_supported(d, r)) {
+        const size_t nf = (size_t)(d >> 2) * bpm::dmma_ntiles(r) * 32;
+        CU_TRY(cudaMalloc(&h->wfrag, sizeof(double) * nf));
+        bpm::w_fragment_kernel<<<cdiv((int64_t)nf, 256), 256>>>(h->wfrag, h->tparams + d, d, r);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaDeviceSynchronize());
+      }
       break;
     }
     case BPM_TARGET_LINEFIT: {

@@ -30,6 +30,7 @@ struct TargetView {
   BimodalParams bimodal;
   const double* mu;
   const double* W;
+  const double* Wf;   // see GaussArgs
   int r;
   double c0;
   int log_of_pdf;
@@ -171,6 +172,7 @@ inline int launch_gauss_rows(const double* X, int n, int ld, int d, int r, const
 struct GaussArgs {
   const double* mu;
   const double* W;
+  const double* Wf;   // W in DMMA fragment order (w_fragment_kernel, built once per bpm_set_target), or nullptr
   int r;
   double c0;
   int log_of_pdf;
@@ -726,6 +728,19 @@ __device__ __forceinline__ void load_W_fragments(double* Wf, double* mus, const 
     Wf[idx] = j < r ? W[(size_t)k * r + j] : 0.0;
   }
   for (int k = tid; k < d; k += nthreads) mus[k] = mu[k];
+}
+
+// The same layout written ONCE per target into global memory (bpm_set_target): the v4 kernel then brings W in
+// with a single TMA bulk copy instead of 40 scattered loads + index divisions per consumer thread per launch.
+__global__ void w_fragment_kernel(double* __restrict__ Wf, const double* __restrict__ W, int d, int r) {
+  const int NT = dmma_ntiles(r);
+  const int total = (d >> 2) * NT * 32;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int lane = idx & 31, t = idx >> 5;
+    const int k4 = t / NT, nt = t - k4 * NT;
+    const int k = 4 * k4 + (lane & 3), j = 8 * nt + (lane >> 2);
+    Wf[idx] = j < r ? W[(size_t)k * r + j] : 0.0;
+  }
 }
 
 // maha = |(P[row] - mu) . W|^2 for one m-tile (8 rows) per warp, no cross-warp hand-off: the four
@@ -1597,7 +1612,7 @@ inline int try_fused_phase(const TargetView& tv, const PhaseArgs& a, cudaStream_
   *done = 0;
   if (tv.target == BPM_TARGET_GAUSS && gauss_rows_supported(a.d, tv.r) && (a.ld % 2) == 0) {
     GaussArgs g;
-    g.mu = tv.mu; g.W = tv.W; g.r = tv.r; g.c0 = tv.c0; g.log_of_pdf = tv.log_of_pdf;
+    g.mu = tv.mu; g.W = tv.W; g.Wf = tv.Wf; g.r = tv.r; g.c0 = tv.c0; g.log_of_pdf = tv.log_of_pdf;
     const size_t sm = fused_gauss_smem(a.d);
     const int n_tiles = (a.nA + kTileRows - 1) / kTileRows;
     cudaError_t e;

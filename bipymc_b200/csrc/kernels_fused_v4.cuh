@@ -63,7 +63,7 @@ __host__ __device__ inline V4Layout v4_layout(int d, int r, int npair) {
   L.land_rows = 2 * npair;
   L.land = take(sizeof(double) * (size_t)kV3ProdWarps * L.land_rows * d);
   L.scratch = take(2 * ((sizeof(TileScratch) + 127) & ~(size_t)127));
-  L.bars = take(sizeof(uint64_t) * (kV3ProdWarps + 2 * kV3ConsWarps));
+  L.bars = take(sizeof(uint64_t) * (kV3ProdWarps + 2 * kV3ConsWarps));     // LAND[16], DONEm[8], WREADY, 7 spare
   L.total = o;
   return L;
 }
@@ -104,15 +104,27 @@ fused_gauss_v4_kernel(const PhaseArgs a, const GaussArgs g) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem4 + L4.bars);
   uint64_t* LAND = bars;                               // [16] partner rows of the warp's chain have landed
   uint64_t* DONEm = bars + kV3ProdWarps;               // [8]  consumer cw is done with its m-tile
+  uint64_t* WREADY = DONEm + kV3ConsWarps;             // W fragments + mu have landed (TMA, g.Wf != nullptr)
   // "all 8 rows of m-tile cw are in the tile" is named barrier kV4BarFull0 + cw: 8 producing warps arrive,
   // the consumer warp syncs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  fill_tables_v3(a, g, tb, threadIdx.x, kV3Threads);
   if (threadIdx.x == 0) {
     for (int w = 0; w < kV3ProdWarps; ++w) mbar_init(LAND + w, 1);
     for (int w = 0; w < kV3ConsWarps; ++w) mbar_init(DONEm + w, 1);
+    mbar_init(WREADY, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (g.Wf) {
+      // W (83 KB at d = r = 100, fragment order prepared by w_fragment_kernel) and mu arrive as two bulk copies
+      // issued before anything else happens in the CTA; the consumers wait for them on WREADY.  The in-kernel
+      // rearrangement this replaces (load_W_fragments) held the consumer warps for the first ~20 us of a launch:
+      // 6.3 % of all warp samples on its one load line, profiles/r2/r2zd_v4_source_lines.txt.
+      const uint32_t wbytes = (uint32_t)(sizeof(double) * (size_t)(d >> 2) * NT * 32), mbytes = (uint32_t)(d * 8);
+      mbar_expect_tx(WREADY, wbytes + mbytes);
+      bulk_g2s(tb.Ws, g.Wf, wbytes, WREADY);
+      bulk_g2s(tb.mus, g.mu, mbytes, WREADY);
+    }
   }
+  fill_tables_v3(a, g, tb, threadIdx.x, kV3Threads);
   __syncthreads();
   const PhaseLists L = phase_lists(a);
   const int per_cta = (L.n_self + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -123,8 +135,12 @@ fused_gauss_v4_kernel(const PhaseArgs a, const GaussArgs g) {
   if (warp < kV3ConsWarps) {
     // ------------------------------ consumers ------------------------------------------
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    load_W_fragments(tb.Ws, tb.mus, g.W, g.mu, d, g.r, threadIdx.x, kV3ConsThreads);
-    nbar_sync(BAR_CONS, kV3ConsThreads);
+    if (g.Wf) {
+      mbar_wait(WREADY, 0);
+    } else {
+      load_W_fragments(tb.Ws, tb.mus, g.W, g.mu, d, g.r, threadIdx.x, kV3ConsThreads);
+      nbar_sync(BAR_CONS, kV3ConsThreads);
+    }
     unsigned n_acc = 0, n_rej = 0;
     const bool decider = (lane & 3) == 0;
     const int my_row = 8 * warp + (lane >> 2);

@@ -680,9 +680,13 @@ __device__ __forceinline__ void cr_finish(const double* __restrict__ block_part,
       for (int b = 0; b < nb_here; ++b) w += stage[b * nv + threadIdx.x];
     __syncthreads();
   }
-  if ((int)threadIdx.x < nv) part[threadIdx.x] = w;
+  __shared__ double part_s[2 * BPM_MAX_CR];        // cr_apply reads the sums from here, not back from global memory
+  if ((int)threadIdx.x < nv) {
+    part[threadIdx.x] = w;
+    part_s[threadIdx.x] = w;
+  }
   __syncthreads();
-  if (threadIdx.x == 0 && apply) cr_apply(part, n_cr, dm, cnt, p_cr);
+  if (threadIdx.x == 0 && apply) cr_apply(part_s, n_cr, dm, cnt, p_cr);
 }
 
 __global__ void __launch_bounds__(256) cr_update_kernel(const double* __restrict__ cr_delta,

@@ -49,6 +49,9 @@ struct PhaseArgs {
   // phase lists: perm[0:nA) is half "a", perm[nA:N) half "b" before the flip swap
   const int32_t* perm;
   const int32_t* flip;  // device flag (demc.py:81,98-100)
+  // The flag is a function of (seed, generation) -- or the replayed value -- so the host evaluates it too and
+  // passes it by value: the kernels' first dependent global load (flag -> list -> chain id -> rows) goes away.
+  int32_t flip_known;   // flip_val below is valid
   // sharded handles: this rank's chains of each half, compacted in list order into
   // loc_list[0 : loc_cnt[0]) and loc_list[nA : nA + loc_cnt[1]); nullptr when the rank owns all chains
   const int32_t* loc_list;
@@ -130,7 +133,7 @@ __device__ __forceinline__ int pool_chain(const PhaseLists& L, int r, int c) {
   return L.skip_self ? r + (r >= c ? 1 : 0) : L.pool[r];
 }
 __device__ __forceinline__ PhaseLists phase_lists(const PhaseArgs& a) {
-  const int32_t first = (a.phase ^ (*a.flip != 0)) == 0;  // true: self is perm[0:nA)
+  const int32_t first = (a.phase ^ (a.flip_known ? a.flip_val : (*a.flip != 0))) == 0;  // true: self is perm[0:nA)
   PhaseLists L;
   L.skip_self = 0;
   if (a.serial) {   // samplers.py:275-277: valid_pool_ids = np.delete(range(n_chains), i)
@@ -145,7 +148,8 @@ __device__ __forceinline__ PhaseLists phase_lists(const PhaseArgs& a) {
   }
   if (a.loc_cnt) {   // only the local chains of the half, densely packed
     L.self = a.loc_list + (first ? 0 : a.nA);
-    L.n_self = a.loc_cnt[first ? 0 : 1];
+    // (a handle that owns every chain packs whole halves: the counts are known without the load)
+    L.n_self = (a.chain_lo == 0 && a.chain_hi == a.N) ? (first ? a.nA : a.N - a.nA) : a.loc_cnt[first ? 0 : 1];
   }
   return L;
 }
