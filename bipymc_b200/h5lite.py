@@ -505,6 +505,8 @@ class File(Group):
             cshape = tuple(int(c) for c in chunks)
             if len(cshape) != len(shape) or any(c < 1 for c in cshape):
                 raise ValueError("chunks must match the dataset's rank")
+            if any(c > n for c, n in zip(cshape, shape) if n > 0):
+                raise ValueError("Chunk shape must not be greater than data shape in any dimension")
         rank = len(shape)
         grid = [(-(-n // c)) for n, c in zip(shape, cshape)]
         children, keys = [], []

@@ -289,3 +289,37 @@ def test_mcmc_chain_h5_round_trip(tmp_path, monkeypatch):
             assert np.array_equal(e.chain, ch.chain)
     with pytest.raises(RuntimeError):
         c.write_chain_h5(12345)
+
+
+def test_round_trip_property(tmp_path):
+    """Random shapes, dtypes, chunk shapes and filters survive a write / read cycle, alone and after an append."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    counter = [0]
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(st.lists(st.integers(1, 9), min_size=1, max_size=3), st.sampled_from(["<f8", "<f4", "<i8", "<i4", "<u2", "|u1", ">f8", ">i4"]),
+           st.sampled_from([None, "gzip"]), st.booleans(), st.integers(0, 2 ** 31 - 1), st.data())
+    def run(shape, dtype, compression, shuffle, seed, data):
+        counter[0] += 1
+        f = str(tmp_path / ("p%d.h5" % counter[0]))
+        rng = np.random.RandomState(seed)
+        a = (rng.randn(*shape) * 100).astype(dtype)
+        chunks = None
+        if compression or shuffle:
+            chunks = tuple(data.draw(st.integers(1, n)) for n in shape) if data.draw(st.booleans()) else None
+        with h5.File(f, "w") as h:
+            h.create_dataset("/g/sub/a", data=a, compression=compression, shuffle=shuffle, chunks=chunks)
+            h["/g"].attrs["v"] = a.ravel()[:3]
+        with h5.File(f, "a") as h:
+            h.create_dataset("/g/b", data=a.T.copy(), compression=compression)
+        with h5.File(f, "r") as h:
+            got = h["/g/sub/a"]
+            assert got.shape == a.shape and got.dtype == a.dtype
+            assert np.array_equal(got[...], a) and np.array_equal(h["/g/b"][...], a.T)
+            assert np.array_equal(h["/g"].attrs["v"], a.ravel()[:3])
+            assert (got.compression == "gzip") == (compression == "gzip") and got.shuffle == bool(shuffle)
+
+    run()
+    with h5.File(str(tmp_path / "c.h5"), "w") as h:
+        with pytest.raises(ValueError):
+            h.create_dataset("x", data=np.zeros((4, 2)), compression="gzip", chunks=(8, 2))
