@@ -133,8 +133,8 @@ def test_bipymc_b200_warm_starts_from_a_reference_checkpoint_and_the_reference_f
     for i in range(12):
         assert mine.am_chains[i].chain_len == T
         np.testing.assert_array_equal(mine.am_chains[i].chain, s.am_chains[i].chain)
-    mine.run_mcmc(12 * 4, _k_gen0=T - 1)                     # and it continues from there
-    assert mine.am_chains[0].chain_len == T + 4
+    mine.run_mcmc(12 * 4, _k_gen0=T - 1)                     # and it continues from there: 4 * N samples = 3 generations
+    assert mine.am_chains[0].chain_len == T + 3
     g = str(tmp_path / "mine_ckpt.h5")
     mine.save_state(g)
     r = _ref_sampler(ref, steps=0, warm_start=True, h5_file=g, dim=2)
