@@ -1,4 +1,4 @@
-# round 2 (session 2), 1 GPU: the full GPU suite once more after the fix of the interop test's generation count
+# round 2 (session 2), 1 GPU: ncu --set full of the rewritten split-path kernels at d = 1000 (one report: the merge-back limit is 64 MiB)
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2zl_pytest.log 2>&1; tail -4 gpurun_out/r2zl_pytest.log
+timeout 200 ncu --set full --clock-control none -k regex:"propose_kernel|accept_kernel" -s 20 -c 2 -o gpurun_out/prof_r2zm_c5 -f python tools/bench_configs.py c5shape > gpurun_out/r2zm_ncu_c5.log 2>&1; tail -n 2 gpurun_out/r2zm_ncu_c5.log; ls -la gpurun_out
