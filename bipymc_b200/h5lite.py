@@ -71,7 +71,7 @@ def _encode_datatype(dt):
 
 def _decode_datatype(b):
     cls, ver = b[0] & 0x0F, b[0] >> 4
-    f0, f1 = b[1], b[2]
+    f0 = b[1]
     size = struct.unpack_from("<I", b, 4)[0]
     order = ">" if (f0 & 1) else "<"
     if cls == 0:
@@ -90,7 +90,7 @@ def _encode_dataspace(shape):
 
 
 def _decode_dataspace(b):
-    ver, rank, flags = b[0], b[1], b[2]
+    ver, rank = b[0], b[1]
     if ver == 1:
         off = 8
     elif ver == 2:

@@ -3,7 +3,6 @@
 format is pinned here structure by structure against the HDF5 File Format Specification (version 1.1
 structures, what h5py writes with libver="earliest"); tests/test_hdf5_optional.py cross-reads with h5py
 wherever it imports."""
-import os
 import struct
 import zlib
 
@@ -233,7 +232,7 @@ def test_reader_follows_continuation_blocks_and_v2_dataspace(tmp_path):
     with h5.File(f, "w") as h:
         h.create_dataset("d", data=np.arange(4.0))
     raw = bytearray(open(f, "rb").read())
-    name_off, root_oh = struct.unpack_from("<QQ", raw, 56)
+    root_oh = struct.unpack_from("<Q", raw, 64)[0]
     # a second block at the end of the file: a NIL message, then a version-3 attribute "k" = int32 9
     dt = bytes.fromhex("1008000004000000" "00002000")
     attr = struct.pack("<BBHHHB", 3, 0, 2, len(dt), 4, 0) + b"k\0" + dt + bytes([2, 0, 0, 1]) + struct.pack("<i", 9)
@@ -242,7 +241,6 @@ def test_reader_follows_continuation_blocks_and_v2_dataspace(tmp_path):
     block_at = len(raw)
     raw += block
     # rewrite the root header: symbol-table message + continuation message, 4 messages in total
-    ver, _, nmsg, refs, size = struct.unpack_from("<BBHII", raw, root_oh)
     st = bytes(raw[root_oh + 16:root_oh + 16 + 24])
     cont = struct.pack("<HHB3x", 0x10, 16, 0) + struct.pack("<QQ", block_at, len(block))
     new_oh = len(raw)
